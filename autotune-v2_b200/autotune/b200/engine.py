@@ -1,0 +1,136 @@
+"""Batched entry points: whole Monte-Carlo jobs (many independent optimiser repetitions) as single kernel pipelines.
+
+This replaces the reference's repetition loop (experiments/run_simulation.py:147-157) - the reference has no
+equivalent call; everything it needs is described by the same objects the reference's loop builds each iteration
+(problem, scheduler, optimiser).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import ops
+
+FUNC_DOMAINS = {  # benchmarks/opt_function_problem.py:15-46
+    'egg': (-512, 512, -512, 512), 'branin': (-5, 10, 1, 15), 'camel': (-3, 3, -2, 2),
+    'wave': (-5.12, 5.12, -5.12, 5.12), 'rastrigin': (-5.12, 5.12, -5.12, 5.12)}
+
+
+def _family_tuple(f):
+    """Accept ShapeFamily / EvaluatorParams (arm first) or a bare 6-tuple (ml, nec, up, smooth, start, end)."""
+    f = tuple(f)
+    if len(f) >= 7:
+        f = f[1:7]
+    if len(f) == 3:
+        f = f + (False, 0, 200)
+    if len(f) != 6:
+        raise ValueError(f'cannot interpret shape family {f!r}')
+    return (float(f[0]), float(f[1]), float(f[2]), bool(f[3]), float(f[4]), float(f[5]))
+
+
+class HyperbandSimSpec:
+    """Everything that defines a Hyperband-on-simulation Monte-Carlo job except the repetition count and the seed."""
+
+    def __init__(self, func_name, shape_families, max_iter=81, eta=3, init_noise=0.0, scheduler='uniform',
+                 min_or_max='min'):
+        if func_name not in nat.FUNC_IDS:
+            raise KeyError(func_name)
+        if scheduler not in ('uniform', 'round-robin'):
+            raise ValueError(f'unknown scheduler {scheduler!r}')
+        if min_or_max in (min, max):
+            min_or_max = min_or_max.__name__
+        if min_or_max not in ('min', 'max'):
+            raise ValueError(f"optimization must be a built in function: min or max, instead {min_or_max} was supplied")
+        self.func_name, self.R, self.eta = func_name, int(max_iter), int(eta)
+        self.families = [_family_tuple(f) for f in shape_families]
+        if not 1 <= len(self.families) <= nat.MAX_FAMILIES:
+            raise ValueError(f'between 1 and {nat.MAX_FAMILIES} shape families are supported')
+        self.init_noise, self.scheduler, self.min_or_max = float(init_noise), scheduler, min_or_max
+        self.plan = nat.bracket_plan(self.R, self.eta)
+        cfg = nat.SimConfig()
+        cfg.func, cfg.n_families = nat.FUNC_IDS[func_name], len(self.families)
+        cfg.scheduler = nat.SCHED_UNIFORM if scheduler == 'uniform' else nat.SCHED_ROUND_ROBIN
+        cfg.descending = int(min_or_max == 'max')
+        cfg.x_min, cfg.x_max, cfg.y_min, cfg.y_max = FUNC_DOMAINS[func_name]
+        cfg.init_noise = self.init_noise
+        for i, (ml, nec, up, sm, s0, s1) in enumerate(self.families):
+            cfg.fam[i] = nat.Family(ml, nec, up, s0, s1, int(sm), 0)
+        self.cfg = cfg
+        if any(f[3] for f in self.families) and nat.lib.at2_savgol_window(self.R) > self.R:
+            # the reference fails the same way, inside scipy, on the first smooth read-out
+            raise ValueError("If mode is 'interp', window_length must be less than or equal to the size of x.")
+        self.plan_bytes, self.cfg_bytes = ops.struct_tensor(self.plan), ops.struct_tensor(self.cfg)
+        self._tables = {}
+
+    # ---- derived sizes ----
+    @property
+    def n_arms(self):
+        return self.plan.n_arms
+
+    @property
+    def n_rounds(self):
+        return self.plan.n_rounds
+
+    @property
+    def checkpoints(self):
+        return [self.plan.ckpt_time[c] for c in range(self.plan.n_ckpts)]
+
+    @property
+    def arm_epochs_per_repetition(self):
+        """Necessary arm-epochs: every arm's R-1 steps."""
+        return self.plan.n_arms * (self.R - 1)
+
+    def rounds(self):
+        p = self.plan
+        return [dict(bracket=b, n_eval=p.round_n_eval[r], keep=min(p.round_keep[r], p.round_n_eval[r]),
+                     time=p.round_time[r], ckpt=p.round_ckpt[r])
+                for b in range(p.n_brackets) for r in range(p.bracket_first_round[b], p.bracket_first_round[b + 1])]
+
+    def tables(self, device, dtype=torch.float32):
+        """Constant tables on `device` (built once per (device, dtype) by at2_hb_tables_build, pinned H2D copy)."""
+        device = torch.device(device)
+        key = (str(device), dtype)
+        if key not in self._tables:
+            is64 = int(dtype == torch.float64)
+            nbytes = nat.lib.at2_hb_tables_bytes(C.byref(self.plan), C.byref(self.cfg), is64)
+            if nbytes < 0:
+                raise nat.At2Error(nat.lib.at2_last_error().decode())
+            host = torch.empty(nbytes // (8 if is64 else 4), dtype=dtype)
+            nat.check(nat.lib.at2_hb_tables_build(C.byref(self.plan), C.byref(self.cfg), is64, host.data_ptr()))
+            self._tables[key] = host.to(device)
+        return self._tables[key]
+
+
+def _cuda_device(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError('no CUDA device: the B200 path has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False):
+    """`n_reps` independent Hyperband repetitions on the simulation problem of `spec`, one fused kernel launch.
+
+    Returns a dict of device tensors: ofe[n], ofe_arm[n], best_xy[n,2] and, with details=True, round_best[n,rounds],
+    round_best_arm, survivors[n, n_surv], ckpt_loss[n, arms, ckpts].  Repetition i is keyed by (seed, rep_offset+i).
+    """
+    device = _cuda_device(device)
+    outs = torch.ops.at2.hb_sim_f32(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes, int(n_reps),
+                                    int(rep_offset), int(seed), bool(details))
+    return dict(zip(ops.HB_OUTPUT_NAMES, outs))
+
+
+def run_hyperband_predrawn(spec, f1, fn, family, gamma, xy=None, device=None, dtype=torch.float64):
+    """Parity entry: recurrence + read-out + halving on pre-drawn per-arm inputs (host arrays or tensors).
+
+    f1, fn: [n, A]; family: [n, A] int; gamma: [n, A, R-1]; xy: [n, A, 2] (echoed into best_xy only)."""
+    device = _cuda_device(device)
+
+    def dev(a, dt):
+        return torch.as_tensor(np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a).to(device=device, dtype=dt).contiguous()
+    f1, fn, gamma = dev(f1, dtype), dev(fn, dtype), dev(gamma, dtype)
+    family = dev(family, torch.int32)
+    xy = dev(xy, dtype) if xy is not None else torch.zeros(*f1.shape, 2, device=device, dtype=dtype)
+    outs = torch.ops.at2.hb_sim_predrawn(spec.tables(device, dtype), spec.plan_bytes, spec.cfg_bytes, f1, fn, family,
+                                         gamma, xy)
+    return dict(zip(ops.HB_OUTPUT_NAMES, outs))

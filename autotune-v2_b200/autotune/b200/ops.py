@@ -1,0 +1,104 @@
+"""PyTorch custom ops (`torch.ops.at2.*`) over the C ABI of libat2_b200.
+
+Each op allocates its outputs as torch tensors on the inputs' CUDA device and enqueues the library call on torch's
+current stream of that device, so the ops compose with torch streams/events like any other CUDA op.  Struct arguments
+(`at2_plan`, `at2_sim_config`) travel as CPU uint8 tensors holding the struct bytes.
+"""
+import ctypes as C
+from typing import List
+
+import torch
+
+from . import _native as nat
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f'{what} must live on a CUDA device (the B200 path has no CPU fallback); got {t.device}')
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _struct(cls, t: torch.Tensor):
+    if t.device.type != 'cpu' or t.dtype != torch.uint8 or t.numel() != C.sizeof(cls):
+        raise RuntimeError(f'expected a CPU uint8 tensor of {C.sizeof(cls)} bytes for {cls.__name__}')
+    return cls.from_buffer_copy(t.numpy().tobytes())
+
+
+def struct_tensor(obj) -> torch.Tensor:
+    return torch.frombuffer(bytearray(bytes(obj)), dtype=torch.uint8).clone()
+
+
+def _outputs(plan, n_reps, device, dtype, details):
+    o = {'ofe': torch.empty(n_reps, device=device, dtype=dtype),
+         'ofe_arm': torch.empty(n_reps, device=device, dtype=torch.int32),
+         'best_xy': torch.empty(n_reps, 2, device=device, dtype=dtype)}
+    if details:
+        o['round_best'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=dtype)
+        o['round_best_arm'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=torch.int32)
+        o['survivors'] = torch.empty(n_reps, plan.n_surv, device=device, dtype=torch.int32)
+        o['ckpt_loss'] = torch.empty(n_reps, plan.n_arms, plan.n_ckpts, device=device, dtype=dtype)
+    ptr = lambda k: o[k].data_ptr() if k in o else None  # noqa: E731
+    outs = nat.HbOutputs(ptr('ofe'), ptr('ofe_arm'), ptr('best_xy'), ptr('round_best'), ptr('round_best_arm'),
+                         ptr('survivors'), ptr('ckpt_loss'))
+    order = ['ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors', 'ckpt_loss']
+    return outs, [o[k] for k in order if k in o]
+
+
+HB_OUTPUT_NAMES = ['ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors', 'ckpt_loss']
+
+
+@torch.library.custom_op('at2::hb_sim_f32', mutates_args=(), device_types='cuda')
+def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
+               seed: int, details: bool) -> List[torch.Tensor]:
+    """Fused Philox/Gamma simulation + successive halving for `n_reps` Hyperband repetitions (at2_hb_sim_f32)."""
+    _require_cuda(tables, 'tables')
+    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
+    with torch.cuda.device(tables.device):
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
+        nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
+                                         seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
+    return tensors
+
+
+@hb_sim_f32.register_fake
+def _(tables, plan_bytes, cfg_bytes, n_reps, rep_offset, seed, details):
+    raise RuntimeError('at2::hb_sim_f32 has no meta/CPU implementation')
+
+
+@torch.library.custom_op('at2::hb_sim_predrawn', mutates_args=(), device_types='cuda')
+def hb_sim_predrawn(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, f1: torch.Tensor,
+                    fn: torch.Tensor, family: torch.Tensor, gamma: torch.Tensor, xy: torch.Tensor) -> List[torch.Tensor]:
+    """Recurrence + read-out + successive halving on pre-drawn inputs; dtype of `f1` picks the f64 (bit-exact
+    reference operation order) or f32 variant (at2_hb_sim_predrawn_f64 / _f32)."""
+    for name, t in (('tables', tables), ('f1', f1), ('fn', fn), ('family', family), ('gamma', gamma), ('xy', xy)):
+        _require_cuda(t, name)
+    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
+    dtype = f1.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise RuntimeError('f1 must be float32 or float64')
+    n_reps = f1.shape[0]
+    want = {'f1': (n_reps, plan.n_arms), 'fn': (n_reps, plan.n_arms), 'family': (n_reps, plan.n_arms),
+            'gamma': (n_reps, plan.n_arms, plan.R - 1), 'xy': (n_reps, plan.n_arms, 2)}
+    for name, t in (('f1', f1), ('fn', fn), ('family', family), ('gamma', gamma), ('xy', xy)):
+        if tuple(t.shape) != want[name] or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be contiguous with shape {want[name]}, got {tuple(t.shape)}')
+        if name != 'family' and t.dtype != dtype:
+            raise RuntimeError(f'{name} must have dtype {dtype}')
+    if family.dtype != torch.int32 or tables.dtype != dtype:
+        raise RuntimeError('family must be int32 and tables must match the dtype of f1')
+    fn_c = nat.lib.at2_hb_sim_predrawn_f64 if dtype == torch.float64 else nat.lib.at2_hb_sim_predrawn_f32
+    with torch.cuda.device(f1.device):
+        outs, tensors = _outputs(plan, n_reps, f1.device, dtype, True)
+        nat.check(fn_c(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, f1.data_ptr(), fn.data_ptr(),
+                       family.data_ptr(), gamma.data_ptr(), xy.data_ptr(), C.byref(outs), _stream_ptr(f1.device)))
+    return tensors
+
+
+@torch.library.custom_op('at2::fma_peak_probe', mutates_args=('sink',), device_types='cuda')
+def fma_peak_probe(sink: torch.Tensor, blocks: int, threads: int, iters: int) -> None:
+    _require_cuda(sink, 'sink')
+    with torch.cuda.device(sink.device):
+        nat.check(nat.lib.at2_fma_peak_probe(blocks, threads, iters, sink.data_ptr(), _stream_ptr(sink.device)))

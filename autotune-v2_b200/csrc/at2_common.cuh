@@ -1,0 +1,84 @@
+// Shared definitions for libat2_b200 (sm_100a).  See include/at2.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "at2.h"
+
+// ---- error plumbing (thread-local message, no exceptions across the ABI) -------------------------------------------
+void at2_set_error(const char* fmt, ...);
+void at2_count_launch(int n);
+void at2_reset_launch_count();
+
+#define AT2_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            at2_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return AT2_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define AT2_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            at2_set_error(__VA_ARGS__); \
+            return AT2_EINVAL;          \
+        }                               \
+    } while (0)
+
+// ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
+// gam[t]   t in [0,R): {d, c, d*log2(e), d*scale}     Marsaglia-Tsang constants of step t (entry 0 unused)
+// pw[f][t] f in [0,F), t in [0,R): {P, P11}           (t/(R-1))**nec and (t/(R-1))**(1.1*nec)
+// sg[t][c] t in [0,R), c in [0,sg_stride)             Savitzky-Golay weight of raw[t] in the smoothed value at
+//                                                      checkpoint c (present only when some family is smooth)
+__host__ __device__ inline int at2_sg_stride(int n_ckpts) { return n_ckpts <= 4 ? 4 : (n_ckpts <= 8 ? 8 : 16); }
+
+struct At2TableLayout {
+    int R, F, has_smooth, sg_stride;
+    __host__ __device__ int off_gam() const { return 0; }
+    __host__ __device__ int off_pw() const { return 4 * R; }
+    __host__ __device__ int off_sg() const { return 4 * R + 2 * F * R; }
+    __host__ __device__ int total() const { return 4 * R + 2 * F * R + (has_smooth ? sg_stride * R : 0); }
+};
+
+static inline int at2_cfg_has_smooth(const at2_sim_config* cfg) {
+    for (int f = 0; f < cfg->n_families; ++f)
+        if (cfg->fam[f].is_smooth) return 1;
+    return 0;
+}
+
+// ---- Philox4x32-10 (Salmon et al., SC'11), counter-based -------------------------------------------------------------
+#define AT2_PHILOX_M0 0xD2511F53u
+#define AT2_PHILOX_M1 0xCD9E8D57u
+#define AT2_PHILOX_W0 0x9E3779B9u
+#define AT2_PHILOX_W1 0xBB67AE85u
+
+struct At2U4 {
+    uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ At2U4 at2_philox10(At2U4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)AT2_PHILOX_M0 * c.x;
+        const uint64_t p1 = (uint64_t)AT2_PHILOX_M1 * c.z;
+        At2U4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ k0;
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ k1;
+        n.w = (uint32_t)p0;
+        c = n;
+        k0 += AT2_PHILOX_W0;
+        k1 += AT2_PHILOX_W1;
+    }
+    return c;
+}
+
+// RNG stream tags (4th counter word)
+#define AT2_STREAM_ARM 0u   // arm initialisation: x, y, family, z
+#define AT2_STREAM_TRAJ 1u  // trajectory attempts
+#define AT2_STREAM_TPE 2u   // TPE candidate sampling

@@ -1,0 +1,655 @@
+// (a)+(b) fused: Gamma-process trajectory simulation + Hyperband successive halving, one launch for all repetitions.
+//
+// Work decomposition (B200: 148 SMs, 4 SMSPs each, no HBM traffic to speak of - the kernel is issue/XU bound):
+//   * a CTA owns a *tile* of G consecutive repetitions; its G*A arm trajectories are spread flat over the CTA's lanes
+//     (one lane = one arm at a time) so lane occupancy does not depend on A being a multiple of 32;
+//   * every lane runs its own Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang attempt loop.  A rejected attempt
+//     simply does not advance that lane's epoch, so lanes drift apart by a few epochs instead of the whole warp
+//     re-drawing whenever any lane rejects; per-epoch constants come from shared-memory tables indexed per lane;
+//   * only the losses at the Hyperband checkpoints are kept (shared memory, C values per arm); smooth families
+//     accumulate the Savitzky-Golay dot products of those C read-outs on the fly, so no trajectory is ever stored;
+//   * successive halving then runs per repetition inside one warp: (loss, position) keys, bitonic network in shared
+//     memory for the wide first round, pure warp-shuffle network once a round fits in 32 lanes.
+//
+// Reference behaviour implemented (paths relative to the reference root):
+//   core/simulation_evaluator.py:36-48,84-116   Gamma draw + recurrence
+//   core/simulation_evaluator.py:76-82          .fs read-out (raw or Savitzky-Golay)
+//   benchmarks/opt_function_simulation_problem.py:50-86,91-118   f_1 / f_n, int(n_resources) read-out
+//   benchmarks/opt_function_problem.py:49-147   test functions;  core/arm.py:44-55, core/params.py:36 arm draw
+//   core/shape_family_scheduler.py:50-77        family choice
+//   optimisers/sequential/hyperband_optimiser.py:46-57,74-106    stable top-k, round-best, OFE (core/optimiser.py:67-68)
+#include <cfloat>
+#include <climits>
+#include <cstdlib>
+
+#include "at2_common.cuh"
+
+namespace {
+
+enum { MODE_PHILOX = 0, MODE_PREDRAWN = 1 };
+
+// ---- arithmetic policies ---------------------------------------------------------------------------------------------
+// double: the reference's float64 operation order with explicitly un-fused IEEE ops (bit-exact parity path).
+// float : production arithmetic, contraction to FFMA welcome.
+template <typename T>
+struct Fam {
+    T ml, up, s0, s1;  // float: ml = ml_agg/100 folded; double: raw ml_agg
+    int smooth, pw_off;
+};
+
+__device__ __forceinline__ double step_exact(double f, double g, int t, int R, double fn, double ml_agg, double up_spik,
+                                             double P, double P11) {
+    if (g == 2.0) return f;                                                        // :100-101
+    if (g > 2.0) {                                                                 // :102-107
+        const double debt = __dsub_rn(fn, f);
+        const double ml = __dadd_rn(f, __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(g, 2.0), ml_agg), debt), 100.0));
+        return __dadd_rn(ml, __dmul_rn(__dsub_rn(fn, ml), P));
+    }
+    const double up = __dadd_rn(f, __ddiv_rn(__dmul_rn(up_spik, 1.0), __dadd_rn(1.0, g)));  // :108-115
+    double nxt = __dadd_rn(up, __dmul_rn(__dsub_rn(fn, up), P11));
+    if (R - t == 1) nxt = fn;
+    return nxt;
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sin(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_cos(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float step_fast(float f, float g, int t, int R, float fn, float mlc, float upc, float P,
+                                           float P11) {
+    const float ml = fmaf((g - 2.0f) * mlc, fn - f, f);
+    const float dn = fmaf(fn - ml, P, ml);
+    const float up = fmaf(upc, fast_rcp(1.0f + g), f);
+    float un = fmaf(fn - up, P11, up);
+    un = (R - t == 1) ? fn : un;
+    return g > 2.0f ? dn : (g < 2.0f ? un : f);
+}
+
+// ---- test functions in FP32 (benchmarks/opt_function_problem.py:49-138) ------------------------------------------------
+__device__ float base_function(int func, float x, float y) {
+    switch (func) {
+        case AT2_FUNC_EGG:
+            return -(y + 47.0f) * sinf(sqrtf(fabsf(y + 0.5f * x + 47.0f))) - x * sinf(sqrtf(fabsf(x - y - 47.0f)));
+        case AT2_FUNC_BRANIN: {
+            const float b = 5.1f / (4.0f * 9.8696044010893586f), c = 5.0f / 3.14159265358979f;
+            const float tt = 1.0f / (8.0f * 3.14159265358979f);
+            const float q = y - b * x * x + c * x - 6.0f;
+            return q * q + 10.0f * (1.0f - tt) * cosf(x) + 10.0f;
+        }
+        case AT2_FUNC_CAMEL: {
+            const float x2 = x * x, y2 = y * y;
+            return (4.0f - 2.1f * x2 + x2 * x2 / 3.0f) * x2 + x * y + (-4.0f + 4.0f * y2) * y2;
+        }
+        case AT2_FUNC_WAVE: {
+            const float r2 = x * x + y * y;
+            return -(1.0f + cosf(12.0f * sqrtf(r2))) / (0.5f * r2 + 2.0f);
+        }
+        default:  // AT2_FUNC_RASTRIGIN
+            return 20.0f + ((x * x - 10.0f * cospif(2.0f * x)) + (y * y - 10.0f * cospif(2.0f * y)));
+    }
+}
+
+// ---- sort keys: (loss, position) with position breaking ties = python's stable sorted() ---------------------------------
+// float : 64-bit key  [orderable(loss) : 32 | position : 32]
+// double: 96-bit key  {orderable(loss) : 64, position : 32}
+__device__ __forceinline__ uint32_t orderable(float x, bool desc) {
+    x += 0.0f;  // -0.0 -> +0.0 (python compares them equal)
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t o = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    return desc ? ~o : o;
+}
+__device__ __forceinline__ uint64_t orderable(double x, bool desc) {
+    x += 0.0;
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+    const uint64_t o = b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    return desc ? ~o : o;
+}
+
+struct Key32 {  // float losses
+    uint64_t v;
+    __device__ __forceinline__ static Key32 make(float loss, int pos, bool desc) {
+        return Key32{((uint64_t)orderable(loss, desc) << 32) | (uint32_t)pos};
+    }
+    __device__ __forceinline__ static Key32 pad() { return Key32{~0ull}; }
+    __device__ __forceinline__ int pos() const { return (int)(uint32_t)v; }
+    __device__ __forceinline__ bool operator>(const Key32& o) const { return v > o.v; }
+    __device__ __forceinline__ Key32 shfl_xor(int m) const { return Key32{__shfl_xor_sync(0xffffffffu, v, m)}; }
+    __device__ __forceinline__ Key32 shfl(int l) const { return Key32{__shfl_sync(0xffffffffu, v, l)}; }
+};
+struct Key64 {  // double losses
+    uint64_t k;
+    uint32_t p;
+    uint32_t _pad;
+    __device__ __forceinline__ static Key64 make(double loss, int pos, bool desc) {
+        return Key64{orderable(loss, desc), (uint32_t)pos, 0u};
+    }
+    __device__ __forceinline__ static Key64 pad() { return Key64{~0ull, ~0u, 0u}; }
+    __device__ __forceinline__ int pos() const { return (int)p; }
+    __device__ __forceinline__ bool operator>(const Key64& o) const { return k > o.k || (k == o.k && p > o.p); }
+    __device__ __forceinline__ Key64 shfl_xor(int m) const {
+        return Key64{__shfl_xor_sync(0xffffffffu, k, m), __shfl_xor_sync(0xffffffffu, p, m), 0u};
+    }
+    __device__ __forceinline__ Key64 shfl(int l) const {
+        return Key64{__shfl_sync(0xffffffffu, k, l), __shfl_sync(0xffffffffu, p, l), 0u};
+    }
+};
+template <typename T>
+struct KeyOf;
+template <>
+struct KeyOf<float> {
+    typedef Key32 type;
+};
+template <>
+struct KeyOf<double> {
+    typedef Key64 type;
+};
+
+// ascending bitonic network over `npad` (power of two, > 32) keys in shared memory, executed by one warp
+template <typename K>
+__device__ void warp_bitonic_smem(K* keys, int npad, int lane) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = lane; idx < (npad >> 1); idx += 32) {
+                const int a = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
+                const int b = a | j;
+                const bool up = (a & k) == 0;
+                const K ka = keys[a], kb = keys[b];
+                if ((ka > kb) == up) {
+                    keys[a] = kb;
+                    keys[b] = ka;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ascending bitonic network over 32 keys, one per lane, warp shuffles only
+template <typename K>
+__device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const K other = mine.shfl_xor(j);
+            const bool up = (lane & k) == 0;
+            const bool lower = (lane & j) == 0;
+            // the lower lane of a pair keeps the smaller key in an ascending block, the larger in a descending one
+            const bool take_other = (mine > other) == (up == lower);
+            if (take_other) mine = other;
+        }
+    }
+    return mine;
+}
+
+template <typename T>
+struct Params {
+    at2_plan plan;
+    Fam<T> fam[AT2_MAX_FAMILIES];
+    int func, F, scheduler, descending;
+    float x_min, x_rng, y_min, y_rng, noise;
+    const T* tables;
+    long long n_reps, rep_offset;
+    uint32_t key0, key1;
+    int G;        // repetitions per tile
+    int n_tiles;
+    int npad;     // power of two >= widest bracket
+    int stride;   // G * n_arms rounded up to 32
+    // pre-drawn inputs
+    const T* f1;
+    const T* fn;
+    const int* family;
+    const T* gamma;
+    const T* xy;
+    // outputs
+    T* ofe;
+    int* ofe_arm;
+    T* best_xy;
+    T* round_best;
+    int* round_best_arm;
+    int* survivors;
+    T* ckpt_loss;
+};
+
+template <typename T, int MODE, bool HAS_SMOOTH, int CK, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ Params<T> p) {
+    typedef typename KeyOf<T>::type K;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.F;
+    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    T* s_tab = reinterpret_cast<T*>(smem_raw);
+    const int tab_elems = (L.total() + 3) & ~3;
+    T* s_ck = s_tab + tab_elems;                                    // [C][stride]
+    T* s_xy = s_ck + (size_t)C * p.stride;                          // [2][stride]  (x, y of every arm)
+    K* s_keys = reinterpret_cast<K*>(s_xy + 2 * (size_t)p.stride);  // [nwarps][npad]
+    const int nwarps = BLOCK / 32;
+    int* s_ids = reinterpret_cast<int*>(s_keys + (size_t)nwarps * p.npad);  // [nwarps][2][npad]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < L.total(); i += BLOCK) s_tab[i] = p.tables[i];
+    __syncthreads();
+    const T* s_gam = s_tab + L.off_gam();
+    const T* s_pw = s_tab + L.off_pw();
+    const T* s_sg = s_tab + L.off_sg();
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const long long rep0 = (long long)tile * p.G;
+        const int g_eff = (int)min((long long)p.G, p.n_reps - rep0);
+        const int n_items = g_eff * A;
+
+        // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
+        for (int base = warp * 32; base < n_items; base += BLOCK) {
+            const int i = base + lane;
+            const bool active = i < n_items;
+            const int ii = active ? i : 0;
+            const int rep_l = ii / A, arm = ii - rep_l * A;
+            const long long rep_g = rep0 + rep_l;                   // index into per-call arrays
+            const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + arm;
+            T f1, fn, ax = (T)0, ay = (T)0;
+            int fam_i;
+            if constexpr (MODE == MODE_PHILOX) {
+                // arm draw: x, y uniform on the domain (params.py:36), family (shape_family_scheduler.py:61,75),
+                // z ~ N(0,1) for the initial noise (opt_function_problem.py:138)
+                const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
+                const float x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, p.x_rng, p.x_min);
+                const float y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, p.y_rng, p.y_min);
+                fam_i = p.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)F) : arm % F;
+                const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+                const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
+                const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+                const float f = base_function(p.func, x, y);
+                fn = (T)(f - (float)p.fam[fam_i].s1);               // opt_function_simulation_problem.py:63
+                f1 = (T)((f + p.noise * z) - (float)p.fam[fam_i].s0);  // :62,:64
+                ax = (T)x, ay = (T)y;
+            } else {
+                const long long a_g = rep_g * A + arm;
+                f1 = active ? p.f1[a_g] : (T)0;
+                fn = active ? p.fn[a_g] : (T)0;
+                fam_i = active ? p.family[a_g] : 0;
+                if (p.xy != nullptr && active) ax = p.xy[2 * a_g], ay = p.xy[2 * a_g + 1];
+            }
+            const Fam<T> fam = p.fam[fam_i];
+            const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+            if (active) s_xy[ii] = ax, s_xy[p.stride + ii] = ay;
+
+            T f = f1;
+            int t = 1;   // next trajectory position to produce (0-based: f is fs[t-1])
+            int nc = 0;  // next checkpoint to capture (non-smooth arms)
+            int next_pos = p.plan.ckpt_time[0] - 1;
+            T acc[CK];
+#pragma unroll
+            for (int c = 0; c < CK; ++c) acc[c] = HAS_SMOOTH ? s_sg[c] * f : (T)0;  // sg[0][c] * fs[0]
+            if (active && !smooth && next_pos == 0) {
+                s_ck[ii] = f;
+                nc = 1;
+                next_pos = C > 1 ? p.plan.ckpt_time[1] - 1 : INT_MAX;
+            }
+
+            // bookkeeping after fs[t] has been produced
+            auto commit = [&](T fnew) {
+                f = fnew;
+                if (HAS_SMOOTH) {
+                    if (smooth) {
+#pragma unroll
+                        for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[t * L.sg_stride + c], f, acc[c]);
+                    }
+                }
+                if (!smooth && t == next_pos) {
+                    s_ck[nc * p.stride + ii] = f;
+                    ++nc;
+                    next_pos = nc < C ? p.plan.ckpt_time[nc] - 1 : INT_MAX;
+                }
+                ++t;
+            };
+
+            if constexpr (MODE == MODE_PREDRAWN) {
+                const T* grow = p.gamma + (rep_g * A + arm) * (long long)(R - 1);
+                for (int tt = 1; tt < R; ++tt) {
+                    if (!active) break;
+                    const T g = grow[tt - 1];
+                    const T P = s_pw[2 * (fam.pw_off + tt)], P11 = s_pw[2 * (fam.pw_off + tt) + 1];
+                    T fnew;
+                    if constexpr (sizeof(T) == 8)
+                        fnew = (T)step_exact((double)f, (double)g, tt, R, (double)fn, (double)fam.ml, (double)fam.up,
+                                             (double)P, (double)P11);
+                    else
+                        fnew = (T)step_fast((float)f, (float)g, tt, R, (float)fn, (float)fam.ml, (float)fam.up,
+                                            (float)P, (float)P11);
+                    commit(fnew);
+                }
+            } else {
+                // one Philox block = 2 normals + 2 uniforms = 2 Marsaglia-Tsang attempts
+                const float4* gam4 = reinterpret_cast<const float4*>(s_gam);
+                const float2* pw2 = reinterpret_cast<const float2*>(s_pw) + fam.pw_off;
+                const float fnf = (float)fn, mlc = (float)fam.ml, upc = (float)fam.up;
+                uint32_t ctr = 0;
+                auto attempt = [&](float x, float u) {
+                    const bool live = active && t < R;
+                    const int tt = live ? t : 1;
+                    const float4 gm = gam4[tt];                     // d, c, d*log2e, d*scale
+                    const float v = fmaf(gm.y, x, 1.0f);
+                    const float v3 = v * v * v;
+                    // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
+                    const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
+                    const bool ok = live && v > 0.0f && fast_lg2(u) < rhs;
+                    const float g = gm.w * v3;
+                    const float2 pw = pw2[tt];
+                    const float fnew = step_fast((float)f, g, tt, R, fnf, mlc, upc, pw.x, pw.y);
+                    if (ok) commit((T)fnew);
+                };
+                while (__any_sync(0xffffffffu, active && t < R)) {
+                    const At2U4 r = at2_philox10(At2U4{ctr, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_TRAJ}, p.key0, p.key1);
+                    ++ctr;
+                    const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
+                    const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                     // sqrt(-2 ln u1)
+                    const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;                       // [-pi, pi)
+                    const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));                    // (0,1]
+                    const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
+                    attempt(rad * fast_cos(ang), ua);
+                    attempt(rad * fast_sin(ang), ub);
+                }
+            }
+            if (HAS_SMOOTH) {
+                if (active && smooth) {
+#pragma unroll
+                    for (int c = 0; c < CK; ++c)
+                        if (c < C) s_ck[c * p.stride + ii] = acc[c];
+                }
+            }
+        }
+        __syncthreads();
+
+        if (p.ckpt_loss != nullptr) {
+            for (int i = tid; i < n_items * C; i += BLOCK) {
+                const int a = i / C, c = i - a * C;
+                p.ckpt_loss[(rep0 * A + a) * C + c] = s_ck[c * p.stride + a];
+            }
+        }
+
+        // ---------------- phase 2: successive halving, one warp per repetition ----------------
+        K* keys = s_keys + (size_t)warp * p.npad;
+        int* ids_a = s_ids + (size_t)warp * 2 * p.npad;
+        int* ids_b = ids_a + p.npad;
+        const bool desc = p.descending != 0;
+        for (int rep_l = warp; rep_l < g_eff; rep_l += nwarps) {
+            const long long rep_g = rep0 + rep_l;
+            const int arm0 = rep_l * A;
+            T best = (T)0;
+            int best_arm = -1;
+            int surv_w = 0;
+            for (int b = 0; b < p.plan.n_brackets; ++b) {
+                int n_cur = p.plan.bracket_n[b];
+                const int first = p.plan.bracket_first_arm[b];
+                for (int j = lane; j < n_cur; j += 32) ids_a[j] = first + j;
+                __syncwarp();
+                int* ids = ids_a;
+                int* ids_next = ids_b;
+                for (int rd = p.plan.bracket_first_round[b]; rd < p.plan.bracket_first_round[b + 1]; ++rd) {
+                    const int c = p.plan.round_ckpt[rd];
+                    const int keep = min(p.plan.round_keep[rd], n_cur);
+                    T rb_loss;
+                    int rb_arm;
+                    if (n_cur <= 32) {
+                        K mine = K::pad();
+                        T my_loss = (T)0;
+                        int my_id = 0;
+                        if (lane < n_cur) {
+                            my_id = ids[lane];
+                            my_loss = s_ck[c * p.stride + arm0 + my_id];
+                            mine = K::make(my_loss, lane, desc);
+                        }
+                        mine = warp_bitonic_shfl(mine, lane);
+                        const int src = mine.pos() & 31;            // lane that held the key now ranked `lane`
+                        const int sid = __shfl_sync(0xffffffffu, my_id, src);
+                        const T sl = __shfl_sync(0xffffffffu, my_loss, src);
+                        rb_loss = __shfl_sync(0xffffffffu, sl, 0);
+                        rb_arm = __shfl_sync(0xffffffffu, sid, 0);
+                        __syncwarp();
+                        if (lane < keep) ids_next[lane] = sid;
+                    } else {
+                        int npad = 64;
+                        while (npad < n_cur) npad <<= 1;
+                        for (int j = lane; j < npad; j += 32)
+                            keys[j] = j < n_cur ? K::make(s_ck[c * p.stride + arm0 + ids[j]], j, desc) : K::pad();
+                        __syncwarp();
+                        warp_bitonic_smem(keys, npad, lane);
+                        for (int j = lane; j < keep; j += 32) ids_next[j] = ids[keys[j].pos()];
+                        rb_arm = ids[keys[0].pos()];
+                        rb_loss = s_ck[c * p.stride + arm0 + rb_arm];
+                    }
+                    __syncwarp();
+                    if (p.survivors != nullptr)
+                        for (int j = lane; j < keep; j += 32) p.survivors[rep_g * p.plan.n_surv + surv_w + j] = ids_next[j];
+                    surv_w += keep;
+                    if (lane == 0) {
+                        if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = rb_loss;
+                        if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = rb_arm;
+                    }
+                    // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
+                    if (best_arm < 0 || (desc ? rb_loss > best : rb_loss < best)) best = rb_loss, best_arm = rb_arm;
+                    int* tmp = ids;
+                    ids = ids_next;
+                    ids_next = tmp;
+                    n_cur = keep;
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) {
+                if (p.ofe != nullptr) p.ofe[rep_g] = best;
+                if (p.ofe_arm != nullptr) p.ofe_arm[rep_g] = best_arm;
+                if (p.best_xy != nullptr) {
+                    p.best_xy[2 * rep_g] = s_xy[arm0 + best_arm];
+                    p.best_xy[2 * rep_g + 1] = s_xy[p.stride + arm0 + best_arm];
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- launch plumbing ---------------------------------------------------------------------------------------------------
+template <typename T>
+struct LaunchCfg {
+    int G, block, grid, npad, stride;
+    size_t smem;
+};
+
+template <typename T>
+int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, int mode, LaunchCfg<T>* out) {
+    typedef typename KeyOf<T>::type K;
+    const int A = plan->n_arms, C = plan->n_ckpts, R = plan->R;
+    int widest = 0;
+    for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
+    int npad = 64;
+    while (npad < widest) npad <<= 1;
+    const int block = 128;
+    const int nwarps = block / 32;
+    At2TableLayout L{R, F, has_smooth, at2_sg_stride(C)};
+    const size_t tab = (size_t)((L.total() + 3) & ~3) * sizeof(T);
+    const size_t sort_scratch = (size_t)nwarps * npad * (sizeof(K) + 2 * sizeof(int));
+    int dev = 0, max_smem = 0, sms = 0;
+    AT2_CUDA_CHECK(cudaGetDevice(&dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // per-repetition shared memory: C checkpoint losses + (x, y) per arm
+    const size_t per_rep = (size_t)A * (C + 2) * sizeof(T);
+    // target <= ~36 KB per CTA (>= 6 CTAs / SM); among feasible G pick the best lane-packing efficiency
+    const size_t budget = 40 * 1024;
+    int best_g = 1;
+    double best_eff = -1.0;
+    const char* env_g = getenv("AT2_HB_REPS_PER_CTA");
+    for (int g = 1; g <= 64; ++g) {
+        const size_t need = tab + sort_scratch + per_rep * g + 32 * (C + 2) * sizeof(T);
+        if (g > 1 && need > budget) break;
+        const int items = g * A;
+        const int passes = (items + block - 1) / block;
+        double eff = (double)items / ((double)passes * block);
+        // the halving phase wants at least one repetition per warp
+        if (g % nwarps != 0) eff -= 0.02;
+        if (eff > best_eff + 1e-9) best_eff = eff, best_g = g;
+    }
+    if (env_g != nullptr && atoi(env_g) > 0) best_g = atoi(env_g);
+    if ((long long)best_g > n_reps) best_g = (int)n_reps;
+    const int stride = (best_g * A + 31) & ~31;
+    const size_t smem = tab + (size_t)(C + 2) * stride * sizeof(T) + sort_scratch;
+    if (smem > (size_t)max_smem) {
+        at2_set_error("hyperband simulation needs %zu B of shared memory per CTA (R=%d, %d arms, %d checkpoints); device limit %d B",
+                      smem, R, A, C, max_smem);
+        return AT2_ELIMIT;
+    }
+    const long long n_tiles = (n_reps + best_g - 1) / best_g;
+    // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA), capped by 16 warps-worth of CTAs
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    long long grid = (long long)sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    out->G = best_g, out->block = block, out->grid = (int)grid, out->npad = npad, out->stride = stride, out->smem = smem;
+    (void)mode;
+    return AT2_OK;
+}
+
+template <typename T, int MODE, bool HS, int CK>
+int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
+    auto kern = hb_sim_kernel<T, MODE, HS, CK, 128>;
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    kern<<<lc.grid, lc.block, lc.smem, st>>>(p);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    return AT2_OK;
+}
+
+template <typename T, int MODE>
+int launch_dispatch(const Params<T>& p, const LaunchCfg<T>& lc, int has_smooth, cudaStream_t st) {
+    if (!has_smooth) return launch_one<T, MODE, false, 1>(p, lc, st);
+    const int C = p.plan.n_ckpts;
+    if (C <= 4) return launch_one<T, MODE, true, 4>(p, lc, st);
+    if (C <= 6) return launch_one<T, MODE, true, 6>(p, lc, st);
+    if (C <= 8) return launch_one<T, MODE, true, 8>(p, lc, st);
+    return launch_one<T, MODE, true, 16>(p, lc, st);
+}
+
+template <typename T>
+int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, long long n_reps,
+                const at2_hb_outputs* out, Params<T>* p, LaunchCfg<T>* lc, int mode) {
+    AT2_REQUIRE(plan && cfg && d_tables && out, "at2_hb_sim: NULL plan/config/tables/outputs");
+    AT2_REQUIRE(n_reps > 0, "at2_hb_sim: n_reps must be positive (got %lld)", n_reps);
+    AT2_REQUIRE(plan->n_arms > 0 && plan->n_rounds > 0 && plan->n_ckpts > 0 && plan->n_ckpts <= AT2_MAX_CKPTS,
+                "at2_hb_sim: plan is empty or malformed");
+    AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_hb_sim: n_families %d outside [1,%d]",
+                cfg->n_families, AT2_MAX_FAMILIES);
+    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_hb_sim: unknown func id %d", cfg->func);
+    const int has_smooth = at2_cfg_has_smooth(cfg);
+    AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
+                "If mode is 'interp', window_length must be less than or equal to the size of x.");
+    p->plan = *plan;
+    for (int f = 0; f < cfg->n_families; ++f) {
+        p->fam[f].ml = sizeof(T) == 8 ? (T)cfg->fam[f].ml_agg : (T)(cfg->fam[f].ml_agg / 100.0);
+        p->fam[f].up = (T)cfg->fam[f].up_spik;
+        p->fam[f].s0 = (T)cfg->fam[f].start_shift;
+        p->fam[f].s1 = (T)cfg->fam[f].end_shift;
+        p->fam[f].smooth = cfg->fam[f].is_smooth;
+        p->fam[f].pw_off = f * plan->R;
+    }
+    p->func = cfg->func, p->F = cfg->n_families, p->scheduler = cfg->scheduler, p->descending = cfg->descending;
+    p->x_min = (float)cfg->x_min, p->x_rng = (float)(cfg->x_max - cfg->x_min);
+    p->y_min = (float)cfg->y_min, p->y_rng = (float)(cfg->y_max - cfg->y_min);
+    p->noise = (float)cfg->init_noise;
+    p->tables = (const T*)d_tables;
+    p->n_reps = n_reps;
+    p->ofe = (T*)out->d_ofe, p->ofe_arm = out->d_ofe_arm, p->best_xy = (T*)out->d_best_xy;
+    p->round_best = (T*)out->d_round_best, p->round_best_arm = out->d_round_best_arm;
+    p->survivors = out->d_survivors, p->ckpt_loss = (T*)out->d_ckpt_loss;
+    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, mode, lc);
+    if (rc != AT2_OK) return rc;
+    p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
+    p->n_tiles = (int)((n_reps + lc->G - 1) / lc->G);
+    return AT2_OK;
+}
+
+}  // namespace
+
+extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                              int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream) {
+    at2_reset_launch_count();
+    Params<float> p = {};
+    LaunchCfg<float> lc;
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PHILOX);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
+    p.rep_offset = rep_offset;
+    p.key0 = (uint32_t)seed, p.key1 = (uint32_t)(seed >> 32);
+    return launch_dispatch<float, MODE_PHILOX>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
+}
+
+extern "C" int at2_hb_sim_predrawn_f64(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables,
+                                       int64_t n_reps, const double* d_f1, const double* d_fn, const int32_t* d_family,
+                                       const double* d_gamma, const double* d_xy, const at2_hb_outputs* out,
+                                       void* stream) {
+    at2_reset_launch_count();
+    Params<double> p = {};
+    LaunchCfg<double> lc;
+    const int rc = fill_params<double>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PREDRAWN);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f64: NULL input array");
+    p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;
+    return launch_dispatch<double, MODE_PREDRAWN>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
+}
+
+extern "C" int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables,
+                                       int64_t n_reps, const float* d_f1, const float* d_fn, const int32_t* d_family,
+                                       const float* d_gamma, const float* d_xy, const at2_hb_outputs* out,
+                                       void* stream) {
+    at2_reset_launch_count();
+    Params<float> p = {};
+    LaunchCfg<float> lc;
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PREDRAWN);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f32: NULL input array");
+    p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;
+    return launch_dispatch<float, MODE_PREDRAWN>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
+}
+
+// ---- FP32 FMA micro-benchmark (roofline denominator measured in the same run) -----------------------------------------
+__global__ void fma_probe_kernel(long long iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
+    for (long long i = 0; i < iters; ++i) {
+        a0 = fmaf(a0, m, c), a1 = fmaf(a1, m, c), a2 = fmaf(a2, m, c), a3 = fmaf(a3, m, c);
+        a4 = fmaf(a4, m, c), a5 = fmaf(a5, m, c), a6 = fmaf(a6, m, c), a7 = fmaf(a7, m, c);
+    }
+    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chain alive
+}
+
+extern "C" int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, float* d_sink, void* stream) {
+    at2_reset_launch_count();
+    AT2_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && d_sink, "at2_fma_peak_probe: bad argument");
+    fma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, d_sink);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    return AT2_OK;
+}

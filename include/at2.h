@@ -1,0 +1,163 @@
+/*
+ * at2.h - C ABI of libat2_b200: the B200 (sm_100a) implementation of autotune-v2's Monte-Carlo optimiser-evaluation
+ * hot path (Hyperband / TPE / hybrids on Gamma-process loss simulations and on the closest-known-loss-function
+ * approximation, collected into an EPDF-OFE).
+ *
+ * The reference (cristianmatache/autotune-v2) is pure Python and has no FFI of its own: the boundary this library
+ * sits behind is the reference's Python class API (autotune/benchmarks, autotune/optimisers).  Each entry point below
+ * names the reference code (file:line, relative to the reference root) whose work it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy
+ *     default stream).
+ *   - every function returns 0 on success, a negative AT2_E* code on failure; `at2_last_error()` returns a
+ *     thread-local message for the last failure on the calling thread.  Nothing throws or aborts across the ABI.
+ *   - pointers named `d_*` are DEVICE pointers owned by the caller; everything else is host memory.  The library
+ *     allocates nothing and keeps no global state; work is enqueued on `stream` and is asynchronous w.r.t. the host.
+ *   - randomness is counter-based Philox4x32-10 keyed by (seed; global repetition id, arm id): results do not depend
+ *     on grid shape, on how repetitions are sharded over GPUs, or on which entry point variant produced them.
+ */
+#ifndef AT2_H
+#define AT2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AT2_OK 0
+#define AT2_EINVAL (-1)   /* bad argument (message says which) */
+#define AT2_ECUDA (-2)    /* CUDA runtime error (message carries cudaGetErrorString) */
+#define AT2_ELIMIT (-3)   /* a compile-time capacity (AT2_MAX_*) or the shared-memory budget is exceeded */
+
+#define AT2_MAX_BRACKETS 16
+#define AT2_MAX_ROUNDS 64
+#define AT2_MAX_CKPTS 16
+#define AT2_MAX_FAMILIES 8
+
+/* test functions, reference autotune/benchmarks/opt_function_problem.py:141-147 */
+#define AT2_FUNC_EGG 0
+#define AT2_FUNC_BRANIN 1
+#define AT2_FUNC_CAMEL 2
+#define AT2_FUNC_WAVE 3
+#define AT2_FUNC_RASTRIGIN 4
+
+#define AT2_SCHED_UNIFORM 0      /* UniformShapeFamilyScheduler,    core/shape_family_scheduler.py:68-77 */
+#define AT2_SCHED_ROUND_ROBIN 1  /* RoundRobinShapeFamilyScheduler, core/shape_family_scheduler.py:50-65 */
+
+/* Hyperband bracket/round table of one repetition.
+ * Replaces the arithmetic of optimisers/sequential/hyperband_optimiser.py:66-97 (s_max, s_min, B, n, r, n_i, r_i,
+ * int(n_i/eta)).  Rounds are listed bracket after bracket in execution order. */
+typedef struct at2_plan {
+    int32_t R;                                  /* max_iter */
+    int32_t eta;
+    int32_t n_brackets;
+    int32_t n_rounds;                           /* total over brackets */
+    int32_t n_arms;                             /* sum of bracket_n: evaluators created per repetition */
+    int32_t n_ckpts;                            /* distinct int(r_i) values */
+    int32_t n_surv;                             /* sum over rounds of min(keep, n_eval) */
+    int32_t bracket_n[AT2_MAX_BRACKETS];        /* n of each bracket */
+    int32_t bracket_first_arm[AT2_MAX_BRACKETS];
+    int32_t bracket_first_round[AT2_MAX_BRACKETS + 1];
+    int32_t round_n_eval[AT2_MAX_ROUNDS];       /* evaluators evaluated in the round */
+    int32_t round_keep[AT2_MAX_ROUNDS];         /* int(n_i/eta) */
+    int32_t round_time[AT2_MAX_ROUNDS];         /* 1-based trajectory position read: int(r_i), or R when int(r_i)
+                                                   is 0 (python fs[-1]; e.g. R=729, eta=3) */
+    int32_t round_ckpt[AT2_MAX_ROUNDS];         /* index of round_time in ckpt_time */
+    int32_t ckpt_time[AT2_MAX_CKPTS];           /* ascending */
+} at2_plan;
+
+/* One shape family, core/shape_family_scheduler.py:10-17. */
+typedef struct at2_family {
+    double ml_agg, nec_agg, up_spik;
+    double start_shift, end_shift;
+    int32_t is_smooth;
+    int32_t _pad;
+} at2_family;
+
+/* Simulation problem + scheduler configuration (benchmarks/opt_function_simulation_problem.py:91-118 arguments,
+ * benchmarks/opt_function_problem.py:15-46 domains, experiments/run_simulation.py:31-57 constants). */
+typedef struct at2_sim_config {
+    int32_t func;            /* AT2_FUNC_* */
+    int32_t n_families;
+    int32_t scheduler;       /* AT2_SCHED_* */
+    int32_t descending;      /* 0: min_or_max=min, 1: max (core/optimiser.py:52-54) */
+    double x_min, x_max, y_min, y_max;
+    double init_noise;
+    at2_family fam[AT2_MAX_FAMILIES];
+} at2_sim_config;
+
+const char* at2_version(void);
+const char* at2_last_error(void);
+
+/* ---- host-only helpers ------------------------------------------------------------------------------------------ */
+
+/* Fill `plan` for Hyperband(R, eta) with the reference's float arithmetic (hyperband_optimiser.py:66-97).
+ * s_max is the exact integer floor(log_eta R) (what the reference's 64-digit mpmath evaluation yields). */
+int at2_bracket_plan(int32_t R, int32_t eta, at2_plan* plan);
+
+/* Rows of the linear operator W with scipy.signal.savgol_filter(x, window, polyorder=3, mode='interp') == W @ x
+ * (core/simulation_evaluator.py:76-82).  `window` = at2_savgol_window(R).  out[i*R + j] = W[rows[i]][j]. */
+int32_t at2_savgol_window(int32_t R);
+int at2_savgol_rows(int32_t R, int32_t n_rows, const int32_t* rows, double* out);
+
+/* Size in bytes / contents of the per-configuration constant tables consumed by at2_hb_sim_*:
+ * Gamma-step parameters (core/simulation_evaluator.py:36-42), the two time-aggressiveness powers
+ * (t/(R-1))**nec and (t/(R-1))**(1.1*nec) (:105,:112) per family, and the Savitzky-Golay rows at the checkpoints.
+ * `is_f64` selects double (parity path) or float (production path) entries.  The caller copies `host_out` to the
+ * device and passes it as `d_tables`. */
+int64_t at2_hb_tables_bytes(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64);
+int at2_hb_tables_build(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64, void* host_out);
+
+/* ---- (a)+(b): fused simulation + successive halving -------------------------------------------------------------- */
+
+/* Optional per-repetition outputs of at2_hb_sim_*; any pointer may be NULL.  `real` is float or double. */
+typedef struct at2_hb_outputs {
+    void* d_ofe;            /* real[n_reps]            min/max over round-bests (core/optimiser.py:67-68) */
+    int32_t* d_ofe_arm;     /* int32[n_reps]           arm id (creation order within the repetition) of the OFE */
+    void* d_best_xy;        /* real[n_reps][2]         hyperparameters of that arm */
+    void* d_round_best;     /* real[n_reps][n_rounds]  best-in-round (hyperband_optimiser.py:98-99) */
+    int32_t* d_round_best_arm; /* int32[n_reps][n_rounds] */
+    int32_t* d_survivors;   /* int32[n_reps][n_surv]   survivors of every round, sorted order, rounds concatenated */
+    void* d_ckpt_loss;      /* real[n_reps][n_arms][n_ckpts] loss of every arm at every checkpoint */
+} at2_hb_outputs;
+
+/* Production path, FP32, Philox.  Replaces the repetition loop experiments/run_simulation.py:147-157 for
+ * method sim(hb): per repetition draw arms (core/arm.py:44-55) and families, simulate every arm's Gamma-process
+ * trajectory (core/simulation_evaluator.py:84-116, benchmarks/opt_function_simulation_problem.py:50-86), read the
+ * losses at the Hyperband checkpoints and run successive halving (hyperband_optimiser.py:74-106).
+ * Repetition ids rep_offset .. rep_offset+n_reps-1 key the RNG. */
+int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                   int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
+
+/* Pre-drawn inputs (parity paths): nothing is sampled; the kernel only runs the recurrence, the checkpoint read-out
+ * and successive halving.  Per arm: first and target values f_1, f_n (opt_function_simulation_problem.py:61-64),
+ * the family index, and the R-1 Gamma values of its (effective) trajectory.
+ *   d_f1, d_fn : real[n_reps][n_arms]      d_family : int32[n_reps][n_arms]
+ *   d_gamma    : real[n_reps][n_arms][R-1]  d_xy (optional, only echoed to d_best_xy) : real[n_reps][n_arms][2]
+ * The f64 variant executes the reference's float64 operation order with un-fused IEEE add/mul/div, so trajectories
+ * of non-smooth families, survivor sets and OFEs are bit-identical to the reference on the same inputs. */
+int at2_hb_sim_predrawn_f64(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                            const double* d_f1, const double* d_fn, const int32_t* d_family, const double* d_gamma,
+                            const double* d_xy, const at2_hb_outputs* out, void* stream);
+int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                            const float* d_f1, const float* d_fn, const int32_t* d_family, const float* d_gamma,
+                            const float* d_xy, const at2_hb_outputs* out, void* stream);
+
+/* Number of kernel launches the last at2_* call on this thread enqueued (for bench.py's gpu_launches). */
+int32_t at2_last_launch_count(void);
+
+/* Raw Philox4x32-10 block (known-answer tests): out[4] = philox(ctr[4], key[2]).  Host function. */
+void at2_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* FP32 FMA-only micro-benchmark used as the roofline denominator of the simulation kernel: launches a kernel doing
+ * `iters` dependent-chain-free FFMAs per thread on `blocks` x `threads`; the caller times it with CUDA events.
+ * flops = 2 * iters * 8 * blocks * threads (8 independent accumulators per thread). */
+int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, float* d_sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AT2_H */
