@@ -69,6 +69,8 @@ def _load():
                                               C.POINTER(HbOutputs), vp]),
         'at2_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         'at2_fma_peak_probe': (C.c_int, [i32, i32, i64, vp, vp]),
+        'at2_kde_workspace_floats': (i64, [i64, i32]),
+        'at2_kde_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, vp, vp, i64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

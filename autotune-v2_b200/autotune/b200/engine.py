@@ -120,6 +120,22 @@ def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, d
     return dict(zip(ops.HB_OUTPUT_NAMES, outs))
 
 
+def host_start_and_target(spec, xy, fam, z):
+    """f_1 = f(x,y) + noise*z - start_shift and f_n = f(x,y) - end_shift per arm, in float64 on the host
+    (opt_function_simulation_problem.py:61-64).  Evaluated arm by arm through numpy *scalar* calls, as the reference
+    does: numpy's vectorised cos/sin loops are not bit-identical to its scalar path for every input."""
+    from autotune.benchmarks.opt_function_problem import NOISE_FREE_FUNCTIONS
+    func = NOISE_FREE_FUNCTIONS[spec.func_name]
+    xy, fam, z = np.asarray(xy, np.float64), np.asarray(fam), np.asarray(z, np.float64)
+    f1, fn = np.empty(fam.shape, np.float64), np.empty(fam.shape, np.float64)
+    for idx in np.ndindex(*fam.shape):
+        f = func(np.float64(xy[idx + (0,)]), np.float64(xy[idx + (1,)]))
+        ml, nec, up, sm, s0, s1 = spec.families[int(fam[idx])]
+        fn[idx] = f - s1
+        f1[idx] = (f + spec.init_noise * z[idx] * 1) - s0
+    return f1, fn
+
+
 def run_hyperband_predrawn(spec, f1, fn, family, gamma, xy=None, device=None, dtype=torch.float64):
     """Parity entry: recurrence + read-out + halving on pre-drawn per-arm inputs (host arrays or tensors).
 

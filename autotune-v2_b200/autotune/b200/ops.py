@@ -102,3 +102,20 @@ def fma_peak_probe(sink: torch.Tensor, blocks: int, threads: int, iters: int) ->
     _require_cuda(sink, 'sink')
     with torch.cuda.device(sink.device):
         nat.check(nat.lib.at2_fma_peak_probe(blocks, threads, iters, sink.data_ptr(), _stream_ptr(sink.device)))
+
+
+@torch.library.custom_op('at2::kde', mutates_args=(), device_types='cuda')
+def kde(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int) -> torch.Tensor:
+    """Kernel density of the float32 samples `x` on linspace(start, end, grid_points) (at2_kde_f32);
+    kernel 0 = Epanechnikov (the reference's), 1 = Gaussian."""
+    _require_cuda(x, 'x')
+    if x.dtype != torch.float32 or x.dim() != 1 or not x.is_contiguous():
+        raise RuntimeError('x must be a contiguous 1-D float32 tensor')
+    n = x.numel()
+    with torch.cuda.device(x.device):
+        ws_n = nat.lib.at2_kde_workspace_floats(n, grid_points)
+        ws = torch.empty(max(ws_n, 1), device=x.device, dtype=torch.float32)
+        dens = torch.empty(grid_points, device=x.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_kde_f32(x.data_ptr(), n, start, end, grid_points, bandwidth, kernel, dens.data_ptr(),
+                                      ws.data_ptr(), ws_n, _stream_ptr(x.device)))
+    return dens

@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md "Measurement").
+
+Workload (BASELINE.json configs[1]): Hyperband(R=81, eta=3) EPDF-OFE on the flat Branin Gamma-simulation problem,
+10^5 repetitions per GPU per step (weak scaling: repetitions are independent and shard with no data-path collective;
+the one collective is the all-gather of the OFE vector for the KDE).  A step = fused simulation+halving kernel over
+the rank's 10^5 repetitions -> all-gather (N>1) -> Epanechnikov KDE on the 1000-point grid.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one JSON line on rank 0)
+  python bench.py --impl reference ...                           the reference's CPU path (oracle port) on host cores
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'autotune-v2_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FUNC, FAMILIES, R, ETA, NOISE = 'branin', [(0, 1, 0, False, 0, 0)], 81, 3, 0.0
+REPS_PER_GPU = 100000
+KDE_START, KDE_END, KDE_H, KDE_G = 0.37, 1.5, 0.1, 1000   # plot_run_simulations_results.py:27-54 (flat-branin)
+ARMS, ARM_EPOCHS = 117, 117 * 80                          # per repetition
+FLOP_PER_ARM_EPOCH = 32                                   # algorithmic FP32 flop per arm-epoch
+WORKLOAD = ('Hyperband(R=81,eta=3) EPDF-OFE, flat Branin Gamma-simulation, 1e5 repetitions per GPU per step '
+            '(BASELINE.json configs[1])')
+METRIC, UNIT = 'simulated optimiser runs/sec', 'runs/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--reps-per-gpu', type=int, default=REPS_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank):
+    """The reference's own CPU implementation of the path (oracle port - the reference is pure Python and cannot travel
+    to the GPU box), all host cores, each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle.cpu_bench import HyperbandCpuPool, host_cores
+    procs = host_cores()
+    reps_per_proc = 6
+    pool = HyperbandCpuPool(procs)
+    for _ in range(min(args.warmup, 2)):
+        pool.run(FUNC, FAMILIES, R, ETA, NOISE, 2)
+    t0 = time.perf_counter()
+    n = 0
+    for s in range(args.steps):
+        _, _, ofes = pool.run(FUNC, FAMILIES, R, ETA, NOISE, reps_per_proc, seed0=2000 + 131 * s)
+        n += len(ofes)
+    wall = time.perf_counter() - t0
+    pool.close()
+    value = n / wall
+    sample = f'{procs} processes x {reps_per_proc} repetitions per step ({procs * reps_per_proc} runs/step)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': wall / max(args.steps, 1) * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'sample': sample},
+        'arm_epochs_per_s': value * ARM_EPOCHS,
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self._stop_evt = index, period, [], threading.Event()
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: ' + getattr(self, 'err', '?')]}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        names = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+                 0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+                 0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+        reasons = [n for b, n in names.items() if bits & b and n != 'gpu_idle']
+        return {'sm_mhz': mhz[len(mhz) // 2] if mhz else None, 'sm_max_mhz': self.max_mhz, 'reasons': reasons,
+                'samples': len(inside)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured (MEASURED_PEAKS.json)'
+    except Exception:  # noqa: BLE001
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback (B200_PROFILING.md)'
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if args.impl == 'reference':
+        run_reference_arm(args, rank)
+        return
+
+    # CPU baseline first (fork pool must exist before CUDA is initialised); rank 0, N=1 only
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_bench import HyperbandCpuPool, host_cores
+        procs = host_cores()
+        pool = HyperbandCpuPool(procs)
+        pool.run(FUNC, FAMILIES, R, ETA, NOISE, 2)
+        reps_per_proc = 200
+        v, wall, _ = pool.run(FUNC, FAMILIES, R, ETA, NOISE, reps_per_proc)
+        pool.close()
+        cpu_baseline = {'value': v, 'unit': UNIT, 'cores': procs, 'kind': 'port',
+                        'sample': f'{procs} processes x {reps_per_proc} repetitions of the same workload, '
+                                  f'{wall:.1f} s wall', 'arm_epochs_per_s_executed': v * (81 * 160 + 27 * 80 + 9 * 80)}
+
+    import torch
+    import torch.distributed as dist
+    from autotune.b200 import _native as nat
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    from autotune.b200.epdf import density, gather_slices, run_epdf_ofe
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_local = args.reps_per_gpu
+    n_total = n_local * world
+    spec = HyperbandSimSpec(FUNC, FAMILIES, R, ETA, NOISE, 'uniform', 'min')
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- FP32 FMA peak, measured in this run (roofline denominator of the simulation kernel) ----
+    sink = torch.zeros(1, device=dev)
+    blocks, threads, iters = 148 * 8, 256, 40000
+    best_ms = 1e30
+    for _ in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        torch.ops.at2.fma_peak_probe(sink, blocks, threads, iters)
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        best_ms = min(best_ms, a.elapsed_time(b))
+    fma_peak_tflops = 2.0 * 8 * iters * blocks * threads / (best_ms * 1e-3) / 1e12
+
+    def step(seed, sim_events=None):
+        if sim_events is not None:
+            sim_events[0].record(stream)
+        ofe = run_hyperband_repetitions(spec, n_local, seed=seed, rep_offset=rank * n_local, device=dev)['ofe']
+        if sim_events is not None:
+            sim_events[1].record(stream)
+        full = gather_slices(ofe, n_total) if world > 1 else ofe
+        return full, density(full, KDE_START, KDE_END, KDE_H, KDE_G)
+
+    for i in range(args.warmup):
+        step(1000 + i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    sim_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    launches = 0
+    for i in range(args.steps):
+        step(i, sim_ev[i])
+        launches += 3   # fused simulation+halving, KDE partial sums, KDE finish
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    sim_ms = sum(a.elapsed_time(b) for a, b in sim_ev) / max(args.steps, 1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = t.item()
+    ms_per_step = ms_total / max(args.steps, 1)
+    value = n_total * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host buffers (H2D of the step's constant tables, D2H of results) ----
+    import ctypes as C
+    nbytes = nat.lib.at2_hb_tables_bytes(C.byref(spec.plan), C.byref(spec.cfg), 0)
+    host_tab = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    host_ofe = torch.empty(n_total, dtype=torch.float32).pin_memory()
+    host_den = torch.empty(KDE_G, dtype=torch.float32).pin_memory()
+
+    def e2e_step(seed):
+        nat.check(nat.lib.at2_hb_tables_build(C.byref(spec.plan), C.byref(spec.cfg), 0, host_tab.data_ptr()))
+        spec._tables[(str(dev), torch.float32)] = host_tab.to(dev, non_blocking=True)
+        res = run_epdf_ofe(spec, n_total, seed, start=KDE_START, end=KDE_END, bandwidth=KDE_H, grid_points=KDE_G,
+                           device=dev)
+        host_ofe.copy_(res['ofes'], non_blocking=True)
+        host_den.copy_(res['density'], non_blocking=True)
+        torch.cuda.synchronize(dev)
+        return host_den[0].item()
+
+    for i in range(min(args.warmup, 3)):
+        e2e_step(5000 + i)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(6000 + i)
+    barrier()
+    w1 = time.perf_counter()
+    e2e_s = w1 - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = t.item()
+    e2e_value = n_total * args.steps / e2e_s
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        achieved_tflops = n_local * ARM_EPOCHS * FLOP_PER_ARM_EPOCH / (sim_ms * 1e-3) / 1e12
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'reps_per_gpu_per_step': n_local, 'arms_per_rep': ARMS,
+                       'arm_epochs_per_rep': ARM_EPOCHS, 'kde': 'epanechnikov h=0.1 on linspace(0.37,1.5,1000)',
+                       'parallelism': f'repetition-sharded x{world}, one all-gather of OFEs',
+                       'l2': 'no HBM inputs (Philox RNG in-kernel); per-step outputs 1.2 MB; seed changes every step'},
+            'arm_epochs_per_s': value * ARM_EPOCHS,
+            'clocks': sampler.summary(t0, t1),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(nbytes),
+                    'd2h_bytes_per_step': int(4 * n_total + 4 * KDE_G)},
+            'gpu_launches': launches,
+            'roofline': {'kernel': 'hb_sim_kernel<float,PHILOX> (fused simulation + successive halving)',
+                         'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
+                         'frac': achieved_tflops / fma_peak_tflops, 'traffic': None,
+                         'peak_source': 'FFMA micro-benchmark measured in this run (at2_fma_peak_probe); nominal '
+                                        '148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s',
+                         'kernel_ms': sim_ms, 'algorithmic_flop_per_launch': n_local * ARM_EPOCHS * FLOP_PER_ARM_EPOCH,
+                         'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_source': peak_src},
+        }
+        if cpu_baseline is not None:
+            line['cpu_baseline'] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -146,6 +146,18 @@ int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_config* cfg, con
                             const float* d_f1, const float* d_fn, const int32_t* d_family, const float* d_gamma,
                             const float* d_xy, const at2_hb_outputs* out, void* stream);
 
+/* ---- (e): EPDF-OFE kernel density estimate ----------------------------------------------------------------------- */
+
+#define AT2_KDE_EPANECHNIKOV 0   /* the reference's kernel (plot_results.py:13) */
+#define AT2_KDE_GAUSSIAN 1       /* extra */
+
+/* Density of the n samples d_x on the G-point grid linspace(start, end, G) with the given bandwidth:
+ * replaces sklearn's KernelDensity(kernel='epanechnikov', bandwidth).fit(x) + exp(score_samples(grid))
+ * (experiments/simulation_evaluation/plot_results.py:11-17).  d_workspace: at2_kde_workspace_floats(n, G) floats. */
+int64_t at2_kde_workspace_floats(int64_t n, int32_t G);
+int at2_kde_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
+                float* d_density, float* d_workspace, int64_t workspace_floats, void* stream);
+
 /* Number of kernel launches the last at2_* call on this thread enqueued (for bench.py's gpu_launches). */
 int32_t at2_last_launch_count(void);
 

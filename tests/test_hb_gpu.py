@@ -21,12 +21,8 @@ def _spec(cfg):
 
 def _host_f1_fn(cfg, rep):
     """f_1 / f_n per arm in float64 with the product's own host functions (no oracle involved)."""
-    from autotune.benchmarks.opt_function_problem import NOISE_FREE_FUNCTIONS
-    fams = np.asarray([[f[4], f[5]] for f in cfg['families']], np.float64)
-    f = NOISE_FREE_FUNCTIONS[cfg['func']](rep['xy'][:, 0], rep['xy'][:, 1])
-    f_n = f - fams[rep['fam'], 1]
-    f_1 = (f + cfg['noise'] * rep['z'] * 1) - fams[rep['fam'], 0]
-    return f_1, f_n
+    from autotune.b200.engine import host_start_and_target
+    return host_start_and_target(_spec(cfg), rep['xy'], rep['fam'], rep['z'])
 
 
 def _run_predrawn(cfg, reps, dtype):
