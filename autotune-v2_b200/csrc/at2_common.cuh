@@ -31,18 +31,21 @@ void at2_reset_launch_count();
     } while (0)
 
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
-// gam[t]   t in [0,R): {d, c, d*log2(e), d*scale}     Marsaglia-Tsang constants of step t (entry 0 unused)
-// pw[f][t] f in [0,F), t in [0,R): {P, P11}           (t/(R-1))**nec and (t/(R-1))**(1.1*nec)
-// sg[t][c] t in [0,R), c in [0,sg_stride)             Savitzky-Golay weight of raw[t] in the smoothed value at
-//                                                      checkpoint c (present only when some family is smooth)
+// rec[f][t] f in [0,F), t in [0,R]: 8 reals {d, c, d*log2(e), d*scale, P, P11, 0, 0}
+//          Marsaglia-Tsang constants of the Gamma draw of step t and the two time-aggressiveness powers
+//          (t/(R-1))**nec, (t/(R-1))**(1.1*nec) of family f - one 32-byte (float) record per (family, step), so a lane
+//          fetches everything step t needs from one address.  Row 0 is unused; row R is a sentinel whose c is NaN, so
+//          the acceptance test of a finished lane can never pass and no bounds check is needed in the inner loop.
+// sg[t][c]  t in [0,R], c in [0,sg_stride): Savitzky-Golay weight of raw[t] in the smoothed value at checkpoint c
+//          (present only when some family is smooth; row R is zero).
+#define AT2_REC 8
 __host__ __device__ inline int at2_sg_stride(int n_ckpts) { return n_ckpts <= 4 ? 4 : (n_ckpts <= 8 ? 8 : 16); }
 
 struct At2TableLayout {
     int R, F, has_smooth, sg_stride;
-    __host__ __device__ int off_gam() const { return 0; }
-    __host__ __device__ int off_pw() const { return 4 * R; }
-    __host__ __device__ int off_sg() const { return 4 * R + 2 * F * R; }
-    __host__ __device__ int total() const { return 4 * R + 2 * F * R + (has_smooth ? sg_stride * R : 0); }
+    __host__ __device__ int off_rec() const { return 0; }
+    __host__ __device__ int off_sg() const { return AT2_REC * F * (R + 1); }   // 32-byte aligned
+    __host__ __device__ int total() const { return off_sg() + (has_smooth ? sg_stride * (R + 1) : 0); }
 };
 
 static inline int at2_cfg_has_smooth(const at2_sim_config* cfg) {

@@ -220,7 +220,8 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
     At2TableLayout L{R, F, at2_cfg_has_smooth(cfg), at2_sg_stride(plan->n_ckpts)};
     for (int i = 0; i < L.total(); ++i) out[i] = (T)0;
     const double k = 2.0;  // simulation_evaluator.py:94
-    T* gam = out + L.off_gam();
+    T* rec = out + L.off_rec();
+    const int rows = R + 1;
     for (int t = 1; t < R; ++t) {
         const double m = (double)((R + 1) - t);                 // n - time with n = R + 1 (:98)
         const double root = sqrt(k * k + 4 * m);                // :37
@@ -229,18 +230,21 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
         const double scale = 1 / beta;                          // :42
         const double d = alpha - 1.0 / 3.0;                     // Marsaglia & Tsang (2000)
         const double c = 1.0 / sqrt(9.0 * d);
-        gam[4 * t + 0] = (T)d;
-        gam[4 * t + 1] = (T)c;
-        gam[4 * t + 2] = (T)(d * 1.4426950408889634);
-        gam[4 * t + 3] = (T)(d * scale);
-    }
-    T* pw = out + L.off_pw();
-    for (int f = 0; f < F; ++f)
-        for (int t = 1; t < R; ++t) {
-            const double frac = (double)t / (double)(R - 1);
-            pw[2 * (f * R + t) + 0] = (T)pow(frac, cfg->fam[f].nec_agg);          // :105
-            pw[2 * (f * R + t) + 1] = (T)pow(frac, 1.1 * cfg->fam[f].nec_agg);    // :112
+        const double frac = (double)t / (double)(R - 1);
+        for (int f = 0; f < F; ++f) {
+            T* row = rec + (size_t)AT2_REC * (f * rows + t);
+            row[0] = (T)d;
+            row[1] = (T)c;
+            row[2] = (T)(d * 1.4426950408889634);
+            row[3] = (T)(d * scale);
+            row[4] = (T)pow(frac, cfg->fam[f].nec_agg);          // :105
+            row[5] = (T)pow(frac, 1.1 * cfg->fam[f].nec_agg);    // :112
         }
+    }
+    for (int f = 0; f < F; ++f) {   // sentinel row R: NaN slope -> the acceptance test can never pass
+        T* row = rec + (size_t)AT2_REC * (f * rows + R);
+        row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)1.4426950408889634, row[3] = (T)1, row[4] = (T)1, row[5] = (T)1;
+    }
     if (L.has_smooth) {
         int32_t rows[AT2_MAX_CKPTS];
         for (int c = 0; c < plan->n_ckpts; ++c) rows[c] = plan->ckpt_time[c] - 1;

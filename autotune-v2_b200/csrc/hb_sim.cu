@@ -77,13 +77,13 @@ __device__ __forceinline__ float fast_cos(float x) {
     return r;
 }
 
-__device__ __forceinline__ float step_fast(float f, float g, int t, int R, float fn, float mlc, float upc, float P,
-                                           float P11) {
+__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11) {
+    // production arithmetic of simulation_evaluator.py:99-115; at the last step P = P11 = 1 so both branches land on
+    // f_n to within one rounding (the reference's float64 path has the same property on its down branch)
     const float ml = fmaf((g - 2.0f) * mlc, fn - f, f);
     const float dn = fmaf(fn - ml, P, ml);
     const float up = fmaf(upc, fast_rcp(1.0f + g), f);
-    float un = fmaf(fn - up, P11, up);
-    un = (R - t == 1) ? fn : un;
+    const float un = fmaf(fn - up, P11, up);
     return g > 2.0f ? dn : (g < 2.0f ? un : f);
 }
 
@@ -186,11 +186,13 @@ __device__ void warp_bitonic_smem(K* keys, int npad, int lane) {
     }
 }
 
-// ascending bitonic network over 32 keys, one per lane, warp shuffles only
+// ascending bitonic network over the first `n` (<= 32) keys, one per lane, warp shuffles only; lanes >= n hold pads.
+// Only the stages of the smallest power-of-two network covering n are executed (n is warp-uniform).
 template <typename K>
-__device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane) {
+__device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane, int n) {
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
+        if ((k >> 1) >= n) break;
 #pragma unroll
         for (int j = k >> 1; j > 0; j >>= 1) {
             const K other = mine.shfl_xor(j);
@@ -213,10 +215,13 @@ struct Params {
     const T* tables;
     long long n_reps, rep_offset;
     uint32_t key0, key1;
-    int G;        // repetitions per tile
-    int n_tiles;
-    int npad;     // power of two >= widest bracket
-    int stride;   // G * n_arms rounded up to 32
+    int G;            // repetitions per tile
+    long long n_tiles;
+    int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
+    int n_teams;      // teams per CTA
+    int npad;         // power of two >= widest bracket
+    int stride;       // G * n_arms rounded up to 32
+    int team_bytes;   // shared-memory bytes per team
     // pre-drawn inputs
     const T* f1;
     const T* fn;
@@ -233,143 +238,216 @@ struct Params {
     T* ckpt_loss;
 };
 
-template <typename T, int MODE, bool HAS_SMOOTH, int CK, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ Params<T> p) {
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void team_barrier(int team, int team_warps) {
+    if (team_warps == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_warps * 32) : "memory");
+}
+
+// arm draw of the Philox path: x, y uniform on the domain (core/params.py:36), family
+// (core/shape_family_scheduler.py:61,75), z ~ N(0,1) for the initial noise (benchmarks/opt_function_problem.py:138)
+struct ArmDraw {
+    float x, y, z;
+    int fam;
+};
+template <typename T>
+__device__ __forceinline__ ArmDraw draw_arm(const Params<T>& p, unsigned long long gid, int arm) {
+    const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
+    ArmDraw d;
+    d.x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, p.x_rng, p.x_min);
+    d.y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, p.y_rng, p.y_min);
+    d.fam = p.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)p.F) : arm % p.F;
+    const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+    const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
+    d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+    return d;
+}
+
+template <typename T, int MODE, bool HAS_SMOOTH, int CK>
+__global__ void __launch_bounds__(256) hb_sim_kernel(const __grid_constant__ Params<T> p) {
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.F;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
-    T* s_tab = reinterpret_cast<T*>(smem_raw);
     const int tab_elems = (L.total() + 3) & ~3;
-    T* s_ck = s_tab + tab_elems;                                    // [C][stride]
-    T* s_xy = s_ck + (size_t)C * p.stride;                          // [2][stride]  (x, y of every arm)
-    K* s_keys = reinterpret_cast<K*>(s_xy + 2 * (size_t)p.stride);  // [nwarps][npad]
-    const int nwarps = BLOCK / 32;
-    int* s_ids = reinterpret_cast<int*>(s_keys + (size_t)nwarps * p.npad);  // [nwarps][2][npad]
+    T* s_tab = reinterpret_cast<T*>(smem_raw);
+    int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4] positions, then INT_MAX
+    unsigned char* team_base = reinterpret_cast<unsigned char*>(s_ckpos + AT2_MAX_CKPTS + 4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < L.total(); i += BLOCK) s_tab[i] = p.tables[i];
+    const int team = warp / p.team_warps, wteam = warp - team * p.team_warps;
+    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
-    const T* s_gam = s_tab + L.off_gam();
-    const T* s_pw = s_tab + L.off_pw();
+    const T* s_rec = s_tab + L.off_rec();
     const T* s_sg = s_tab + L.off_sg();
 
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const long long rep0 = (long long)tile * p.G;
+    unsigned char* my_team = team_base + (size_t)team * p.team_bytes;
+    T* s_ck = reinterpret_cast<T*>(my_team);                                          // [C][stride]
+    K* keys = reinterpret_cast<K*>(s_ck + (size_t)C * p.stride) + (size_t)wteam * p.npad;   // [team_warps][npad]
+    unsigned short* ids_a = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride) +
+                                                              (size_t)p.team_warps * p.npad) + (size_t)wteam * 2 * p.npad;
+    unsigned short* ids_b = ids_a + p.npad;
+    const bool desc = p.descending != 0;
+
+    const long long team_global = (long long)blockIdx.x * p.n_teams + team;
+    const long long team_stride = (long long)gridDim.x * p.n_teams;
+    for (long long tile = team_global; tile < p.n_tiles; tile += team_stride) {
+        const long long rep0 = tile * p.G;
         const int g_eff = (int)min((long long)p.G, p.n_reps - rep0);
         const int n_items = g_eff * A;
 
         // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
-        for (int base = warp * 32; base < n_items; base += BLOCK) {
+        for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
             const int i = base + lane;
             const bool active = i < n_items;
             const int ii = active ? i : 0;
             const int rep_l = ii / A, arm = ii - rep_l * A;
             const long long rep_g = rep0 + rep_l;                   // index into per-call arrays
             const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + arm;
-            T f1, fn, ax = (T)0, ay = (T)0;
+            T f1, fn;
             int fam_i;
             if constexpr (MODE == MODE_PHILOX) {
-                // arm draw: x, y uniform on the domain (params.py:36), family (shape_family_scheduler.py:61,75),
-                // z ~ N(0,1) for the initial noise (opt_function_problem.py:138)
-                const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
-                const float x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, p.x_rng, p.x_min);
-                const float y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, p.y_rng, p.y_min);
-                fam_i = p.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)F) : arm % F;
-                const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-                const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
-                const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
-                const float f = base_function(p.func, x, y);
-                fn = (T)(f - (float)p.fam[fam_i].s1);               // opt_function_simulation_problem.py:63
-                f1 = (T)((f + p.noise * z) - (float)p.fam[fam_i].s0);  // :62,:64
-                ax = (T)x, ay = (T)y;
+                const ArmDraw d = draw_arm(p, gid, arm);
+                fam_i = d.fam;
+                const float f = base_function(p.func, d.x, d.y);
+                fn = (T)(f - (float)p.fam[fam_i].s1);                       // opt_function_simulation_problem.py:63
+                f1 = (T)((f + p.noise * d.z) - (float)p.fam[fam_i].s0);     // :62,:64
             } else {
                 const long long a_g = rep_g * A + arm;
                 f1 = active ? p.f1[a_g] : (T)0;
                 fn = active ? p.fn[a_g] : (T)0;
                 fam_i = active ? p.family[a_g] : 0;
-                if (p.xy != nullptr && active) ax = p.xy[2 * a_g], ay = p.xy[2 * a_g + 1];
             }
             const Fam<T> fam = p.fam[fam_i];
             const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-            if (active) s_xy[ii] = ax, s_xy[p.stride + ii] = ay;
 
             T f = f1;
-            int t = 1;   // next trajectory position to produce (0-based: f is fs[t-1])
-            int nc = 0;  // next checkpoint to capture (non-smooth arms)
-            int next_pos = p.plan.ckpt_time[0] - 1;
+            int t = active ? 1 : R;   // next trajectory position to produce (0-based: f is fs[t-1]); R = finished
+            int nc = 0;               // next checkpoint to capture (raw arms; smooth arms never capture)
+            int next_pos = (smooth || !active) ? INT_MAX : s_ckpos[0];   // padding lanes never capture
             T acc[CK];
 #pragma unroll
             for (int c = 0; c < CK; ++c) acc[c] = HAS_SMOOTH ? s_sg[c] * f : (T)0;  // sg[0][c] * fs[0]
-            if (active && !smooth && next_pos == 0) {
+            if (active && next_pos == 0) {
                 s_ck[ii] = f;
                 nc = 1;
-                next_pos = C > 1 ? p.plan.ckpt_time[1] - 1 : INT_MAX;
+                next_pos = s_ckpos[1];
             }
-
-            // bookkeeping after fs[t] has been produced
-            auto commit = [&](T fnew) {
-                f = fnew;
-                if (HAS_SMOOTH) {
-                    if (smooth) {
-#pragma unroll
-                        for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[t * L.sg_stride + c], f, acc[c]);
-                    }
-                }
-                if (!smooth && t == next_pos) {
-                    s_ck[nc * p.stride + ii] = f;
-                    ++nc;
-                    next_pos = nc < C ? p.plan.ckpt_time[nc] - 1 : INT_MAX;
-                }
-                ++t;
-            };
 
             if constexpr (MODE == MODE_PREDRAWN) {
                 const T* grow = p.gamma + (rep_g * A + arm) * (long long)(R - 1);
                 for (int tt = 1; tt < R; ++tt) {
                     if (!active) break;
                     const T g = grow[tt - 1];
-                    const T P = s_pw[2 * (fam.pw_off + tt)], P11 = s_pw[2 * (fam.pw_off + tt) + 1];
-                    T fnew;
+                    const T P = s_rec[AT2_REC * (fam.pw_off + tt) + 4], P11 = s_rec[AT2_REC * (fam.pw_off + tt) + 5];
                     if constexpr (sizeof(T) == 8)
-                        fnew = (T)step_exact((double)f, (double)g, tt, R, (double)fn, (double)fam.ml, (double)fam.up,
-                                             (double)P, (double)P11);
+                        f = (T)step_exact((double)f, (double)g, tt, R, (double)fn, (double)fam.ml, (double)fam.up,
+                                          (double)P, (double)P11);
                     else
-                        fnew = (T)step_fast((float)f, (float)g, tt, R, (float)fn, (float)fam.ml, (float)fam.up,
-                                            (float)P, (float)P11);
-                    commit(fnew);
+                        f = (T)step_fast((float)f, (float)g, (float)fn, (float)fam.ml, (float)fam.up, (float)P,
+                                         (float)P11);
+                    if (HAS_SMOOTH && smooth) {
+#pragma unroll
+                        for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[tt * L.sg_stride + c], f, acc[c]);
+                    }
+                    if (tt == next_pos) {
+                        s_ck[nc * p.stride + ii] = f;
+                        ++nc;
+                        next_pos = s_ckpos[nc];
+                    }
                 }
             } else {
-                // one Philox block = 2 normals + 2 uniforms = 2 Marsaglia-Tsang attempts
-                const float4* gam4 = reinterpret_cast<const float4*>(s_gam);
-                const float2* pw2 = reinterpret_cast<const float2*>(s_pw) + fam.pw_off;
+                // One Philox block = 2 normals (Box-Muller) + 2 uniforms = 2 Marsaglia-Tsang attempts.  A lane's epoch
+                // is the shared-memory address of its (family, step) record: an accepted attempt advances it by one
+                // record, a rejected one leaves it, a finished (or padding) lane sits on the sentinel record whose NaN
+                // slope fails every acceptance test - so the attempt is branch-free and needs no bounds check.  The
+                // rare checkpoint capture is tested once per Philox block.  The next block is issued before the
+                // current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
+                uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(s_rec) + (uint32_t)fam.pw_off * (AT2_REC * 4u);
+                uint32_t sg_base = (uint32_t)__cvta_generic_to_shared(s_sg);
+                uint32_t k0 = p.key0, k1 = p.key1;
+                asm volatile("" : "+r"(rec_base), "+r"(sg_base), "+r"(k0), "+r"(k1));   // keep them in registers
+                const uint32_t end_addr = rec_base + (uint32_t)R * (AT2_REC * 4u);
+                uint32_t addr = rec_base + (uint32_t)t * (AT2_REC * 4u);       // record of the step to produce next
+                uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
                 const float fnf = (float)fn, mlc = (float)fam.ml, upc = (float)fam.up;
-                uint32_t ctr = 0;
+                float ff = (float)f;
+                const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
                 auto attempt = [&](float x, float u) {
-                    const bool live = active && t < R;
-                    const int tt = live ? t : 1;
-                    const float4 gm = gam4[tt];                     // d, c, d*log2e, d*scale
+                    const float4 gm = lds128(addr);                               // d, c, d*log2e, d*scale
+                    const float2 pw = lds64(addr + 16u);                          // P, P11
                     const float v = fmaf(gm.y, x, 1.0f);
                     const float v3 = v * v * v;
                     // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
                     const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-                    const bool ok = live && v > 0.0f && fast_lg2(u) < rhs;
-                    const float g = gm.w * v3;
-                    const float2 pw = pw2[tt];
-                    const float fnew = step_fast((float)f, g, tt, R, fnf, mlc, upc, pw.x, pw.y);
-                    if (ok) commit((T)fnew);
+                    const bool ok = v > 0.0f && fast_lg2(u) < rhs;
+                    const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y);
+                    ff = ok ? fnew : ff;
+                    if constexpr (HAS_SMOOTH) {
+                        const float fs = (ok && smooth) ? ff : 0.0f;
+                        const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(L.sg_stride * 4);
+                        if constexpr (CK <= 4) {
+                            const float4 w = lds128(a);
+                            acc[0] = fmaf(w.x, fs, acc[0]), acc[1] = fmaf(w.y, fs, acc[1]);
+                            acc[2] = fmaf(w.z, fs, acc[2]), acc[3] = fmaf(w.w, fs, acc[3]);
+                        } else {
+#pragma unroll
+                            for (int c4 = 0; c4 < CK; c4 += 4) {
+                                const float4 w = lds128(a + c4 * 4u);
+                                acc[c4] = fmaf(w.x, fs, acc[c4]);
+                                if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
+                                if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
+                                if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
+                            }
+                        }
+                    }
+                    addr += ok ? (AT2_REC * 4u) : 0u;
                 };
-                while (__any_sync(0xffffffffu, active && t < R)) {
-                    const At2U4 r = at2_philox10(At2U4{ctr, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_TRAJ}, p.key0, p.key1);
-                    ++ctr;
+                auto consume = [&](const At2U4& r) {
                     const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
                     const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                     // sqrt(-2 ln u1)
                     const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;                       // [-pi, pi)
                     const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));                    // (0,1]
                     const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
                     attempt(rad * fast_cos(ang), ua);
+                    const float f_mid = ff;
+                    const uint32_t addr_mid = addr;
                     attempt(rad * fast_sin(ang), ub);
+                    // checkpoint capture (raw arms): position cap was produced by the first attempt if the epoch had
+                    // already moved past it in between, by the second otherwise
+                    while (addr > cap_addr) {
+                        s_ck[nc * p.stride + ii] = (T)(addr_mid > cap_addr ? f_mid : ff);
+                        ++nc;
+                        const int np = s_ckpos[nc];
+                        cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
+                    }
+                };
+                uint32_t ctr = 1;
+                At2U4 ra = at2_philox10(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1), rb;
+                while (true) {
+                    if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+                    rb = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+                    ++ctr;
+                    consume(ra);
+                    if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+                    ra = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+                    ++ctr;
+                    consume(rb);
                 }
+                t = R;
+                f = (T)ff;
             }
             if (HAS_SMOOTH) {
                 if (active && smooth) {
@@ -379,21 +457,17 @@ __global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ P
                 }
             }
         }
-        __syncthreads();
+        team_barrier(team, p.team_warps);
 
         if (p.ckpt_loss != nullptr) {
-            for (int i = tid; i < n_items * C; i += BLOCK) {
+            for (int i = wteam * 32 + lane; i < n_items * C; i += p.team_warps * 32) {
                 const int a = i / C, c = i - a * C;
                 p.ckpt_loss[(rep0 * A + a) * C + c] = s_ck[c * p.stride + a];
             }
         }
 
         // ---------------- phase 2: successive halving, one warp per repetition ----------------
-        K* keys = s_keys + (size_t)warp * p.npad;
-        int* ids_a = s_ids + (size_t)warp * 2 * p.npad;
-        int* ids_b = ids_a + p.npad;
-        const bool desc = p.descending != 0;
-        for (int rep_l = warp; rep_l < g_eff; rep_l += nwarps) {
+        for (int rep_l = wteam; rep_l < g_eff; rep_l += p.team_warps) {
             const long long rep_g = rep0 + rep_l;
             const int arm0 = rep_l * A;
             T best = (T)0;
@@ -402,13 +476,13 @@ __global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ P
             for (int b = 0; b < p.plan.n_brackets; ++b) {
                 int n_cur = p.plan.bracket_n[b];
                 const int first = p.plan.bracket_first_arm[b];
-                for (int j = lane; j < n_cur; j += 32) ids_a[j] = first + j;
-                __syncwarp();
-                int* ids = ids_a;
-                int* ids_next = ids_b;
+                unsigned short* ids = ids_a;
+                unsigned short* ids_next = ids_b;
                 for (int rd = p.plan.bracket_first_round[b]; rd < p.plan.bracket_first_round[b + 1]; ++rd) {
                     const int c = p.plan.round_ckpt[rd];
                     const int keep = min(p.plan.round_keep[rd], n_cur);
+                    const bool first_round = rd == p.plan.bracket_first_round[b];
+                    const T* col = s_ck + c * p.stride + arm0;
                     T rb_loss;
                     int rb_arm;
                     if (n_cur <= 32) {
@@ -416,32 +490,38 @@ __global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ P
                         T my_loss = (T)0;
                         int my_id = 0;
                         if (lane < n_cur) {
-                            my_id = ids[lane];
-                            my_loss = s_ck[c * p.stride + arm0 + my_id];
+                            my_id = first_round ? first + lane : (int)ids[lane];
+                            my_loss = col[my_id];
                             mine = K::make(my_loss, lane, desc);
                         }
-                        mine = warp_bitonic_shfl(mine, lane);
+                        mine = warp_bitonic_shfl(mine, lane, n_cur);
                         const int src = mine.pos() & 31;            // lane that held the key now ranked `lane`
                         const int sid = __shfl_sync(0xffffffffu, my_id, src);
                         const T sl = __shfl_sync(0xffffffffu, my_loss, src);
                         rb_loss = __shfl_sync(0xffffffffu, sl, 0);
                         rb_arm = __shfl_sync(0xffffffffu, sid, 0);
-                        __syncwarp();
-                        if (lane < keep) ids_next[lane] = sid;
+                        if (lane < keep) ids_next[lane] = (unsigned short)sid;
                     } else {
                         int npad = 64;
                         while (npad < n_cur) npad <<= 1;
-                        for (int j = lane; j < npad; j += 32)
-                            keys[j] = j < n_cur ? K::make(s_ck[c * p.stride + arm0 + ids[j]], j, desc) : K::pad();
+                        for (int j = lane; j < npad; j += 32) {
+                            const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+                            keys[j] = j < n_cur ? K::make(col[id], j, desc) : K::pad();
+                        }
                         __syncwarp();
                         warp_bitonic_smem(keys, npad, lane);
-                        for (int j = lane; j < keep; j += 32) ids_next[j] = ids[keys[j].pos()];
-                        rb_arm = ids[keys[0].pos()];
-                        rb_loss = s_ck[c * p.stride + arm0 + rb_arm];
+                        for (int j = lane; j < keep; j += 32) {
+                            const int pos = keys[j].pos();
+                            ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+                        }
+                        const int pos0 = keys[0].pos();
+                        rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+                        rb_loss = col[rb_arm];
                     }
                     __syncwarp();
                     if (p.survivors != nullptr)
-                        for (int j = lane; j < keep; j += 32) p.survivors[rep_g * p.plan.n_surv + surv_w + j] = ids_next[j];
+                        for (int j = lane; j < keep; j += 32)
+                            p.survivors[rep_g * p.plan.n_surv + surv_w + j] = (int)ids_next[j];
                     surv_w += keep;
                     if (lane == 0) {
                         if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = rb_loss;
@@ -449,7 +529,7 @@ __global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ P
                     }
                     // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
                     if (best_arm < 0 || (desc ? rb_loss > best : rb_loss < best)) best = rb_loss, best_arm = rb_arm;
-                    int* tmp = ids;
+                    unsigned short* tmp = ids;
                     ids = ids_next;
                     ids_next = tmp;
                     n_cur = keep;
@@ -460,81 +540,106 @@ __global__ void __launch_bounds__(BLOCK) hb_sim_kernel(const __grid_constant__ P
                 if (p.ofe != nullptr) p.ofe[rep_g] = best;
                 if (p.ofe_arm != nullptr) p.ofe_arm[rep_g] = best_arm;
                 if (p.best_xy != nullptr) {
-                    p.best_xy[2 * rep_g] = s_xy[arm0 + best_arm];
-                    p.best_xy[2 * rep_g + 1] = s_xy[p.stride + arm0 + best_arm];
+                    if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
+                        const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm;
+                        const ArmDraw d = draw_arm(p, gid, best_arm);
+                        p.best_xy[2 * rep_g] = (T)d.x, p.best_xy[2 * rep_g + 1] = (T)d.y;
+                    } else {
+                        const long long a_g = rep_g * A + best_arm;
+                        p.best_xy[2 * rep_g] = p.xy != nullptr ? p.xy[2 * a_g] : (T)0;
+                        p.best_xy[2 * rep_g + 1] = p.xy != nullptr ? p.xy[2 * a_g + 1] : (T)0;
+                    }
                 }
             }
         }
-        __syncthreads();
+        team_barrier(team, p.team_warps);
     }
 }
 
 // ---- launch plumbing ---------------------------------------------------------------------------------------------------
 template <typename T>
 struct LaunchCfg {
-    int G, block, grid, npad, stride;
+    int G, team_warps, n_teams, block, grid, npad, stride, team_bytes;
     size_t smem;
 };
 
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v != nullptr && atoi(v) > 0) ? atoi(v) : dflt;
+}
+
 template <typename T>
-int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, int mode, LaunchCfg<T>* out) {
+int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, LaunchCfg<T>* out) {
     typedef typename KeyOf<T>::type K;
     const int A = plan->n_arms, C = plan->n_ckpts, R = plan->R;
     int widest = 0;
     for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
     int npad = 64;
     while (npad < widest) npad <<= 1;
-    const int block = 128;
-    const int nwarps = block / 32;
     At2TableLayout L{R, F, has_smooth, at2_sg_stride(C)};
-    const size_t tab = (size_t)((L.total() + 3) & ~3) * sizeof(T);
-    const size_t sort_scratch = (size_t)nwarps * npad * (sizeof(K) + 2 * sizeof(int));
+    const size_t fixed = (size_t)((L.total() + 3) & ~3) * sizeof(T) + (AT2_MAX_CKPTS + 4) * sizeof(int);
+    const size_t sort_per_warp = (size_t)npad * (sizeof(K) + 2 * sizeof(unsigned short));
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // per-repetition shared memory: C checkpoint losses + (x, y) per arm
-    const size_t per_rep = (size_t)A * (C + 2) * sizeof(T);
-    // target <= ~36 KB per CTA (>= 6 CTAs / SM); among feasible G pick the best lane-packing efficiency
-    const size_t budget = 40 * 1024;
-    int best_g = 1;
-    double best_eff = -1.0;
-    const char* env_g = getenv("AT2_HB_REPS_PER_CTA");
-    for (int g = 1; g <= 64; ++g) {
-        const size_t need = tab + sort_scratch + per_rep * g + 32 * (C + 2) * sizeof(T);
-        if (g > 1 && need > budget) break;
-        const int items = g * A;
-        const int passes = (items + block - 1) / block;
-        double eff = (double)items / ((double)passes * block);
-        // the halving phase wants at least one repetition per warp
-        if (g % nwarps != 0) eff -= 0.02;
-        if (eff > best_eff + 1e-9) best_eff = eff, best_g = g;
+    // A team of `tw` warps owns tiles of G repetitions.  Pick (tw, G): every warp of the team gets the same number
+    // of 32-arm groups, lanes are well packed, and the team's shared memory stays small enough for >= ~32 resident
+    // warps per SM.  Small problems end up with tw = 1: warp-private tiles and no block-level barrier at all.
+    const size_t per_warp_budget = 9 * 1024;
+    int best_tw = 1, best_g = 1;
+    double best_score = -1.0;
+    for (int tw = 1; tw <= 8; tw *= 2) {
+        for (int g = 1; g <= 64; ++g) {
+            const int items = g * A;
+            const int groups = (items + 31) / 32;
+            const int per_warp = (groups + tw - 1) / tw;
+            const double packing = (double)items / ((double)per_warp * tw * 32);
+            const int stride = (items + 31) & ~31;
+            const size_t team_bytes = (size_t)C * stride * sizeof(T) + tw * sort_per_warp;
+            if (team_bytes > per_warp_budget * tw && !(tw == 8 && g == 1)) continue;
+            // halving wants at least one repetition per warp of the team
+            const double sh_balance = (double)g / ((double)((g + tw - 1) / tw) * tw);
+            const double score = packing * (0.9 + 0.1 * sh_balance) - 0.002 * tw;
+            if (score > best_score + 1e-9) best_score = score, best_tw = tw, best_g = g;
+        }
     }
-    if (env_g != nullptr && atoi(env_g) > 0) best_g = atoi(env_g);
+    if (best_score < 0) best_tw = 8, best_g = 1;
+    best_tw = env_int("AT2_HB_TEAM_WARPS", best_tw);
+    best_g = env_int("AT2_HB_REPS_PER_TILE", best_g);
     if ((long long)best_g > n_reps) best_g = (int)n_reps;
     const int stride = (best_g * A + 31) & ~31;
-    const size_t smem = tab + (size_t)(C + 2) * stride * sizeof(T) + sort_scratch;
+    size_t team_bytes = (size_t)C * stride * sizeof(T) + best_tw * sort_per_warp;
+    team_bytes = (team_bytes + 15) & ~(size_t)15;
+    int warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", 8);
+    if (warps_per_cta < best_tw) warps_per_cta = best_tw;
+    if (warps_per_cta > 8) warps_per_cta = 8;
+    int n_teams = warps_per_cta / best_tw;
+    const long long n_tiles = (n_reps + best_g - 1) / best_g;
+    while (n_teams > 1 && (fixed + n_teams * team_bytes > (size_t)max_smem || (long long)(n_teams - 1) * sms >= n_tiles)) --n_teams;
+    const size_t smem = fixed + n_teams * team_bytes;
     if (smem > (size_t)max_smem) {
         at2_set_error("hyperband simulation needs %zu B of shared memory per CTA (R=%d, %d arms, %d checkpoints); device limit %d B",
                       smem, R, A, C, max_smem);
         return AT2_ELIMIT;
     }
-    const long long n_tiles = (n_reps + best_g - 1) / best_g;
-    // resident CTAs per SM by shared memory (228 KB per SM, 1 KB reserved per CTA), capped by 16 warps-worth of CTAs
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
+    const int max_by_threads = 2048 / (n_teams * best_tw * 32);
+    if (per_sm > max_by_threads) per_sm = max_by_threads;
     long long grid = (long long)sms * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    out->G = best_g, out->block = block, out->grid = (int)grid, out->npad = npad, out->stride = stride, out->smem = smem;
-    (void)mode;
+    const long long ctas_needed = (n_tiles + n_teams - 1) / n_teams;
+    if (grid > ctas_needed) grid = ctas_needed;
+    out->G = best_g, out->team_warps = best_tw, out->n_teams = n_teams, out->block = n_teams * best_tw * 32;
+    out->grid = (int)grid, out->npad = npad, out->stride = stride, out->team_bytes = (int)team_bytes, out->smem = smem;
     return AT2_OK;
 }
 
 template <typename T, int MODE, bool HS, int CK>
 int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
-    auto kern = hb_sim_kernel<T, MODE, HS, CK, 128>;
+    auto kern = hb_sim_kernel<T, MODE, HS, CK>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<lc.grid, lc.block, lc.smem, st>>>(p);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
@@ -553,11 +658,12 @@ int launch_dispatch(const Params<T>& p, const LaunchCfg<T>& lc, int has_smooth, 
 
 template <typename T>
 int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, long long n_reps,
-                const at2_hb_outputs* out, Params<T>* p, LaunchCfg<T>* lc, int mode) {
+                const at2_hb_outputs* out, Params<T>* p, LaunchCfg<T>* lc) {
     AT2_REQUIRE(plan && cfg && d_tables && out, "at2_hb_sim: NULL plan/config/tables/outputs");
     AT2_REQUIRE(n_reps > 0, "at2_hb_sim: n_reps must be positive (got %lld)", n_reps);
     AT2_REQUIRE(plan->n_arms > 0 && plan->n_rounds > 0 && plan->n_ckpts > 0 && plan->n_ckpts <= AT2_MAX_CKPTS,
                 "at2_hb_sim: plan is empty or malformed");
+    AT2_REQUIRE(plan->n_arms < 65536, "at2_hb_sim: more than 65535 arms per repetition");
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_hb_sim: n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
     AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_hb_sim: unknown func id %d", cfg->func);
@@ -571,7 +677,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
         p->fam[f].s0 = (T)cfg->fam[f].start_shift;
         p->fam[f].s1 = (T)cfg->fam[f].end_shift;
         p->fam[f].smooth = cfg->fam[f].is_smooth;
-        p->fam[f].pw_off = f * plan->R;
+        p->fam[f].pw_off = f * (plan->R + 1);
     }
     p->func = cfg->func, p->F = cfg->n_families, p->scheduler = cfg->scheduler, p->descending = cfg->descending;
     p->x_min = (float)cfg->x_min, p->x_rng = (float)(cfg->x_max - cfg->x_min);
@@ -582,10 +688,11 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->ofe = (T*)out->d_ofe, p->ofe_arm = out->d_ofe_arm, p->best_xy = (T*)out->d_best_xy;
     p->round_best = (T*)out->d_round_best, p->round_best_arm = out->d_round_best_arm;
     p->survivors = out->d_survivors, p->ckpt_loss = (T*)out->d_ckpt_loss;
-    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, mode, lc);
+    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, lc);
     if (rc != AT2_OK) return rc;
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
-    p->n_tiles = (int)((n_reps + lc->G - 1) / lc->G);
+    p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
+    p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     return AT2_OK;
 }
 
@@ -596,7 +703,7 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
-    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PHILOX);
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
     p.rep_offset = rep_offset;
@@ -611,7 +718,7 @@ extern "C" int at2_hb_sim_predrawn_f64(const at2_plan* plan, const at2_sim_confi
     at2_reset_launch_count();
     Params<double> p = {};
     LaunchCfg<double> lc;
-    const int rc = fill_params<double>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PREDRAWN);
+    const int rc = fill_params<double>(plan, cfg, d_tables, n_reps, out, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f64: NULL input array");
     p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;
@@ -625,7 +732,7 @@ extern "C" int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_confi
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
-    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc, MODE_PREDRAWN);
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f32: NULL input array");
     p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;

@@ -112,23 +112,22 @@ def test_tables_f64_bit_exact_with_python_floats(R):
     buf = np.zeros(nbytes // 8, np.float64)
     nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 1, buf.ctypes.data))
     F = len(FAM6)
-    pw = buf[4 * R:4 * R + 2 * F * R].reshape(F, R, 2)
+    rec = buf[:8 * F * (R + 1)].reshape(F, R + 1, 8)
     for f, fam in enumerate(FAM6):
         for t in range(1, R):
-            assert pw[f, t, 0] == (t / (R - 1)) ** fam[1]            # python float pow, simulation_evaluator.py:105
-            assert pw[f, t, 1] == (t / (R - 1)) ** (1.1 * fam[1])    # :112
-    gam = buf[:4 * R].reshape(R, 4)
-    for t in range(1, R):
-        a, s = gp.gamma_shape_scale(t, R)
-        d = a - 1.0 / 3.0
-        assert gam[t, 0] == d and gam[t, 3] == d * s
+            assert rec[f, t, 4] == (t / (R - 1)) ** fam[1]            # python float pow, simulation_evaluator.py:105
+            assert rec[f, t, 5] == (t / (R - 1)) ** (1.1 * fam[1])    # :112
+            a, s = gp.gamma_shape_scale(t, R)
+            d = a - 1.0 / 3.0
+            assert rec[f, t, 0] == d and rec[f, t, 3] == d * s
+        assert np.isnan(rec[f, R, 1])                                 # sentinel row: acceptance can never pass
     # Savitzky-Golay rows at the checkpoints agree with scipy's operator to rounding
     W = gp.savgol_operator(R)
-    sg = buf[4 * R + 2 * F * R:].reshape(R, 8 if plan.n_ckpts > 4 else 4)
+    sg = buf[8 * F * (R + 1):].reshape(R + 1, 8 if plan.n_ckpts > 4 else 4)
     for c in range(plan.n_ckpts):
         row = plan.ckpt_time[c] - 1
-        assert np.max(np.abs(sg[:, c] - W[row])) < 1e-12
-    assert np.all(sg[:, plan.n_ckpts:] == 0)
+        assert np.max(np.abs(sg[:R, c] - W[row])) < 1e-12
+    assert np.all(sg[:, plan.n_ckpts:] == 0) and np.all(sg[R] == 0)
 
 
 def test_savgol_rows_all_rows_and_window_error():
