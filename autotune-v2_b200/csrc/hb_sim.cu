@@ -275,7 +275,10 @@ __device__ __forceinline__ ArmDraw draw_arm(const Params<T>& p, unsigned long lo
 }
 
 template <typename T, int MODE, bool HAS_SMOOTH, int CK>
-__global__ void __launch_bounds__(256) hb_sim_kernel(const __grid_constant__ Params<T> p) {
+#ifndef AT2_HB_MIN_BLOCKS
+#define AT2_HB_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __grid_constant__ Params<T> p) {
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.F;
