@@ -11,6 +11,7 @@ PKG_ROOT = os.path.dirname(os.path.dirname(_HERE))            # .../autotune-v2_
 LIB_PATH = os.path.join(PKG_ROOT, 'lib', 'libat2_b200.so')
 
 MAX_BRACKETS, MAX_ROUNDS, MAX_CKPTS, MAX_FAMILIES = 16, 64, 16, 8
+MAX_PARAMS = 16
 FUNC_IDS = {'egg': 0, 'branin': 1, 'camel': 2, 'wave': 3, 'rastrigin': 4}
 SCHED_UNIFORM, SCHED_ROUND_ROBIN = 0, 1
 
@@ -34,6 +35,16 @@ class SimConfig(C.Structure):
     _fields_ = [('func', C.c_int32), ('n_families', C.c_int32), ('scheduler', C.c_int32), ('descending', C.c_int32),
                 ('x_min', C.c_double), ('x_max', C.c_double), ('y_min', C.c_double), ('y_max', C.c_double),
                 ('init_noise', C.c_double), ('fam', Family * MAX_FAMILIES)]
+
+
+class ParamDesc(C.Structure):
+    _fields_ = [('min_val', C.c_double), ('max_val', C.c_double), ('interval', C.c_double), ('default_val', C.c_double),
+                ('is_log', C.c_int32), ('optimised', C.c_int32)]
+
+
+class DomainDesc(C.Structure):
+    _fields_ = [('n_params', C.c_int32), ('_pad', C.c_int32), ('p', ParamDesc * MAX_PARAMS),
+                ('order', C.c_int32 * MAX_PARAMS)]
 
 
 class HbOutputs(C.Structure):
@@ -69,6 +80,10 @@ def _load():
                                               C.POINTER(HbOutputs), vp]),
         'at2_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         'at2_fma_peak_probe': (C.c_int, [i32, i32, i64, vp, vp]),
+        'at2_nn_workspace_bytes': (i64, [i64, i32, i32]),
+        'at2_nn_lookup_f64': (C.c_int, [C.POINTER(DomainDesc), vp, i32, vp, i64, vp, vp, vp, i32, vp, vp, vp, i64, vp]),
+        'at2_hb_knownfn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(DomainDesc), vp, i32, vp, i32, i32, i64, i64, u64,
+                                         vp, C.POINTER(HbOutputs), vp, vp, vp]),
         'at2_kde_workspace_floats': (i64, [i64, i32]),
         'at2_kde_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, vp, vp, i64, vp]),
     }

@@ -150,3 +150,83 @@ def run_hyperband_predrawn(spec, f1, fn, family, gamma, xy=None, device=None, dt
     outs = torch.ops.at2.hb_sim_predrawn(spec.tables(device, dtype), spec.plan_bytes, spec.cfg_bytes, f1, fn, family,
                                          gamma, xy)
     return dict(zip(ops.HB_OUTPUT_NAMES, outs))
+
+
+# ---- closest-known-loss-function approximation -------------------------------------------------------------------------
+def domain_desc(domain, hyperparams_to_opt):
+    """at2_domain for a `Domain` of continuous `Param`s: declaration order + the attribute order of a drawn arm
+    (core/arm.py:29-55: non-optimised defaults first, then the optimised hyperparameters)."""
+    names = list(domain.hyperparams_names())
+    if not 1 <= len(names) <= nat.MAX_PARAMS:
+        raise ValueError(f'between 1 and {nat.MAX_PARAMS} hyperparameters are supported')
+    desc = nat.DomainDesc()
+    desc.n_params = len(names)
+    for i, n in enumerate(names):
+        prm = domain[n]
+        if getattr(prm, 'distrib', 'uniform') != 'uniform':
+            raise NotImplementedError(f"hyperparameter {n}: only distrib='uniform' is on the device path")
+        is_log = prm.scale == 'log'
+        if is_log and prm.logbase != np.e:
+            raise NotImplementedError(f'hyperparameter {n}: only logbase e is on the device path')
+        optimised = n in hyperparams_to_opt
+        if not optimised and prm.init_val is None:
+            raise ValueError(f"No default value for param {n} was supplied")
+        desc.p[i] = nat.ParamDesc(float(prm.min_val), float(prm.max_val), float(prm.interval or 0.0),
+                                  float(prm.init_val) if prm.init_val is not None else 0.0, int(is_log), int(optimised))
+    order = [i for i, n in enumerate(names) if n not in hyperparams_to_opt] + \
+            [i for i, n in enumerate(names) if n in hyperparams_to_opt]
+    for k, i in enumerate(order):
+        desc.order[k] = i
+    return desc, names
+
+
+class KnownFnSpec:
+    """A closest-known-function problem on the device: the recorded arms and their loss curves.
+
+    known_fs: {Arm: [loss_1 .. loss_L]} as the reference's KnownFnProblem takes it (ragged curves are padded with NaN up
+    to the longest; reading a padded position raises like the reference's IndexError would)."""
+
+    def __init__(self, known_fs, domain, hyperparams_to_opt, device=None):
+        self.desc, self.names = domain_desc(domain, hyperparams_to_opt)
+        self.domain_bytes = ops.struct_tensor(self.desc)
+        arms = list(known_fs.keys())
+        if not arms:
+            raise ValueError('known_fs is empty')
+        self.arms = arms
+        db = np.asarray([[float(a[n]) for n in self.names] for a in arms], np.float64)
+        self.lengths = np.asarray([len(known_fs[a]) for a in arms], np.int64)
+        L = int(self.lengths.max())
+        curves = np.full((len(arms), L), np.nan)
+        for i, a in enumerate(arms):
+            curves[i, :self.lengths[i]] = np.asarray(known_fs[a], np.float64)
+        device = _cuda_device(device)
+        self.device = device
+        self.db = torch.from_numpy(db).to(device)
+        self.curves = torch.from_numpy(curves).to(device)
+
+    def lookup(self, queries, times=None):
+        """Nearest recorded arm of each query row (raw values in domain order); with `times` also the loss read-out."""
+        q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float64)).to(self.device)
+        if times is None:
+            idx, dist, _ = torch.ops.at2.nn_lookup(self.domain_bytes, self.db, q, self.db.new_empty((0, 0)),
+                                                   torch.empty(0, device=self.device, dtype=torch.int32))
+            return idx, dist
+        t = torch.as_tensor(np.asarray(times, np.int32)).to(self.device)
+        return tuple(torch.ops.at2.nn_lookup(self.domain_bytes, self.db, q, self.curves, t))
+
+
+def run_knownfn_hyperband(kspec, max_iter, eta, n_reps, seed=0, rep_offset=0, min_or_max='min', predrawn=None,
+                          details=False):
+    """`n_reps` Hyperband repetitions on the closest-known-function problem, one fused launch."""
+    if min_or_max in (min, max):
+        min_or_max = min_or_max.__name__
+    plan = nat.bracket_plan(max_iter, eta)
+    L_min = int(kspec.lengths.min())
+    for c in range(plan.n_ckpts):
+        if plan.ckpt_time[c] > L_min:
+            raise IndexError('list index out of range')   # what the reference raises on a too-short recorded curve
+    pre = kspec.db.new_empty(0) if predrawn is None else \
+        torch.as_tensor(np.ascontiguousarray(predrawn, dtype=np.float64)).to(kspec.device).contiguous()
+    outs = torch.ops.at2.hb_knownfn(ops.struct_tensor(plan), kspec.domain_bytes, kspec.db, kspec.curves,
+                                    min_or_max == 'max', int(n_reps), int(rep_offset), int(seed), pre, bool(details))
+    return dict(zip([k for k in ops.KF_OUTPUT_NAMES if details or k in ('ofe', 'ofe_arm', 'best_arm_vals')], outs))

@@ -119,3 +119,80 @@ def kde(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: 
         nat.check(nat.lib.at2_kde_f32(x.data_ptr(), n, start, end, grid_points, bandwidth, kernel, dens.data_ptr(),
                                       ws.data_ptr(), ws_n, _stream_ptr(x.device)))
     return dens
+
+
+def _opt_ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else None
+
+
+@torch.library.custom_op('at2::nn_lookup', mutates_args=(), device_types='cuda')
+def nn_lookup(domain_bytes: torch.Tensor, db: torch.Tensor, queries: torch.Tensor, curves: torch.Tensor,
+              time: torch.Tensor) -> List[torch.Tensor]:
+    """Nearest recorded arm of every query (raw hyperparameter values, domain order) under the reference's normalised
+    squared error (at2_nn_lookup_f64).  Returns [idx int32[nq], dist f64[nq], loss f64[nq]]; `loss` is
+    curves[idx][time-1] when `curves`/`time` are non-empty, else empty."""
+    for name, t in (('db', db), ('queries', queries)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float64 or t.dim() != 2 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 2-D float64 tensor')
+    dom = _struct(nat.DomainDesc, domain_bytes)
+    A, D = db.shape
+    nq = queries.shape[0]
+    if D != dom.n_params or queries.shape[1] != D:
+        raise RuntimeError(f'db/queries must have {dom.n_params} columns')
+    gather = curves.numel() > 0
+    if gather and (curves.dtype != torch.float64 or curves.shape[0] != A or time.dtype != torch.int32 or time.numel() != nq):
+        raise RuntimeError('curves must be float64 [A, L] and time int32 [nq]')
+    with torch.cuda.device(db.device):
+        idx = torch.empty(nq, device=db.device, dtype=torch.int32)
+        dist = torch.empty(nq, device=db.device, dtype=torch.float64)
+        loss = torch.empty(nq if gather else 0, device=db.device, dtype=torch.float64)
+        ws_bytes = nat.lib.at2_nn_workspace_bytes(nq, A, D)
+        ws = torch.empty(max(ws_bytes, 16), device=db.device, dtype=torch.uint8)
+        nat.check(nat.lib.at2_nn_lookup_f64(C.byref(dom), db.data_ptr(), A, queries.data_ptr(), nq, idx.data_ptr(),
+                                            dist.data_ptr(), _opt_ptr(curves) if gather else None,
+                                            curves.shape[1] if gather else 0, _opt_ptr(time) if gather else None,
+                                            _opt_ptr(loss), ws.data_ptr(), ws_bytes, _stream_ptr(db.device)))
+    return [idx, dist, loss]
+
+
+KF_OUTPUT_NAMES = ['ofe', 'ofe_arm', 'best_arm_vals', 'round_best', 'round_best_arm', 'survivors', 'ckpt_loss', 'nn_idx']
+
+
+@torch.library.custom_op('at2::hb_knownfn', mutates_args=(), device_types='cuda')
+def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.Tensor, curves: torch.Tensor,
+               descending: bool, n_reps: int, rep_offset: int, seed: int, predrawn: torch.Tensor,
+               details: bool) -> List[torch.Tensor]:
+    """Hyperband repetitions on the closest-known-function problem (at2_hb_knownfn_f64).  `predrawn` is either empty
+    (arms are drawn from Philox streams) or float64 [n_reps, n_arms, D] raw proposed arms."""
+    for name, t in (('db', db), ('curves', curves)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float64 or t.dim() != 2 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 2-D float64 tensor')
+    plan, dom = _struct(nat.Plan, plan_bytes), _struct(nat.DomainDesc, domain_bytes)
+    A, D = db.shape
+    if D != dom.n_params or curves.shape[0] != A:
+        raise RuntimeError('db must be [A, D] with D = domain size and curves [A, L]')
+    if predrawn.numel() > 0:
+        _require_cuda(predrawn, 'predrawn')
+        if predrawn.dtype != torch.float64 or tuple(predrawn.shape) != (n_reps, plan.n_arms, D) or not predrawn.is_contiguous():
+            raise RuntimeError(f'predrawn must be contiguous float64 [{n_reps}, {plan.n_arms}, {D}]')
+    dev = db.device
+    with torch.cuda.device(dev):
+        o = {'ofe': torch.empty(n_reps, device=dev, dtype=torch.float64),
+             'ofe_arm': torch.empty(n_reps, device=dev, dtype=torch.int32),
+             'best_arm_vals': torch.empty(n_reps, D, device=dev, dtype=torch.float64)}
+        if details:
+            o['round_best'] = torch.empty(n_reps, plan.n_rounds, device=dev, dtype=torch.float64)
+            o['round_best_arm'] = torch.empty(n_reps, plan.n_rounds, device=dev, dtype=torch.int32)
+            o['survivors'] = torch.empty(n_reps, plan.n_surv, device=dev, dtype=torch.int32)
+            o['ckpt_loss'] = torch.empty(n_reps, plan.n_arms, plan.n_ckpts, device=dev, dtype=torch.float64)
+            o['nn_idx'] = torch.empty(n_reps, plan.n_arms, device=dev, dtype=torch.int32)
+        ptr = lambda k: o[k].data_ptr() if k in o else None  # noqa: E731
+        outs = nat.HbOutputs(ptr('ofe'), ptr('ofe_arm'), None, ptr('round_best'), ptr('round_best_arm'),
+                             ptr('survivors'), ptr('ckpt_loss'))
+        nat.check(nat.lib.at2_hb_knownfn_f64(C.byref(plan), C.byref(dom), db.data_ptr(), A, curves.data_ptr(),
+                                             curves.shape[1], int(descending), n_reps, rep_offset,
+                                             seed & 0xFFFFFFFFFFFFFFFF, _opt_ptr(predrawn), C.byref(outs),
+                                             ptr('nn_idx'), ptr('best_arm_vals'), _stream_ptr(dev)))
+    return [o[k] for k in KF_OUTPUT_NAMES if k in o]

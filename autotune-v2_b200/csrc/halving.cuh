@@ -1,0 +1,207 @@
+// (b) Successive halving of one repetition inside one warp - shared by the simulation and the closest-known-function
+// kernels.  Reference: optimisers/sequential/hyperband_optimiser.py:46-57 (stable sorted() top-k), :89-100 (rounds,
+// best-in-round), core/optimiser.py:67-68 (OFE = first optimum over the round-bests).
+#pragma once
+#include "at2_common.cuh"
+
+namespace {
+
+// ---- sort keys: (loss, position) with position breaking ties = python's stable sorted() ---------------------------------
+// float : 64-bit key  [orderable(loss) : 32 | position : 32]
+// double: 96-bit key  {orderable(loss) : 64, position : 32}
+__device__ __forceinline__ uint32_t orderable(float x, bool desc) {
+    x += 0.0f;  // -0.0 -> +0.0 (python compares them equal)
+    const uint32_t b = __float_as_uint(x);
+    const uint32_t o = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+    return desc ? ~o : o;
+}
+__device__ __forceinline__ uint64_t orderable(double x, bool desc) {
+    x += 0.0;
+    const uint64_t b = (uint64_t)__double_as_longlong(x);
+    const uint64_t o = b ^ ((b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+    return desc ? ~o : o;
+}
+
+struct Key32 {  // float losses
+    uint64_t v;
+    __device__ __forceinline__ static Key32 make(float loss, int pos, bool desc) {
+        return Key32{((uint64_t)orderable(loss, desc) << 32) | (uint32_t)pos};
+    }
+    __device__ __forceinline__ static Key32 pad() { return Key32{~0ull}; }
+    __device__ __forceinline__ int pos() const { return (int)(uint32_t)v; }
+    __device__ __forceinline__ bool operator>(const Key32& o) const { return v > o.v; }
+    __device__ __forceinline__ Key32 shfl_xor(int m) const { return Key32{__shfl_xor_sync(0xffffffffu, v, m)}; }
+    __device__ __forceinline__ Key32 shfl(int l) const { return Key32{__shfl_sync(0xffffffffu, v, l)}; }
+};
+struct Key64 {  // double losses
+    uint64_t k;
+    uint32_t p;
+    uint32_t _pad;
+    __device__ __forceinline__ static Key64 make(double loss, int pos, bool desc) {
+        return Key64{orderable(loss, desc), (uint32_t)pos, 0u};
+    }
+    __device__ __forceinline__ static Key64 pad() { return Key64{~0ull, ~0u, 0u}; }
+    __device__ __forceinline__ int pos() const { return (int)p; }
+    __device__ __forceinline__ bool operator>(const Key64& o) const { return k > o.k || (k == o.k && p > o.p); }
+    __device__ __forceinline__ Key64 shfl_xor(int m) const {
+        return Key64{__shfl_xor_sync(0xffffffffu, k, m), __shfl_xor_sync(0xffffffffu, p, m), 0u};
+    }
+    __device__ __forceinline__ Key64 shfl(int l) const {
+        return Key64{__shfl_sync(0xffffffffu, k, l), __shfl_sync(0xffffffffu, p, l), 0u};
+    }
+};
+template <typename T>
+struct KeyOf;
+template <>
+struct KeyOf<float> {
+    typedef Key32 type;
+};
+template <>
+struct KeyOf<double> {
+    typedef Key64 type;
+};
+
+// ascending bitonic network over `npad` (power of two, > 32) keys in shared memory, executed by one warp
+template <typename K>
+__device__ void warp_bitonic_smem(K* keys, int npad, int lane) {
+    for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = lane; idx < (npad >> 1); idx += 32) {
+                const int a = ((idx & ~(j - 1)) << 1) | (idx & (j - 1));
+                const int b = a | j;
+                const bool up = (a & k) == 0;
+                const K ka = keys[a], kb = keys[b];
+                if ((ka > kb) == up) {
+                    keys[a] = kb;
+                    keys[b] = ka;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ascending bitonic network over the first `n` (<= 32) keys, one per lane, warp shuffles only; lanes >= n hold pads.
+// Only the stages of the smallest power-of-two network covering n are executed (n is warp-uniform).
+template <typename K>
+__device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane, int n) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+        if ((k >> 1) >= n) break;
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const K other = mine.shfl_xor(j);
+            const bool up = (lane & k) == 0;
+            const bool lower = (lane & j) == 0;
+            // the lower lane of a pair keeps the smaller key in an ascending block, the larger in a descending one
+            const bool take_other = (mine > other) == (up == lower);
+            if (take_other) mine = other;
+        }
+    }
+    return mine;
+}
+
+template <typename T>
+struct HalvingOut {
+    T* ofe;
+    int* ofe_arm;
+    T* round_best;
+    int* round_best_arm;
+    int* survivors;
+};
+
+// Runs every bracket/round of `plan` for one repetition whose checkpoint losses sit in shared memory as
+// ck[c * stride + arm]; writes the requested outputs for repetition `rep_g`; returns the arm id of the OFE.
+// keys: npad sort keys, ids_a/ids_b: npad arm ids each (warp-private scratch).  All 32 lanes must call it.
+template <typename T>
+__device__ int warp_halving(const at2_plan& plan, const T* ck, int stride, typename KeyOf<T>::type* keys,
+                            unsigned short* ids_a, unsigned short* ids_b, bool desc, int lane, long long rep_g,
+                            const HalvingOut<T>& out) {
+    typedef typename KeyOf<T>::type K;
+    T best = (T)0;
+    int best_arm = -1;
+    int surv_w = 0;
+    for (int b = 0; b < plan.n_brackets; ++b) {
+        int n_cur = plan.bracket_n[b];
+        const int first = plan.bracket_first_arm[b];
+        unsigned short* ids = ids_a;
+        unsigned short* ids_next = ids_b;
+        for (int rd = plan.bracket_first_round[b]; rd < plan.bracket_first_round[b + 1]; ++rd) {
+            const int c = plan.round_ckpt[rd];
+            const int keep = min(plan.round_keep[rd], n_cur);
+            const bool first_round = rd == plan.bracket_first_round[b];
+            const T* col = ck + c * stride;
+            T rb_loss;
+            int rb_arm;
+            if (n_cur <= 32) {
+                K mine = K::pad();
+                T my_loss = (T)0;
+                int my_id = 0;
+                if (lane < n_cur) {
+                    my_id = first_round ? first + lane : (int)ids[lane];
+                    my_loss = col[my_id];
+                    mine = K::make(my_loss, lane, desc);
+                }
+                mine = warp_bitonic_shfl(mine, lane, n_cur);
+                const int src = mine.pos() & 31;            // lane that held the key now ranked `lane`
+                const int sid = __shfl_sync(0xffffffffu, my_id, src);
+                const T sl = __shfl_sync(0xffffffffu, my_loss, src);
+                rb_loss = __shfl_sync(0xffffffffu, sl, 0);
+                rb_arm = __shfl_sync(0xffffffffu, sid, 0);
+                if (lane < keep) ids_next[lane] = (unsigned short)sid;
+            } else {
+                int npad = 64;
+                while (npad < n_cur) npad <<= 1;
+                for (int j = lane; j < npad; j += 32) {
+                    const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+                    keys[j] = j < n_cur ? K::make(col[id], j, desc) : K::pad();
+                }
+                __syncwarp();
+                warp_bitonic_smem(keys, npad, lane);
+                for (int j = lane; j < keep; j += 32) {
+                    const int pos = keys[j].pos();
+                    ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+                }
+                const int pos0 = keys[0].pos();
+                rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+                rb_loss = col[rb_arm];
+            }
+            __syncwarp();
+            if (out.survivors != nullptr)
+                for (int j = lane; j < keep; j += 32) out.survivors[rep_g * plan.n_surv + surv_w + j] = (int)ids_next[j];
+            surv_w += keep;
+            if (lane == 0) {
+                if (out.round_best != nullptr) out.round_best[rep_g * plan.n_rounds + rd] = rb_loss;
+                if (out.round_best_arm != nullptr) out.round_best_arm[rep_g * plan.n_rounds + rd] = rb_arm;
+            }
+            // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
+            if (best_arm < 0 || (desc ? rb_loss > best : rb_loss < best)) best = rb_loss, best_arm = rb_arm;
+            unsigned short* tmp = ids;
+            ids = ids_next;
+            ids_next = tmp;
+            n_cur = keep;
+            __syncwarp();
+        }
+    }
+    if (lane == 0) {
+        if (out.ofe != nullptr) out.ofe[rep_g] = best;
+        if (out.ofe_arm != nullptr) out.ofe_arm[rep_g] = best_arm;
+    }
+    return best_arm;
+}
+
+// bytes of warp-private sort scratch for brackets up to `npad` wide
+template <typename T>
+__host__ __device__ inline size_t halving_scratch_bytes(int npad) {
+    return (size_t)npad * (sizeof(typename KeyOf<T>::type) + 2 * sizeof(unsigned short));
+}
+
+inline int halving_npad(const at2_plan* plan) {
+    int widest = 0;
+    for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
+    int npad = 64;
+    while (npad < widest) npad <<= 1;
+    return npad;
+}
+
+}  // namespace

@@ -146,6 +146,47 @@ int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_config* cfg, con
                             const float* d_f1, const float* d_fn, const int32_t* d_family, const float* d_gamma,
                             const float* d_xy, const at2_hb_outputs* out, void* stream);
 
+/* ---- (d): closest-known-loss-function approximation ------------------------------------------------------------------ */
+
+#define AT2_MAX_PARAMS 16
+
+/* One hyperparameter of a problem domain (core/params.py:12-24).  For is_log the bounds are exponents of e. */
+typedef struct at2_param {
+    double min_val, max_val;
+    double interval;        /* 0 = continuous; otherwise values are floor(v/interval)*interval (params.py:44-45) */
+    double default_val;     /* init_val, used when the hyperparameter is not optimised (core/arm.py:29-42) */
+    int32_t is_log;
+    int32_t optimised;
+} at2_param;
+
+/* Domain in declaration order + the attribute order of an arm made by Arm().draw_hp_val (core/arm.py:44-55:
+ * non-optimised defaults first, then the optimised ones), which is the summation order of the squared error. */
+typedef struct at2_domain {
+    int32_t n_params;
+    int32_t _pad;
+    at2_param p[AT2_MAX_PARAMS];
+    int32_t order[AT2_MAX_PARAMS];
+} at2_domain;
+
+/* Batched nearest recorded arm: replaces the scan of benchmarks/known_loss_fn_problem.py:35-50 (+ Arm.normalize,
+ * core/arm.py:57-70) for nq proposed arms at once.  d_db[A][D] and d_queries[nq][D] hold RAW hyperparameter values in
+ * domain order.  Optional fused read-out (:61): d_loss[i] = d_curves[idx[i]][d_time[i] - 1].
+ * float64, un-fused, first minimum wins -> indices are bit-identical to the reference's. */
+int64_t at2_nn_workspace_bytes(int64_t nq, int32_t A, int32_t D);
+int at2_nn_lookup_f64(const at2_domain* domain, const double* d_db, int32_t A, const double* d_queries, int64_t nq,
+                      int32_t* d_idx, double* d_dist, const double* d_curves, int32_t L, const int32_t* d_time,
+                      double* d_loss, void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* Hyperband repetitions on the closest-known-function problem, fused: replaces the loop of
+ * experiments/run_closest_loss_fn_approximation.py:183-194 for method sim(hb).  Per repetition: draw the arms
+ * (core/arm.py:44-55) or take them from d_predrawn_arms[n_reps][n_arms][D], find each one's nearest recorded arm,
+ * read its curve at the Hyperband checkpoints, run successive halving.  Outputs as at2_hb_outputs with real = double
+ * (d_best_xy unused); optional d_nn_idx[n_reps][n_arms], d_best_arm_vals[n_reps][D]. */
+int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain, const double* d_db, int32_t A,
+                       const double* d_curves, int32_t L, int32_t descending, int64_t n_reps, int64_t rep_offset,
+                       uint64_t seed, const double* d_predrawn_arms, const at2_hb_outputs* out, int32_t* d_nn_idx,
+                       double* d_best_arm_vals, void* stream);
+
 /* ---- (e): EPDF-OFE kernel density estimate ----------------------------------------------------------------------- */
 
 #define AT2_KDE_EPANECHNIKOV 0   /* the reference's kernel (plot_results.py:13) */

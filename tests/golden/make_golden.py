@@ -334,12 +334,96 @@ def make_seeded_ofes():
     print('wrote', path)
 
 
+def make_knownfn():
+    """Closest-known-loss-function goldens from the reference's own KnownFnProblem / KnownFnEvaluator on a synthetic
+    recorded-arm database (the real one is git-ignored upstream): nearest-arm index + loss for individual queries,
+    and seeded Hyperband repetitions (R=81 and the script default R=6)."""
+    import random
+
+    from autotune.benchmarks import KnownFnProblem
+    from autotune.benchmarks.cifar_problem import HYPERPARAMETERS_TO_OPTIMIZE as CIFAR_OPT
+    from autotune.benchmarks.cifar_problem import HYPERPARAMS_DOMAIN as CIFAR_DOM
+    from autotune.benchmarks.known_loss_fn_problem import KnownFnEvaluator
+    from autotune.benchmarks.mnist_problem import HYPERPARAMS_DOMAIN as MNIST_DOM
+
+    sys.path.insert(0, ROOT)
+    from oracle import known_fn as okf
+
+    class RealProblem(HyperparameterOptimisationProblem):
+        def get_evaluator(self, arm=None):
+            raise NotImplementedError
+
+    out = {}
+    for tag, dom, to_opt, odom, n_arms in [('mnist', MNIST_DOM, (), okf.MNIST_DOMAIN, 425),
+                                           ('cifar', CIFAR_DOM, CIFAR_OPT, okf.CIFAR_DOMAIN, 300)]:
+        with redirect_stdout(io.StringIO()):
+            real = RealProblem(dom, to_opt)
+        # hyperparams_to_opt goes through a set() upstream; the draw order is the domain order regardless
+        db_dicts, curves = okf.synthetic_db(odom, n_arms, 300, seed=0)
+        names = okf.attribute_order(odom)
+        known_fs = {Arm(**{n: d[n] for n in names}): list(c) for d, c in zip(db_dicts, curves)}
+        assert len(known_fs) == n_arms
+        out[f'{tag}_db'] = np.asarray([[float(d[n]) for n in names] for d in db_dicts], np.float64)
+        out[f'{tag}_names'] = np.array(names)
+        # (1) individual queries through the reference evaluator
+        np.random.seed(7)
+        with redirect_stdout(io.StringIO()):
+            problem = KnownFnProblem(known_fs=known_fs, real_problem=real)
+        q_vals, q_idx, q_loss = [], [], []
+        keys = list(known_fs.keys())
+        for k in range(200):
+            with redirect_stdout(io.StringIO()):
+                ev = problem.get_evaluator()
+                goals = ev.evaluate(n_resources=(1, 3, 9, 27, 81)[k % 5])
+            assert list(ev.arm.__dict__.keys()) == names
+            q_vals.append([float(ev.arm[n]) for n in names])
+            q_loss.append(goals.fval)
+            q_idx.append(next(i for i, a in enumerate(keys) if known_fs[a] is goals.fvals))
+        out[f'{tag}_query'] = np.asarray(q_vals, np.float64)
+        out[f'{tag}_query_idx'] = np.asarray(q_idx, np.int32)
+        out[f'{tag}_query_loss'] = np.asarray(q_loss, np.float64)
+        # (2) seeded Hyperband repetitions
+        for R in (81, 6):
+            np.random.seed(100 + R)
+            random.seed(100 + R)
+            ofes, arms_all, best_ids = [], [], []
+            n_reps = 3 if R == 81 else 6
+            for _ in range(n_reps):
+                created = []
+                orig = KnownFnProblem.get_evaluator
+
+                def get_evaluator(self, *a, **k):
+                    ev = orig(self, *a, **k)
+                    ev.golden_id = len(created)
+                    created.append(ev)
+                    return ev
+                KnownFnProblem.get_evaluator = get_evaluator
+                try:
+                    with redirect_stdout(io.StringIO()):
+                        problem = KnownFnProblem(known_fs=known_fs, real_problem=real)
+                        opt = HyperbandOptimiser(eta=3, max_iter=R, min_or_max=min, optimisation_func=fval,
+                                                 is_simulation=True)
+                        best = opt.run_optimisation(problem, verbosity=False)
+                finally:
+                    KnownFnProblem.get_evaluator = orig
+                ofes.append(fval(best.optimisation_goals))
+                best_ids.append(best.evaluator.golden_id)
+                arms_all.append([[float(ev.arm[n]) for n in names] for ev in created])
+            out[f'{tag}_hb_R{R}_ofe'] = np.asarray(ofes, np.float64)
+            out[f'{tag}_hb_R{R}_ofe_id'] = np.asarray(best_ids, np.int32)
+            out[f'{tag}_hb_R{R}_arms'] = np.asarray(arms_all, np.float64)
+    path = os.path.join(HERE, 'knownfn.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for fn in sys.argv[1:]:
             globals()[fn]()
         sys.exit(0)
     make_seeded_ofes()
+    make_knownfn()
     make_bracket_tables()
     make_hyperband_cases()
     make_epdf_vectors()
