@@ -60,7 +60,9 @@ def test_lookup_against_oracle_with_ties_and_many_queries(tag):
     for k, row in enumerate(q):
         arm = {n: row[spec.names.index(n)] for n in okf.attribute_order(odom)}
         i, d = okf.nearest(arm, arms, odom)
-        assert int(idx[k]) == i and float(dist[k]) == d
+        # the index is bit-exact; the distance itself may differ in the last bit because python's `** 2` goes through
+        # libm pow(), which is not correctly rounded for every input, while the device squares exactly
+        assert int(idx[k]) == i and abs(float(dist[k]) - d) <= 4e-16 * max(d, 1e-300)
     # few queries -> the database is split over CTAs; many queries -> one chunk: same answer
     big = np.tile(q, (400, 1))
     idx_big, _ = spec.lookup(big)
@@ -73,22 +75,15 @@ def test_duplicate_recorded_arms_first_wins():
     dom = _product_domain(okf.MNIST_DOMAIN)
     names = list(dom.hyperparams_names())
 
-    class A2(Arm):      # distinct keys with identical hyperparameters
-        def __init__(self, tag, **kw):
-            super().__init__(**kw)
-            object.__setattr__(self, '_tag', tag)
-
+    class A2(Arm):      # distinct dictionary keys with identical hyperparameters
         def __hash__(self):
-            return hash(self._tag)
+            return id(self)
 
         def __eq__(self, other):
             return self is other
     vals = dict(learning_rate=0.01, weight_decay=0.001, momentum=0.5, batch_size=100)
-    known_fs = {}
-    for t in range(5):
-        a = A2(t, **vals)
-        del a.__dict__['_tag']
-        known_fs[a] = [float(t)] * 10
+    known_fs = {A2(**vals): [float(t)] * 10 for t in range(5)}
+    assert len(known_fs) == 5
     spec = KnownFnSpec(known_fs, dom, tuple(names))
     idx, _ = spec.lookup([[vals[n] for n in names]] * 3)
     assert idx.tolist() == [0, 0, 0]
