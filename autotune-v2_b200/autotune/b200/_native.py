@@ -23,7 +23,7 @@ class Plan(C.Structure):
                 ('bracket_first_round', C.c_int32 * (MAX_BRACKETS + 1)),
                 ('round_n_eval', C.c_int32 * MAX_ROUNDS), ('round_keep', C.c_int32 * MAX_ROUNDS),
                 ('round_time', C.c_int32 * MAX_ROUNDS), ('round_ckpt', C.c_int32 * MAX_ROUNDS),
-                ('ckpt_time', C.c_int32 * MAX_CKPTS)]
+                ('ckpt_time', C.c_int32 * MAX_CKPTS), ('bracket_r0', C.c_double * MAX_BRACKETS)]
 
 
 class Family(C.Structure):
@@ -45,6 +45,14 @@ class ParamDesc(C.Structure):
 class DomainDesc(C.Structure):
     _fields_ = [('n_params', C.c_int32), ('_pad', C.c_int32), ('p', ParamDesc * MAX_PARAMS),
                 ('order', C.c_int32 * MAX_PARAMS)]
+
+
+class TpeConfig(C.Structure):
+    _fields_ = [('enabled', C.c_int32), ('n_startup', C.c_int32), ('n_candidates', C.c_int32), ('lf', C.c_int32),
+                ('transfer', C.c_int32), ('threshold', C.c_int32), ('gamma', C.c_double), ('prior_weight', C.c_double)]
+
+
+TRANSFER_IDS = {'none': 0, 'all': 1, 'longest': 2, 'same': 3, 'threshold': 4}
 
 
 class HbOutputs(C.Structure):
@@ -80,6 +88,10 @@ def _load():
                                               C.POINTER(HbOutputs), vp]),
         'at2_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
         'at2_fma_peak_probe': (C.c_int, [i32, i32, i64, vp, vp]),
+        'at2_single_round_plan': (C.c_int, [i32, i32, i32, C.POINTER(Plan)]),
+        'at2_tpe_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), C.POINTER(TpeConfig), vp, i64, i64, u64,
+                                      C.POINTER(HbOutputs), vp, vp]),
+        'at2_tpe_score_f32': (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_double, C.POINTER(TpeConfig), vp, i32, vp, vp, vp]),
         'at2_nn_workspace_bytes': (i64, [i64, i32, i32]),
         'at2_nn_lookup_f64': (C.c_int, [C.POINTER(DomainDesc), vp, i32, vp, i64, vp, vp, vp, i32, vp, vp, vp, i64, vp]),
         'at2_hb_knownfn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(DomainDesc), vp, i32, vp, i32, i32, i64, i64, u64,

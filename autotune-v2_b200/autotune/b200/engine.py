@@ -230,3 +230,52 @@ def run_knownfn_hyperband(kspec, max_iter, eta, n_reps, seed=0, rep_offset=0, mi
     outs = torch.ops.at2.hb_knownfn(ops.struct_tensor(plan), kspec.domain_bytes, kspec.db, kspec.curves,
                                     min_or_max == 'max', int(n_reps), int(rep_offset), int(seed), pre, bool(details))
     return dict(zip([k for k in ops.KF_OUTPUT_NAMES if details or k in ('ofe', 'ofe_arm', 'best_arm_vals')], outs))
+
+
+# ---- TPE / hybrids ---------------------------------------------------------------------------------------------------------
+def tpe_config(enabled=True, transfer='none', threshold=0, n_startup=10, n_candidates=24, gamma=0.25, prior_weight=1.0,
+               lf=25):
+    """at2_tpe_config with hyperopt 0.2.4's tpe.suggest defaults and the reference's n_startup_jobs base of 10
+    (tpe_optimiser.py:52)."""
+    if transfer not in nat.TRANSFER_IDS:
+        raise ValueError(f'unknown transfer mode {transfer!r}')
+    return nat.TpeConfig(int(enabled), int(n_startup), int(n_candidates), int(lf), nat.TRANSFER_IDS[transfer],
+                         int(threshold or 0), float(gamma), float(prior_weight))
+
+
+def single_round_plan(R, n_evals, n_resources):
+    plan = nat.Plan()
+    rc = nat.lib.at2_single_round_plan(int(R), int(n_evals), int(n_resources), C.byref(plan))
+    if rc != 0:
+        msg = nat.lib.at2_last_error().decode()
+        raise (IndexError if 'index out of range' in msg else ValueError)(msg)
+    return plan
+
+
+def run_optimiser_repetitions(spec, n_reps, tpe, seed=0, rep_offset=0, device=None, details=False, plan=None):
+    """Monte-Carlo repetitions of any optimiser of the family {Hyperband, Hyperband+TPE (+transfer), TPE, random search}
+    on the simulation problem of `spec`: one fused launch (at2_tpe_sim_f32).  `plan` overrides the Hyperband plan of
+    `spec` (stand-alone TPE / random search use single_round_plan)."""
+    device = _cuda_device(device)
+    plan = spec.plan if plan is None else plan
+    outs = torch.ops.at2.tpe_sim(spec.tables(device, torch.float32), ops.struct_tensor(plan), spec.cfg_bytes,
+                                 ops.struct_tensor(tpe), int(n_reps), int(rep_offset), int(seed), bool(details))
+    return dict(zip(ops.HB_OUTPUT_NAMES + ['arm_xy'] if details else ops.HB_OUTPUT_NAMES, outs))
+
+
+def run_hybrid_repetitions(spec, n_reps, transfer='none', threshold=None, seed=0, rep_offset=0, device=None,
+                           details=False):
+    """HybridHyperbandTpe{,NoTransfer,TransferAll,TransferLongest,TransferSame,TransferThreshold}Optimiser."""
+    return run_optimiser_repetitions(spec, n_reps, tpe_config(True, transfer, threshold), seed, rep_offset, device, details)
+
+
+def run_tpe_repetitions(spec, n_reps, n_resources, max_iter, seed=0, rep_offset=0, device=None, details=False):
+    """Stand-alone TpeOptimiser(n_resources, max_iter): max_iter sequential evaluations at n_resources."""
+    plan = single_round_plan(spec.R, max_iter, n_resources)
+    return run_optimiser_repetitions(spec, n_reps, tpe_config(True), seed, rep_offset, device, details, plan)
+
+
+def run_random_repetitions(spec, n_reps, n_resources, max_iter, seed=0, rep_offset=0, device=None, details=False):
+    """RandomOptimiser(n_resources, max_iter): max_iter random arms evaluated at n_resources."""
+    plan = single_round_plan(spec.R, max_iter, n_resources)
+    return run_optimiser_repetitions(spec, n_reps, tpe_config(False), seed, rep_offset, device, details, plan)

@@ -196,3 +196,41 @@ def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.T
                                              seed & 0xFFFFFFFFFFFFFFFF, _opt_ptr(predrawn), C.byref(outs),
                                              ptr('nn_idx'), ptr('best_arm_vals'), _stream_ptr(dev)))
     return [o[k] for k in KF_OUTPUT_NAMES if k in o]
+
+
+@torch.library.custom_op('at2::tpe_sim', mutates_args=(), device_types='cuda')
+def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, tpe_bytes: torch.Tensor, n_reps: int,
+            rep_offset: int, seed: int, details: bool) -> List[torch.Tensor]:
+    """Hyperband-TPE hybrids / stand-alone TPE / random search on the simulation problem (at2_tpe_sim_f32).
+    Returns the at2::hb_sim_f32 outputs followed by arm_xy [n_reps, n_arms, 2] when `details`."""
+    _require_cuda(tables, 'tables')
+    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
+    tpe = _struct(nat.TpeConfig, tpe_bytes)
+    with torch.cuda.device(tables.device):
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
+        arm_xy = torch.empty(n_reps, plan.n_arms, 2, device=tables.device, dtype=torch.float32) if details else None
+        nat.check(nat.lib.at2_tpe_sim_f32(C.byref(plan), C.byref(cfg), C.byref(tpe), tables.data_ptr(), n_reps, rep_offset,
+                                          seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs),
+                                          arm_xy.data_ptr() if details else None, _stream_ptr(tables.device)))
+    return tensors + ([arm_xy] if details else [])
+
+
+@torch.library.custom_op('at2::tpe_score', mutates_args=(), device_types='cuda')
+def tpe_score(obs: torch.Tensor, loss: torch.Tensor, low: float, high: float, tpe_bytes: torch.Tensor,
+              candidates: torch.Tensor) -> List[torch.Tensor]:
+    """log l(x) - log g(x) of the adaptive Parzen models built from (obs, loss) [n_problems, n_obs] for the given
+    candidates [n_problems, n_cand] (at2_tpe_score_f32).  Returns [scores, models[n_problems, 2, cap+1, 3]]."""
+    for name, t in (('obs', obs), ('loss', loss), ('candidates', candidates)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float32 or t.dim() != 2 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 2-D float32 tensor')
+    tpe = _struct(nat.TpeConfig, tpe_bytes)
+    n_prob, n_obs = obs.shape
+    cap = (n_obs + 31) // 32 * 32
+    with torch.cuda.device(obs.device):
+        scores = torch.empty_like(candidates)
+        models = torch.zeros(n_prob, 2, cap + 1, 3, device=obs.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_tpe_score_f32(obs.data_ptr(), loss.data_ptr(), n_obs, n_prob, low, high, C.byref(tpe),
+                                            candidates.data_ptr(), candidates.shape[1], scores.data_ptr(),
+                                            models.data_ptr(), _stream_ptr(obs.device)))
+    return [scores, models]

@@ -58,6 +58,7 @@ extern "C" int at2_bracket_plan(int32_t R, int32_t eta, at2_plan* plan) {
         plan->bracket_n[nb] = (int32_t)n;
         plan->bracket_first_arm[nb] = arms;
         plan->bracket_first_round[nb] = nr;
+        plan->bracket_r0[nb] = r;
         long long alive = n;
         for (int i = 0; i <= s; ++i) {                          // :89
             if (nr >= AT2_MAX_ROUNDS) {

@@ -110,84 +110,105 @@ struct HalvingOut {
     int* survivors;
 };
 
-// Runs every bracket/round of `plan` for one repetition whose checkpoint losses sit in shared memory as
-// ck[c * stride + arm]; writes the requested outputs for repetition `rep_g`; returns the arm id of the OFE.
-// keys: npad sort keys, ids_a/ids_b: npad arm ids each (warp-private scratch).  All 32 lanes must call it.
+template <typename T>
+struct HalvingState {
+    T best;
+    int best_arm;
+    int surv_w;
+};
+
+// Runs the rounds of bracket `b` for one repetition whose checkpoint losses sit in shared memory as
+// ck[c * stride + arm]; writes the requested per-round outputs for repetition `rep_g` and folds the round-bests into
+// `st`.  keys: npad sort keys, ids_a/ids_b: npad arm ids each (warp-private scratch).  When `latest_ck` is given,
+// latest_ck[arm] ends up holding the checkpoint index of the last round the arm was evaluated in (what the hybrids'
+// history transfer keys on, hybrid_hyperband_tpe_with_transfer.py:96-98).  All 32 lanes must call it.
+template <typename T>
+__device__ void warp_halving_bracket(const at2_plan& plan, int b, const T* ck, int stride, typename KeyOf<T>::type* keys,
+                                     unsigned short* ids_a, unsigned short* ids_b, bool desc, int lane, long long rep_g,
+                                     const HalvingOut<T>& out, HalvingState<T>& st, unsigned char* latest_ck = nullptr) {
+    typedef typename KeyOf<T>::type K;
+    int n_cur = plan.bracket_n[b];
+    const int first = plan.bracket_first_arm[b];
+    unsigned short* ids = ids_a;
+    unsigned short* ids_next = ids_b;
+    for (int rd = plan.bracket_first_round[b]; rd < plan.bracket_first_round[b + 1]; ++rd) {
+        const int c = plan.round_ckpt[rd];
+        const int keep = min(plan.round_keep[rd], n_cur);
+        const bool first_round = rd == plan.bracket_first_round[b];
+        const T* col = ck + c * stride;
+        T rb_loss;
+        int rb_arm;
+        if (latest_ck != nullptr)
+            for (int j = lane; j < n_cur; j += 32) latest_ck[first_round ? first + j : (int)ids[j]] = (unsigned char)c;
+        if (n_cur <= 32) {
+            K mine = K::pad();
+            T my_loss = (T)0;
+            int my_id = 0;
+            if (lane < n_cur) {
+                my_id = first_round ? first + lane : (int)ids[lane];
+                my_loss = col[my_id];
+                mine = K::make(my_loss, lane, desc);
+            }
+            mine = warp_bitonic_shfl(mine, lane, n_cur);
+            const int src = mine.pos() & 31;            // lane that held the key now ranked `lane`
+            const int sid = __shfl_sync(0xffffffffu, my_id, src);
+            const T sl = __shfl_sync(0xffffffffu, my_loss, src);
+            rb_loss = __shfl_sync(0xffffffffu, sl, 0);
+            rb_arm = __shfl_sync(0xffffffffu, sid, 0);
+            if (lane < keep) ids_next[lane] = (unsigned short)sid;
+        } else {
+            int npad = 64;
+            while (npad < n_cur) npad <<= 1;
+            for (int j = lane; j < npad; j += 32) {
+                const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+                keys[j] = j < n_cur ? K::make(col[id], j, desc) : K::pad();
+            }
+            __syncwarp();
+            warp_bitonic_smem(keys, npad, lane);
+            for (int j = lane; j < keep; j += 32) {
+                const int pos = keys[j].pos();
+                ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+            }
+            const int pos0 = keys[0].pos();
+            rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+            rb_loss = col[rb_arm];
+        }
+        __syncwarp();
+        if (out.survivors != nullptr)
+            for (int j = lane; j < keep; j += 32) out.survivors[rep_g * plan.n_surv + st.surv_w + j] = (int)ids_next[j];
+        st.surv_w += keep;
+        if (lane == 0) {
+            if (out.round_best != nullptr) out.round_best[rep_g * plan.n_rounds + rd] = rb_loss;
+            if (out.round_best_arm != nullptr) out.round_best_arm[rep_g * plan.n_rounds + rd] = rb_arm;
+        }
+        // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
+        if (st.best_arm < 0 || (desc ? rb_loss > st.best : rb_loss < st.best)) st.best = rb_loss, st.best_arm = rb_arm;
+        unsigned short* tmp = ids;
+        ids = ids_next;
+        ids_next = tmp;
+        n_cur = keep;
+        __syncwarp();
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void halving_finish(const HalvingOut<T>& out, const HalvingState<T>& st, int lane, long long rep_g) {
+    if (lane == 0) {
+        if (out.ofe != nullptr) out.ofe[rep_g] = st.best;
+        if (out.ofe_arm != nullptr) out.ofe_arm[rep_g] = st.best_arm;
+    }
+}
+
+// All brackets of `plan` for one repetition; returns the arm id of the OFE.
 template <typename T>
 __device__ int warp_halving(const at2_plan& plan, const T* ck, int stride, typename KeyOf<T>::type* keys,
                             unsigned short* ids_a, unsigned short* ids_b, bool desc, int lane, long long rep_g,
                             const HalvingOut<T>& out) {
-    typedef typename KeyOf<T>::type K;
-    T best = (T)0;
-    int best_arm = -1;
-    int surv_w = 0;
-    for (int b = 0; b < plan.n_brackets; ++b) {
-        int n_cur = plan.bracket_n[b];
-        const int first = plan.bracket_first_arm[b];
-        unsigned short* ids = ids_a;
-        unsigned short* ids_next = ids_b;
-        for (int rd = plan.bracket_first_round[b]; rd < plan.bracket_first_round[b + 1]; ++rd) {
-            const int c = plan.round_ckpt[rd];
-            const int keep = min(plan.round_keep[rd], n_cur);
-            const bool first_round = rd == plan.bracket_first_round[b];
-            const T* col = ck + c * stride;
-            T rb_loss;
-            int rb_arm;
-            if (n_cur <= 32) {
-                K mine = K::pad();
-                T my_loss = (T)0;
-                int my_id = 0;
-                if (lane < n_cur) {
-                    my_id = first_round ? first + lane : (int)ids[lane];
-                    my_loss = col[my_id];
-                    mine = K::make(my_loss, lane, desc);
-                }
-                mine = warp_bitonic_shfl(mine, lane, n_cur);
-                const int src = mine.pos() & 31;            // lane that held the key now ranked `lane`
-                const int sid = __shfl_sync(0xffffffffu, my_id, src);
-                const T sl = __shfl_sync(0xffffffffu, my_loss, src);
-                rb_loss = __shfl_sync(0xffffffffu, sl, 0);
-                rb_arm = __shfl_sync(0xffffffffu, sid, 0);
-                if (lane < keep) ids_next[lane] = (unsigned short)sid;
-            } else {
-                int npad = 64;
-                while (npad < n_cur) npad <<= 1;
-                for (int j = lane; j < npad; j += 32) {
-                    const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
-                    keys[j] = j < n_cur ? K::make(col[id], j, desc) : K::pad();
-                }
-                __syncwarp();
-                warp_bitonic_smem(keys, npad, lane);
-                for (int j = lane; j < keep; j += 32) {
-                    const int pos = keys[j].pos();
-                    ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
-                }
-                const int pos0 = keys[0].pos();
-                rb_arm = first_round ? first + pos0 : (int)ids[pos0];
-                rb_loss = col[rb_arm];
-            }
-            __syncwarp();
-            if (out.survivors != nullptr)
-                for (int j = lane; j < keep; j += 32) out.survivors[rep_g * plan.n_surv + surv_w + j] = (int)ids_next[j];
-            surv_w += keep;
-            if (lane == 0) {
-                if (out.round_best != nullptr) out.round_best[rep_g * plan.n_rounds + rd] = rb_loss;
-                if (out.round_best_arm != nullptr) out.round_best_arm[rep_g * plan.n_rounds + rd] = rb_arm;
-            }
-            // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
-            if (best_arm < 0 || (desc ? rb_loss > best : rb_loss < best)) best = rb_loss, best_arm = rb_arm;
-            unsigned short* tmp = ids;
-            ids = ids_next;
-            ids_next = tmp;
-            n_cur = keep;
-            __syncwarp();
-        }
-    }
-    if (lane == 0) {
-        if (out.ofe != nullptr) out.ofe[rep_g] = best;
-        if (out.ofe_arm != nullptr) out.ofe_arm[rep_g] = best_arm;
-    }
-    return best_arm;
+    HalvingState<T> st{(T)0, -1, 0};
+    for (int b = 0; b < plan.n_brackets; ++b)
+        warp_halving_bracket<T>(plan, b, ck, stride, keys, ids_a, ids_b, desc, lane, rep_g, out, st);
+    halving_finish<T>(out, st, lane, rep_g);
+    return st.best_arm;
 }
 
 // bytes of warp-private sort scratch for brackets up to `npad` wide

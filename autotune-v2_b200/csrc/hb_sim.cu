@@ -24,103 +24,18 @@
 
 #include "at2_common.cuh"
 #include "halving.cuh"
+#include "sim_core.cuh"
 
 namespace {
-
-enum { MODE_PHILOX = 0, MODE_PREDRAWN = 1 };
-
-// ---- arithmetic policies ---------------------------------------------------------------------------------------------
-// double: the reference's float64 operation order with explicitly un-fused IEEE ops (bit-exact parity path).
-// float : production arithmetic, contraction to FFMA welcome.
-template <typename T>
-struct Fam {
-    T ml, up, s0, s1;  // float: ml = ml_agg/100 folded; double: raw ml_agg
-    int smooth, pw_off;
-};
-
-__device__ __forceinline__ double step_exact(double f, double g, int t, int R, double fn, double ml_agg, double up_spik,
-                                             double P, double P11) {
-    if (g == 2.0) return f;                                                        // :100-101
-    if (g > 2.0) {                                                                 // :102-107
-        const double debt = __dsub_rn(fn, f);
-        const double ml = __dadd_rn(f, __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(g, 2.0), ml_agg), debt), 100.0));
-        return __dadd_rn(ml, __dmul_rn(__dsub_rn(fn, ml), P));
-    }
-    const double up = __dadd_rn(f, __ddiv_rn(__dmul_rn(up_spik, 1.0), __dadd_rn(1.0, g)));  // :108-115
-    double nxt = __dadd_rn(up, __dmul_rn(__dsub_rn(fn, up), P11));
-    if (R - t == 1) nxt = fn;
-    return nxt;
-}
-
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_lg2(float x) {
-    float r;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_sqrt(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_sin(float x) {
-    float r;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_cos(float x) {
-    float r;
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11) {
-    // production arithmetic of simulation_evaluator.py:99-115; at the last step P = P11 = 1 so both branches land on
-    // f_n to within one rounding (the reference's float64 path has the same property on its down branch)
-    const float ml = fmaf((g - 2.0f) * mlc, fn - f, f);
-    const float dn = fmaf(fn - ml, P, ml);
-    const float up = fmaf(upc, fast_rcp(1.0f + g), f);
-    const float un = fmaf(fn - up, P11, up);
-    return g > 2.0f ? dn : (g < 2.0f ? un : f);
-}
-
-// ---- test functions in FP32 (benchmarks/opt_function_problem.py:49-138) ------------------------------------------------
-__device__ float base_function(int func, float x, float y) {
-    switch (func) {
-        case AT2_FUNC_EGG:
-            return -(y + 47.0f) * sinf(sqrtf(fabsf(y + 0.5f * x + 47.0f))) - x * sinf(sqrtf(fabsf(x - y - 47.0f)));
-        case AT2_FUNC_BRANIN: {
-            const float b = 5.1f / (4.0f * 9.8696044010893586f), c = 5.0f / 3.14159265358979f;
-            const float tt = 1.0f / (8.0f * 3.14159265358979f);
-            const float q = y - b * x * x + c * x - 6.0f;
-            return q * q + 10.0f * (1.0f - tt) * cosf(x) + 10.0f;
-        }
-        case AT2_FUNC_CAMEL: {
-            const float x2 = x * x, y2 = y * y;
-            return (4.0f - 2.1f * x2 + x2 * x2 / 3.0f) * x2 + x * y + (-4.0f + 4.0f * y2) * y2;
-        }
-        case AT2_FUNC_WAVE: {
-            const float r2 = x * x + y * y;
-            return -(1.0f + cosf(12.0f * sqrtf(r2))) / (0.5f * r2 + 2.0f);
-        }
-        default:  // AT2_FUNC_RASTRIGIN
-            return 20.0f + ((x * x - 10.0f * cospif(2.0f * x)) + (y * y - 10.0f * cospif(2.0f * y)));
-    }
-}
 
 template <typename T>
 struct Params {
     at2_plan plan;
     Fam<T> fam[AT2_MAX_FAMILIES];
-    int func, F, scheduler, descending;
-    float x_min, x_rng, y_min, y_rng, noise;
+    ArmSpace sp;
+    int descending;
     const T* tables;
     long long n_reps, rep_offset;
-    uint32_t key0, key1;
     int G;            // repetitions per tile
     long long n_tiles;
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
@@ -144,50 +59,14 @@ struct Params {
     T* ckpt_loss;
 };
 
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float2 lds64(uint32_t addr) {
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void team_barrier(int team, int team_warps) {
-    if (team_warps == 1)
-        __syncwarp();
-    else
-        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_warps * 32) : "memory");
-}
-
-// arm draw of the Philox path: x, y uniform on the domain (core/params.py:36), family
-// (core/shape_family_scheduler.py:61,75), z ~ N(0,1) for the initial noise (benchmarks/opt_function_problem.py:138)
-struct ArmDraw {
-    float x, y, z;
-    int fam;
-};
-template <typename T>
-__device__ __forceinline__ ArmDraw draw_arm(const Params<T>& p, unsigned long long gid, int arm) {
-    const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
-    ArmDraw d;
-    d.x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, p.x_rng, p.x_min);
-    d.y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, p.y_rng, p.y_min);
-    d.fam = p.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)p.F) : arm % p.F;
-    const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-    const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, p.key0, p.key1);
-    d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
-    return d;
-}
-
-template <typename T, int MODE, bool HAS_SMOOTH, int CK>
 #ifndef AT2_HB_MIN_BLOCKS
-#define AT2_HB_MIN_BLOCKS 1
+#define AT2_HB_MIN_BLOCKS 4
 #endif
+template <typename T, int MODE, bool HAS_SMOOTH, int CK>
 __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __grid_constant__ Params<T> p) {
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.F;
+    const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
     const int tab_elems = (L.total() + 3) & ~3;
     T* s_tab = reinterpret_cast<T*>(smem_raw);
@@ -201,6 +80,8 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
     __syncthreads();
     const T* s_rec = s_tab + L.off_rec();
     const T* s_sg = s_tab + L.off_sg();
+    const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
+                       L.sg_stride};
 
     unsigned char* my_team = team_base + (size_t)team * p.team_bytes;
     T* s_ck = reinterpret_cast<T*>(my_team);                                          // [C][stride]
@@ -225,37 +106,32 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
             const int rep_l = ii / A, arm = ii - rep_l * A;
             const long long rep_g = rep0 + rep_l;                   // index into per-call arrays
             const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + arm;
-            T f1, fn;
-            int fam_i;
             if constexpr (MODE == MODE_PHILOX) {
-                const ArmDraw d = draw_arm(p, gid, arm);
-                fam_i = d.fam;
-                const float f = base_function(p.func, d.x, d.y);
-                fn = (T)(f - (float)p.fam[fam_i].s1);                       // opt_function_simulation_problem.py:63
-                f1 = (T)((f + p.noise * d.z) - (float)p.fam[fam_i].s0);     // :62,:64
+                const ArmDraw d = draw_arm(p.sp, gid, arm);
+                const Fam<T> fam = p.fam[d.fam];
+                const float f = base_function(p.sp.func, d.x, d.y);
+                const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
+                const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
+                philox_trajectory<T, HAS_SMOOTH, CK>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
+                                                     (float)fam.up, fam.pw_off, gid, p.sp.key0, p.sp.key1, R, s_ck + ii,
+                                                     p.stride, C);
             } else {
                 const long long a_g = rep_g * A + arm;
-                f1 = active ? p.f1[a_g] : (T)0;
-                fn = active ? p.fn[a_g] : (T)0;
-                fam_i = active ? p.family[a_g] : 0;
-            }
-            const Fam<T> fam = p.fam[fam_i];
-            const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-
-            T f = f1;
-            int t = active ? 1 : R;   // next trajectory position to produce (0-based: f is fs[t-1]); R = finished
-            int nc = 0;               // next checkpoint to capture (raw arms; smooth arms never capture)
-            int next_pos = (smooth || !active) ? INT_MAX : s_ckpos[0];   // padding lanes never capture
-            T acc[CK];
+                const T f1 = active ? p.f1[a_g] : (T)0;
+                const T fn = active ? p.fn[a_g] : (T)0;
+                const Fam<T> fam = p.fam[active ? p.family[a_g] : 0];
+                const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+                T f = f1;
+                int nc = 0;               // next checkpoint to capture (raw arms; smooth arms never capture)
+                int next_pos = (smooth || !active) ? INT_MAX : s_ckpos[0];
+                T acc[CK];
 #pragma unroll
-            for (int c = 0; c < CK; ++c) acc[c] = HAS_SMOOTH ? s_sg[c] * f : (T)0;  // sg[0][c] * fs[0]
-            if (active && next_pos == 0) {
-                s_ck[ii] = f;
-                nc = 1;
-                next_pos = s_ckpos[1];
-            }
-
-            if constexpr (MODE == MODE_PREDRAWN) {
+                for (int c = 0; c < CK; ++c) acc[c] = HAS_SMOOTH ? s_sg[c] * f : (T)0;  // sg[0][c] * fs[0]
+                if (active && next_pos == 0) {
+                    s_ck[ii] = f;
+                    nc = 1;
+                    next_pos = s_ckpos[1];
+                }
                 const T* grow = p.gamma + (rep_g * A + arm) * (long long)(R - 1);
                 for (int tt = 1; tt < R; ++tt) {
                     if (!active) break;
@@ -277,92 +153,12 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
                         next_pos = s_ckpos[nc];
                     }
                 }
-            } else {
-                // One Philox block = 2 normals (Box-Muller) + 2 uniforms = 2 Marsaglia-Tsang attempts.  A lane's epoch
-                // is the shared-memory address of its (family, step) record: an accepted attempt advances it by one
-                // record, a rejected one leaves it, a finished (or padding) lane sits on the sentinel record whose NaN
-                // slope fails every acceptance test - so the attempt is branch-free and needs no bounds check.  The
-                // rare checkpoint capture is tested once per Philox block.  The next block is issued before the
-                // current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
-                uint32_t rec_base = (uint32_t)__cvta_generic_to_shared(s_rec) + (uint32_t)fam.pw_off * (AT2_REC * 4u);
-                uint32_t sg_base = (uint32_t)__cvta_generic_to_shared(s_sg);
-                uint32_t k0 = p.key0, k1 = p.key1;
-                asm volatile("" : "+r"(rec_base), "+r"(sg_base), "+r"(k0), "+r"(k1));   // keep them in registers
-                const uint32_t end_addr = rec_base + (uint32_t)R * (AT2_REC * 4u);
-                uint32_t addr = rec_base + (uint32_t)t * (AT2_REC * 4u);       // record of the step to produce next
-                uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
-                const float fnf = (float)fn, mlc = (float)fam.ml, upc = (float)fam.up;
-                float ff = (float)f;
-                const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-                auto attempt = [&](float x, float u) {
-                    const float4 gm = lds128(addr);                               // d, c, d*log2e, d*scale
-                    const float2 pw = lds64(addr + 16u);                          // P, P11
-                    const float v = fmaf(gm.y, x, 1.0f);
-                    const float v3 = v * v * v;
-                    // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
-                    const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-                    const bool ok = v > 0.0f && fast_lg2(u) < rhs;
-                    const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y);
-                    ff = ok ? fnew : ff;
-                    if constexpr (HAS_SMOOTH) {
-                        const float fs = (ok && smooth) ? ff : 0.0f;
-                        const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(L.sg_stride * 4);
-                        if constexpr (CK <= 4) {
-                            const float4 w = lds128(a);
-                            acc[0] = fmaf(w.x, fs, acc[0]), acc[1] = fmaf(w.y, fs, acc[1]);
-                            acc[2] = fmaf(w.z, fs, acc[2]), acc[3] = fmaf(w.w, fs, acc[3]);
-                        } else {
+                if (HAS_SMOOTH) {
+                    if (active && smooth) {
 #pragma unroll
-                            for (int c4 = 0; c4 < CK; c4 += 4) {
-                                const float4 w = lds128(a + c4 * 4u);
-                                acc[c4] = fmaf(w.x, fs, acc[c4]);
-                                if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
-                                if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
-                                if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
-                            }
-                        }
+                        for (int c = 0; c < CK; ++c)
+                            if (c < C) s_ck[c * p.stride + ii] = acc[c];
                     }
-                    addr += ok ? (AT2_REC * 4u) : 0u;
-                };
-                auto consume = [&](const At2U4& r) {
-                    const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
-                    const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                     // sqrt(-2 ln u1)
-                    const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;                       // [-pi, pi)
-                    const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));                    // (0,1]
-                    const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
-                    attempt(rad * fast_cos(ang), ua);
-                    const float f_mid = ff;
-                    const uint32_t addr_mid = addr;
-                    attempt(rad * fast_sin(ang), ub);
-                    // checkpoint capture (raw arms): position cap was produced by the first attempt if the epoch had
-                    // already moved past it in between, by the second otherwise
-                    while (addr > cap_addr) {
-                        s_ck[nc * p.stride + ii] = (T)(addr_mid > cap_addr ? f_mid : ff);
-                        ++nc;
-                        const int np = s_ckpos[nc];
-                        cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
-                    }
-                };
-                uint32_t ctr = 1;
-                At2U4 ra = at2_philox10(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1), rb;
-                while (true) {
-                    if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-                    rb = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
-                    ++ctr;
-                    consume(ra);
-                    if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-                    ra = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
-                    ++ctr;
-                    consume(rb);
-                }
-                t = R;
-                f = (T)ff;
-            }
-            if (HAS_SMOOTH) {
-                if (active && smooth) {
-#pragma unroll
-                    for (int c = 0; c < CK; ++c)
-                        if (c < C) s_ck[c * p.stride + ii] = acc[c];
                 }
             }
         }
@@ -384,7 +180,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
             if (lane == 0 && p.best_xy != nullptr) {
                 if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm;
-                    const ArmDraw d = draw_arm(p, gid, best_arm);
+                    const ArmDraw d = draw_arm(p.sp, gid, best_arm);
                     p.best_xy[2 * rep_g] = (T)d.x, p.best_xy[2 * rep_g + 1] = (T)d.y;
                 } else {
                     const long long a_g = rep_g * A + best_arm;
@@ -520,10 +316,10 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
         p->fam[f].smooth = cfg->fam[f].is_smooth;
         p->fam[f].pw_off = f * (plan->R + 1);
     }
-    p->func = cfg->func, p->F = cfg->n_families, p->scheduler = cfg->scheduler, p->descending = cfg->descending;
-    p->x_min = (float)cfg->x_min, p->x_rng = (float)(cfg->x_max - cfg->x_min);
-    p->y_min = (float)cfg->y_min, p->y_rng = (float)(cfg->y_max - cfg->y_min);
-    p->noise = (float)cfg->init_noise;
+    p->sp.func = cfg->func, p->sp.F = cfg->n_families, p->sp.scheduler = cfg->scheduler, p->descending = cfg->descending;
+    p->sp.x_min = (float)cfg->x_min, p->sp.x_rng = (float)(cfg->x_max - cfg->x_min);
+    p->sp.y_min = (float)cfg->y_min, p->sp.y_rng = (float)(cfg->y_max - cfg->y_min);
+    p->sp.noise = (float)cfg->init_noise;
     p->tables = (const T*)d_tables;
     p->n_reps = n_reps;
     p->ofe = (T*)out->d_ofe, p->ofe_arm = out->d_ofe_arm, p->best_xy = (T*)out->d_best_xy;
@@ -548,7 +344,7 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
     p.rep_offset = rep_offset;
-    p.key0 = (uint32_t)seed, p.key1 = (uint32_t)(seed >> 32);
+    p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
     return launch_dispatch<float, MODE_PHILOX>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
 }
 

@@ -1,0 +1,258 @@
+// Device-side core of the Gamma-process simulation, shared by the Hyperband kernel (hb_sim.cu) and the TPE / hybrid
+// kernel (tpe_sim.cu).  Reference: core/simulation_evaluator.py:36-48,84-116 (Gamma draw + recurrence),
+// benchmarks/opt_function_problem.py:49-138 (test functions), core/arm.py:44-55 + core/params.py:36 (arm draw),
+// core/shape_family_scheduler.py:50-77 (family choice).
+#pragma once
+#include <climits>
+
+#include "at2_common.cuh"
+
+namespace {
+
+enum { MODE_PHILOX = 0, MODE_PREDRAWN = 1 };
+
+// ---- arithmetic policies ---------------------------------------------------------------------------------------------
+// double: the reference's float64 operation order with explicitly un-fused IEEE ops (bit-exact parity path).
+// float : production arithmetic, contraction to FFMA welcome.
+template <typename T>
+struct Fam {
+    T ml, up, s0, s1;  // float: ml = ml_agg/100 folded; double: raw ml_agg
+    int smooth, pw_off;
+};
+
+__device__ __forceinline__ double step_exact(double f, double g, int t, int R, double fn, double ml_agg, double up_spik,
+                                             double P, double P11) {
+    if (g == 2.0) return f;                                                        // :100-101
+    if (g > 2.0) {                                                                 // :102-107
+        const double debt = __dsub_rn(fn, f);
+        const double ml = __dadd_rn(f, __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(g, 2.0), ml_agg), debt), 100.0));
+        return __dadd_rn(ml, __dmul_rn(__dsub_rn(fn, ml), P));
+    }
+    const double up = __dadd_rn(f, __ddiv_rn(__dmul_rn(up_spik, 1.0), __dadd_rn(1.0, g)));  // :108-115
+    double nxt = __dadd_rn(up, __dmul_rn(__dsub_rn(fn, up), P11));
+    if (R - t == 1) nxt = fn;
+    return nxt;
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sin(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_cos(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11) {
+    // production arithmetic of simulation_evaluator.py:99-115; at the last step P = P11 = 1 so both branches land on
+    // f_n to within one rounding (the reference's float64 path has the same property on its down branch)
+    const float ml = fmaf((g - 2.0f) * mlc, fn - f, f);
+    const float dn = fmaf(fn - ml, P, ml);
+    const float up = fmaf(upc, fast_rcp(1.0f + g), f);
+    const float un = fmaf(fn - up, P11, up);
+    return g > 2.0f ? dn : (g < 2.0f ? un : f);
+}
+
+// ---- test functions in FP32 (benchmarks/opt_function_problem.py:49-138) ------------------------------------------------
+__device__ float base_function(int func, float x, float y) {
+    switch (func) {
+        case AT2_FUNC_EGG:
+            return -(y + 47.0f) * sinf(sqrtf(fabsf(y + 0.5f * x + 47.0f))) - x * sinf(sqrtf(fabsf(x - y - 47.0f)));
+        case AT2_FUNC_BRANIN: {
+            const float b = 5.1f / (4.0f * 9.8696044010893586f), c = 5.0f / 3.14159265358979f;
+            const float tt = 1.0f / (8.0f * 3.14159265358979f);
+            const float q = y - b * x * x + c * x - 6.0f;
+            return q * q + 10.0f * (1.0f - tt) * cosf(x) + 10.0f;
+        }
+        case AT2_FUNC_CAMEL: {
+            const float x2 = x * x, y2 = y * y;
+            return (4.0f - 2.1f * x2 + x2 * x2 / 3.0f) * x2 + x * y + (-4.0f + 4.0f * y2) * y2;
+        }
+        case AT2_FUNC_WAVE: {
+            const float r2 = x * x + y * y;
+            return -(1.0f + cosf(12.0f * sqrtf(r2))) / (0.5f * r2 + 2.0f);
+        }
+        default:  // AT2_FUNC_RASTRIGIN
+            return 20.0f + ((x * x - 10.0f * cospif(2.0f * x)) + (y * y - 10.0f * cospif(2.0f * y)));
+    }
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void team_barrier(int team, int team_warps) {
+    if (team_warps == 1)
+        __syncwarp();
+    else
+        asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(team_warps * 32) : "memory");
+}
+
+
+// Where arms live and how they are drawn (Philox path).
+struct ArmSpace {
+    int func, F, scheduler;
+    float x_min, x_rng, y_min, y_rng, noise;
+    uint32_t key0, key1;
+};
+
+// arm draw of the Philox path: x, y uniform on the domain (core/params.py:36), family
+// (core/shape_family_scheduler.py:61,75), z ~ N(0,1) for the initial noise (benchmarks/opt_function_problem.py:138)
+struct ArmDraw {
+    float x, y, z;
+    int fam;
+};
+__device__ __forceinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long gid, int arm) {
+    const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
+    ArmDraw d;
+    d.x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
+    d.y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
+    d.fam = sp.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)sp.F) : arm % sp.F;
+    const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+    const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
+    d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+    return d;
+}
+
+// Shared-memory tables of one CTA as the trajectory loop sees them.
+struct SimTables {
+    uint32_t rec_addr;     // shared-space address of rec[0][0]
+    uint32_t sg_addr;      // shared-space address of sg[0][0]
+    const int* ckpos;      // checkpoint positions (ckpt_time - 1), INT_MAX-terminated, in shared memory
+    int R, sg_stride;
+};
+
+// One arm per lane: runs the lane's Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang -> recurrence until every
+// lane of the warp has produced position stop_t - 1 (stop_t = R: the whole trajectory), writing the raw arms'
+// checkpoint losses to ck[c * stride] as their positions are produced and the smooth arms' Savitzky-Golay read-outs at
+// the end.  All 32 lanes must call it; lanes with active == false do nothing.
+//
+// One Philox block = 2 normals + 2 uniforms = 2 Marsaglia-Tsang attempts.  A lane's epoch is the shared-memory address
+// of its (family, step) record: an accepted attempt advances it by one record, a rejected one leaves it, a finished (or
+// padding) lane sits on the sentinel record whose NaN slope fails every acceptance test - so the attempt is branch-free
+// and needs no bounds check.  The rare checkpoint capture is tested once per Philox block.  The next block is issued
+// before the current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
+template <typename T, bool HAS_SMOOTH, int CK>
+__device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
+                                                  float mlc, float upc, int pw_off, unsigned long long gid, uint32_t key0,
+                                                  uint32_t key1, int stop_t, T* ck, int stride, int C) {
+    const int R = tb.R;
+    uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
+    uint32_t sg_base = tb.sg_addr;
+    uint32_t k0 = key0, k1 = key1;
+    asm volatile("" : "+r"(rec_base), "+r"(sg_base), "+r"(k0), "+r"(k1));   // keep them in registers
+    // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
+    const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
+    uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
+    int nc = 0;                                                                // next checkpoint to capture
+    int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[0];              // padding lanes never capture
+    float ff = f1;
+    float acc[CK];
+#pragma unroll
+    for (int c = 0; c < CK; ++c) acc[c] = 0.0f;
+    if constexpr (HAS_SMOOTH) {
+        const float f0 = (active && smooth) ? ff : 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < CK; c4 += 4) {                                  // sg[0][c] * fs[0]
+            const float4 w = lds128(sg_base + c4 * 4u);
+            acc[c4] = w.x * f0;
+            if (c4 + 1 < CK) acc[c4 + 1] = w.y * f0;
+            if (c4 + 2 < CK) acc[c4 + 2] = w.z * f0;
+            if (c4 + 3 < CK) acc[c4 + 3] = w.w * f0;
+        }
+    }
+    if (active && next_pos == 0) {
+        ck[0] = (T)ff;
+        nc = 1;
+        next_pos = tb.ckpos[1];
+    }
+    uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
+    const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
+    auto attempt = [&](float x, float u) {
+        const float4 gm = lds128(addr);                               // d, c, d*log2e, d*scale
+        const float2 pw = lds64(addr + 16u);                          // P, P11
+        const float v = fmaf(gm.y, x, 1.0f);
+        const float v3 = v * v * v;
+        // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
+        const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
+        const bool ok = v > 0.0f && fast_lg2(u) < rhs;
+        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y);
+        ff = ok ? fnew : ff;
+        if constexpr (HAS_SMOOTH) {
+            const float fs = (ok && smooth) ? ff : 0.0f;
+            const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4);
+#pragma unroll
+            for (int c4 = 0; c4 < CK; c4 += 4) {
+                const float4 w = lds128(a + c4 * 4u);
+                acc[c4] = fmaf(w.x, fs, acc[c4]);
+                if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
+                if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
+                if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
+            }
+        }
+        addr += ok ? (AT2_REC * 4u) : 0u;
+    };
+    auto consume = [&](const At2U4& r) {
+        const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
+        const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                     // sqrt(-2 ln u1)
+        const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;                       // [-pi, pi)
+        const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));                    // (0,1]
+        const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
+        attempt(rad * fast_cos(ang), ua);
+        const float f_mid = ff;
+        const uint32_t addr_mid = addr;
+        attempt(rad * fast_sin(ang), ub);
+        // checkpoint capture (raw arms): position cap was produced by the first attempt if the epoch had already moved
+        // past it in between, by the second otherwise
+        while (addr > cap_addr) {
+            ck[nc * stride] = (T)(addr_mid > cap_addr ? f_mid : ff);
+            ++nc;
+            const int np = tb.ckpos[nc];
+            cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
+        }
+    };
+    uint32_t ctr = 1;
+    At2U4 ra = at2_philox10(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1), rb;
+    while (true) {
+        if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+        rb = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+        ++ctr;
+        consume(ra);
+        if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+        ra = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+        ++ctr;
+        consume(rb);
+    }
+    if constexpr (HAS_SMOOTH) {
+        if (active && smooth) {
+#pragma unroll
+            for (int c = 0; c < CK; ++c)
+                if (c < C) ck[c * stride] = (T)acc[c];
+        }
+    }
+}
+
+}  // namespace

@@ -1,0 +1,586 @@
+// (c) TPE: Parzen-estimator suggestion fused with the Gamma-process simulation and successive halving - the hybrids
+// (Hyperband whose first round of every bracket is a TPE run, with optional history transfer between brackets), plus
+// stand-alone TPE and random search as degenerate single-bracket plans.
+//
+// Reference call sites: optimisers/sequential/tpe_optimiser.py:40-89 (hyperopt.fmin with tpe.suggest,
+// n_startup_jobs = 10 + injected), hybrid_hyperband_tpe_optimiser.py:41-95,
+// hybrid_hyperband_tpe_with_transfer.py:50-209 (transfer predicates, latest-resource bookkeeping).  The TPE arithmetic
+// itself lives in third-party hyperopt 0.2.4 (absent from the reference tree and from this image): what is implemented
+// here is the published algorithm as restated in oracle/tpe.py - adaptive Parzen estimators over the "good"
+// (n_below = min(ceil(gamma sqrt N), 25) lowest losses) and "bad" observations of each hp.uniform hyperparameter
+// independently, 24 candidates drawn from the truncated good mixture, the candidate maximising log l(x) - log g(x).
+//
+// Mapping: one warp = one repetition.  The TPE phase of a bracket is sequential in its arms (suggestion k needs the
+// losses of arms 0..k-1 at the bracket's first resource level), so the warp's 32 lanes are spent *inside* a suggestion:
+// lanes = candidates for sampling and scoring (pairwise candidate x component kernel evaluations, components
+// broadcast from shared memory), lanes = observations for the order statistics (good/bad split, sorted insertion,
+// compaction, bandwidths).  FP32 CUDA cores + MUFU (ex2/lg2/erf); not a dense contraction, so no tensor cores.
+// Trajectories use exactly the streams and arithmetic of the Hyperband kernel (sim_core.cuh): with TPE disabled the
+// results are bit-identical to at2_hb_sim_f32.
+#include <cfloat>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+
+#include "at2_common.cuh"
+#include "halving.cuh"
+#include "sim_core.cuh"
+
+namespace {
+
+struct TpeDev {
+    int enabled, n_startup, n_cand, lf, transfer, threshold;
+    float gamma, prior_weight;
+};
+
+struct TpeParams {
+    at2_plan plan;
+    Fam<float> fam[AT2_MAX_FAMILIES];
+    ArmSpace sp;
+    TpeDev tpe;
+    int descending;
+    const float* tables;
+    long long n_reps, rep_offset;
+    int npad, cap, warp_bytes;
+    float* ofe;
+    int* ofe_arm;
+    float* best_xy;
+    float* round_best;
+    int* round_best_arm;
+    int* survivors;
+    float* ckpt_loss;
+    float* arm_xy;      // optional [n_reps][n_arms][2]
+};
+
+// warp-private working set
+struct TpeWarp {
+    float *ck, *ax, *ay, *af1, *afn, *ox, *oy, *ol;
+    float4* comp;
+    unsigned short *srt0, *srt1, *cmp, *age;
+    unsigned char *afam, *latest, *below;
+    int n_obs;
+};
+
+__device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// append observation (x, y, l) and keep the per-dimension sorted index lists sorted (stable: after equal values)
+__device__ void tpe_insert(TpeWarp& w, float x, float y, float l, int lane) {
+    const int n = w.n_obs;
+    if (lane == 0) w.ox[n] = x, w.oy[n] = y, w.ol[n] = l;
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const float* vals = d ? w.oy : w.ox;
+        unsigned short* srt = d ? w.srt1 : w.srt0;
+        const float v = d ? y : x;
+        int cnt = 0;
+        for (int j = lane; j < n; j += 32) cnt += vals[srt[j]] <= v ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        for (int base = ((n - 1) >> 5) << 5; base >= 0 && base + 31 >= cnt; base -= 32) {
+            const int j = base + lane;
+            const bool mv = j >= cnt && j < n;
+            const unsigned short e = mv ? srt[j] : 0;
+            __syncwarp();
+            if (mv) srt[j + 1] = e;
+            __syncwarp();
+        }
+        if (lane == 0) srt[cnt] = (unsigned short)n;
+        __syncwarp();
+    }
+    w.n_obs = n + 1;
+}
+
+// flag the n_below observations with the lowest losses (ties: older first) and rank every observation by age inside
+// its own set (tpe.ap_filter_trials keeps both sets in trial order; linear forgetting weighs by that order)
+__device__ void tpe_split(TpeWarp& w, int n_below, int lane) {
+    const int n = w.n_obs;
+    for (int j = lane; j < n; j += 32) w.below[j] = 0;
+    __syncwarp();
+    for (int s = 0; s < n_below; ++s) {
+        float best = FLT_MAX;
+        int bi = INT_MAX;
+        for (int j = lane; j < n; j += 32) {
+            const float l = w.ol[j];
+            if (!w.below[j] && (l < best || (l == best && j < bi))) best = l, bi = j;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) best = ob, bi = oi;
+        }
+        if (lane == 0 && bi != INT_MAX) w.below[bi] = 1;
+        __syncwarp();
+    }
+    int cb = 0, ca = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < n;
+        const bool fb = valid && w.below[j];
+        const unsigned mb = __ballot_sync(0xffffffffu, fb), ma = __ballot_sync(0xffffffffu, valid && !fb);
+        if (valid) w.age[j] = (unsigned short)(fb ? cb + __popc(mb & lanemask_lt(lane)) : ca + __popc(ma & lanemask_lt(lane)));
+        cb += __popc(mb);
+        ca += __popc(ma);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float lf_weight(int age, int n, int lf) {
+    // np.concatenate([np.linspace(1/n, 1, n - lf), np.ones(lf)])[age]   (tpe.linear_forgetting_weights)
+    const int num = n - lf;
+    if (age >= num) return 1.0f;
+    const float lo = 1.0f / (float)n;
+    return num == 1 ? lo : lo + (float)age * ((1.0f - lo) / (float)(num - 1));
+}
+
+__device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
+    return 0.5f * (1.0f + erff((x - mu) / fmaxf(1.41421356237f * sigma, 1e-12f)));
+}
+
+// Adaptive Parzen estimator (tpe.adaptive_parzen_normal + the truncation mass of tpe.GMM1_lpdf) over the observations
+// of dimension d whose `below` flag equals want_below.  Leaves comp[0..m] = {coef, mu, sqrt(log2(e)/2)/sigma, weight}
+// with coef = weight / (sigma * p_accept) (the common 1/sqrt(2 pi) cancels in l/g) and returns m + 1.
+__device__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane) {
+    const int n = w.n_obs;
+    const float* vals = d ? w.oy : w.ox;
+    const unsigned short* srt = d ? w.srt1 : w.srt0;
+    int m = 0;
+    for (int base = 0; base < n; base += 32) {                 // members in sorted order
+        const int j = base + lane;
+        const int idx = j < n ? srt[j] : 0;
+        const bool f = j < n && (w.below[idx] != 0) == want_below;
+        const unsigned mask = __ballot_sync(0xffffffffu, f);
+        if (f) w.cmp[m + __popc(mask & lanemask_lt(lane))] = (unsigned short)idx;
+        m += __popc(mask);
+    }
+    __syncwarp();
+    const float prior_mu = 0.5f * (hi + lo), prior_sigma = hi - lo;
+    int pp = 0;                                                  // np.searchsorted(sorted, prior_mu): members < prior_mu
+    for (int j = lane; j < m; j += 32) pp += vals[w.cmp[j]] < prior_mu ? 1 : 0;
+    pp = __reduce_add_sync(0xffffffffu, pp);
+    const int nc = m + 1;
+    const float minsigma = prior_sigma / fminf(100.0f, 1.0f + (float)nc), maxsigma = prior_sigma;
+    auto mu_at = [&](int p) { return p < pp ? vals[w.cmp[p]] : (p == pp ? prior_mu : vals[w.cmp[p - 1]]); };
+    float sum_w = 0.0f, sum_acc = 0.0f;
+    for (int p = lane; p < nc; p += 32) {
+        const float mu = mu_at(p);
+        float sigma, wt;
+        if (p == pp) {
+            sigma = prior_sigma, wt = cfg.prior_weight;
+        } else {
+            if (m == 1)
+                sigma = 0.5f * prior_sigma;
+            else if (p == 0)
+                sigma = mu_at(1) - mu;
+            else if (p == nc - 1)
+                sigma = mu - mu_at(p - 1);
+            else
+                sigma = fmaxf(mu - mu_at(p - 1), mu_at(p + 1) - mu);
+            sigma = fminf(fmaxf(sigma, minsigma), maxsigma);
+            const int idx = w.cmp[p < pp ? p : p - 1];
+            wt = (cfg.lf > 0 && cfg.lf < m) ? lf_weight(w.age[idx], m, cfg.lf) : 1.0f;
+        }
+        w.comp[p] = make_float4(wt, mu, sigma, 0.0f);
+        sum_w += wt;
+        sum_acc += wt * (normal_cdf(hi, mu, sigma) - normal_cdf(lo, mu, sigma));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_w += __shfl_xor_sync(0xffffffffu, sum_w, o);
+        sum_acc += __shfl_xor_sync(0xffffffffu, sum_acc, o);
+    }
+    const float inv_w = 1.0f / sum_w;
+    const float inv_acc = sum_w / sum_acc;                       // 1 / p_accept
+    __syncwarp();
+    for (int p = lane; p < nc; p += 32) {
+        const float4 c = w.comp[p];
+        const float wn = c.x * inv_w;
+        w.comp[p] = make_float4(wn * inv_acc / c.z, c.y, 0.84932180028801904f / c.z, wn);
+    }
+    __syncwarp();
+    return nc;
+}
+
+// sum_p coef_p * exp(-((x - mu_p)/sigma_p)^2 / 2) of the model currently in comp[]
+__device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) {
+    float s = 0.0f;
+    for (int p = 0; p < nc; ++p) {
+        const float4 c = w.comp[p];
+        const float z = (x - c.y) * c.z;
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z));
+        s = fmaf(c.x, e, s);
+    }
+    return s;
+}
+
+// One hyperparameter of one suggestion: candidates from the good model, argmax of log l - log g
+// (tpe.build_posterior, ap_uniform_sampler, GMM1, GMM1_lpdf, broadcast_best).
+__device__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, unsigned long long gid,
+                                 uint32_t key0, uint32_t key1, int lane) {
+    const int nb = tpe_build_model(w, d, true, lo, hi, cfg, lane);
+    // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection
+    float cand = 0.5f * (lo + hi);
+    if (lane < cfg.n_cand) {
+        for (int attempt = 0; attempt < 64; ++attempt) {
+            const At2U4 r = at2_philox10(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
+                                               (uint32_t)(gid >> 32), AT2_STREAM_TPE}, key0, key1);
+            const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f;
+            int pick = 0;
+            float cum = w.comp[0].w;
+            while (pick < nb - 1 && u >= cum) cum += w.comp[++pick].w;
+            const float u1 = fmaf((float)(r.y >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+            const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r.z >> 8) * 1.1920928955078125e-7f);
+            const float4 c = w.comp[pick];
+            const float v = fmaf(0.84932180028801904f / c.z, z, c.y);
+            if (v >= lo && v < hi) {
+                cand = v;
+                break;
+            }
+        }
+    }
+    const float l_good = tpe_mixture(w, nb, cand);
+    __syncwarp();
+    const int na = tpe_build_model(w, d, false, lo, hi, cfg, lane);
+    const float l_bad = tpe_mixture(w, na, cand);
+    float score = lane < cfg.n_cand ? fast_lg2(l_good) - fast_lg2(l_bad) : -FLT_MAX;
+    if (score != score) score = -FLT_MAX;
+    int who = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                          // np.argmax: first maximum
+        const float os = __shfl_xor_sync(0xffffffffu, score, o);
+        const int ow = __shfl_xor_sync(0xffffffffu, who, o);
+        if (os > score || (os == score && ow < who)) score = os, who = ow;
+    }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, cand, who);
+}
+
+__device__ __forceinline__ bool transferable(int mode, int r_arm, double r_bracket, int R, int threshold) {
+    switch (mode) {   // hybrid_hyperband_tpe_with_transfer.py:161-209
+        case AT2_TRANSFER_LONGEST: return r_arm >= R;
+        case AT2_TRANSFER_ALL: return (double)r_arm >= r_bracket;
+        case AT2_TRANSFER_SAME: return (double)r_arm == r_bracket;
+        case AT2_TRANSFER_THRESHOLD: return r_arm >= threshold && (double)r_arm >= r_bracket;
+        default: return false;
+    }
+}
+
+template <bool HAS_SMOOTH, int CK>
+__global__ void __launch_bounds__(128) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, cap = p.cap;
+    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    const int tab_elems = (L.total() + 3) & ~3;
+    float* s_tab = reinterpret_cast<float*>(smem_raw);
+    int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4]
+    int* s_sglast = s_ckpos + AT2_MAX_CKPTS + 4;                     // [AT2_MAX_CKPTS + 4] last position a smooth read-out needs
+    unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_sglast + AT2_MAX_CKPTS + 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
+    __syncthreads();
+    const float* s_rec = s_tab + L.off_rec();
+    const float* s_sg = s_tab + L.off_sg();
+    if (tid < AT2_MAX_CKPTS + 4) {
+        int last = tid < C ? p.plan.ckpt_time[tid] - 1 : 0;
+        if (HAS_SMOOTH && tid < C)
+            for (int t = 0; t < R; ++t)
+                if (s_sg[t * L.sg_stride + tid] != 0.0f) last = max(last, t);
+        s_sglast[tid] = last;
+    }
+    __syncthreads();
+    const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
+                       L.sg_stride};
+
+    // carve the warp's working set
+    unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
+    TpeWarp w;
+    float* fp = reinterpret_cast<float*>(mine);
+    w.ck = fp, fp += (size_t)C * cap;
+    w.ax = fp, fp += cap;
+    w.ay = fp, fp += cap;
+    w.af1 = fp, fp += cap;
+    w.afn = fp, fp += cap;
+    w.ox = fp, fp += cap;
+    w.oy = fp, fp += cap;
+    w.ol = fp, fp += cap;
+    w.comp = reinterpret_cast<float4*>(fp), fp += 4 * (cap + 4);
+    Key32* keys = reinterpret_cast<Key32*>(fp);
+    unsigned short* up = reinterpret_cast<unsigned short*>(keys + p.npad);
+    unsigned short* ids_a = up;
+    up += p.npad;
+    unsigned short* ids_b = up;
+    up += p.npad;
+    w.srt0 = up, up += cap;
+    w.srt1 = up, up += cap;
+    w.cmp = up, up += cap;
+    w.age = up, up += cap;
+    unsigned char* bp = reinterpret_cast<unsigned char*>(up);
+    w.afam = bp, bp += cap;
+    w.latest = bp, bp += cap;
+    w.below = bp, bp += cap;
+    w.n_obs = 0;
+
+    const bool desc = p.descending != 0;
+    const float sign = desc ? -1.0f : 1.0f;
+    const float x_lo = p.sp.x_min, x_hi = p.sp.x_min + p.sp.x_rng, y_lo = p.sp.y_min, y_hi = p.sp.y_min + p.sp.y_rng;
+    const HalvingOut<float> ho{p.ofe, p.ofe_arm, p.round_best, p.round_best_arm, p.survivors};
+
+    for (long long rep = (long long)blockIdx.x * nwarps + warp; rep < p.n_reps; rep += (long long)gridDim.x * nwarps) {
+        HalvingState<float> st{0.0f, -1, 0};
+        const unsigned long long gid0 = (unsigned long long)(p.rep_offset + rep) * (unsigned long long)A;
+        for (int b = 0; b < p.plan.n_brackets; ++b) {
+            const int n_b = p.plan.bracket_n[b], first = p.plan.bracket_first_arm[b];
+            const int rd0 = p.plan.bracket_first_round[b];
+            const int c0 = p.plan.round_ckpt[rd0];
+            const double r0 = p.plan.bracket_r0[b];   // the un-truncated float the reference compares against
+            // ---- observations injected from earlier brackets (hybrid_hyperband_tpe_with_transfer.py:116-158) ----
+            w.n_obs = 0;
+            if (p.tpe.enabled && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE) {
+                for (int a = 0; a < first; ++a) {
+                    const int lc = w.latest[a];
+                    if (transferable(p.tpe.transfer, p.plan.ckpt_time[lc], r0, R, p.tpe.threshold))
+                        tpe_insert(w, w.ax[a], w.ay[a], sign * w.ck[lc * cap + a], lane);
+                }
+            }
+            const int n_startup = p.tpe.n_startup + w.n_obs;         // tpe_optimiser.py:52
+            const bool use_tpe = p.tpe.enabled && n_b > p.tpe.n_startup;
+            // ---- round 0 arms, one after the other ----
+            for (int k = 0; k < n_b; ++k) {
+                const int arm = first + k;
+                const unsigned long long gid = gid0 + arm;
+                const ArmDraw d = draw_arm(p.sp, gid, arm);          // warp-uniform
+                float x = d.x, y = d.y;
+                if (use_tpe && w.n_obs >= n_startup) {
+                    const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
+                    tpe_split(w, (int)g, lane);
+                    x = tpe_suggest_dim(w, 0, x_lo, x_hi, p.tpe, gid, p.sp.key0, p.sp.key1, lane);
+                    y = tpe_suggest_dim(w, 1, y_lo, y_hi, p.tpe, gid, p.sp.key0, p.sp.key1, lane);
+                }
+                const Fam<float> fam = p.fam[d.fam];
+                const float f = base_function(p.sp.func, x, y);
+                const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
+                if (lane == 0) w.ax[arm] = x, w.ay[arm] = y, w.af1[arm] = f1, w.afn[arm] = fn, w.afam[arm] = (unsigned char)d.fam;
+                __syncwarp();
+                if (use_tpe && k + 1 < n_b) {
+                    // the loss TPE sees: the arm's read-out at the bracket's first resource level - simulate just far
+                    // enough (all lanes redundantly walk the same stream; the full trajectory is redone below)
+                    const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+                    const int stop_t = (smooth ? s_sglast[c0] : s_ckpos[c0]) + 1;
+                    philox_trajectory<float, HAS_SMOOTH, CK>(tb, true, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
+                                                             p.sp.key0, p.sp.key1, stop_t, w.ck + arm, cap, C);
+                    __syncwarp();
+                    tpe_insert(w, x, y, sign * w.ck[c0 * cap + arm], lane);
+                }
+            }
+            // ---- full trajectories of the bracket's arms, one arm per lane ----
+            for (int base = 0; base < n_b; base += 32) {
+                const int k = base + lane;
+                const bool active = k < n_b;
+                const int arm = first + (active ? k : 0);
+                const Fam<float> fam = p.fam[w.afam[arm]];
+                philox_trajectory<float, HAS_SMOOTH, CK>(tb, active, HAS_SMOOTH && fam.smooth != 0, w.af1[arm], w.afn[arm],
+                                                         fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.key0, p.sp.key1, R,
+                                                         w.ck + arm, cap, C);
+            }
+            __syncwarp();
+            warp_halving_bracket<float>(p.plan, b, w.ck, cap, keys, ids_a, ids_b, desc, lane, rep, ho, st, w.latest);
+        }
+        halving_finish<float>(ho, st, lane, rep);
+        if (p.ckpt_loss != nullptr)
+            for (int i = lane; i < A * C; i += 32) p.ckpt_loss[rep * A * C + i] = w.ck[(i % C) * cap + i / C];
+        if (p.arm_xy != nullptr)
+            for (int a = lane; a < A; a += 32) p.arm_xy[(rep * A + a) * 2] = w.ax[a], p.arm_xy[(rep * A + a) * 2 + 1] = w.ay[a];
+        if (lane == 0 && p.best_xy != nullptr) p.best_xy[2 * rep] = w.ax[st.best_arm], p.best_xy[2 * rep + 1] = w.ay[st.best_arm];
+        __syncwarp();
+    }
+}
+
+// stand-alone scoring entry (tests): build both models from given observations, score given candidates
+__global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __restrict__ loss, int n_obs, float lo, float hi,
+                                 TpeDev cfg, const float* __restrict__ cand, int n_cand, float* __restrict__ score_out,
+                                 float* __restrict__ model_out, int cap, int n_prob) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const size_t warp_bytes = (size_t)cap * (3 * 4 + 4 * 2 + 1) + 16 * (cap + 4) + 64;
+    unsigned char* mine = smem_raw + (size_t)warp * ((warp_bytes + 15) & ~(size_t)15);
+    TpeWarp w = {};
+    float* fp = reinterpret_cast<float*>(mine);
+    w.comp = reinterpret_cast<float4*>(fp), fp += 4 * (cap + 4);
+    w.ox = fp, fp += cap;
+    w.oy = fp, fp += cap;
+    w.ol = fp, fp += cap;
+    unsigned short* up = reinterpret_cast<unsigned short*>(fp);
+    w.srt0 = up, up += cap;
+    w.srt1 = up, up += cap;
+    w.cmp = up, up += cap;
+    w.age = up, up += cap;
+    w.below = reinterpret_cast<unsigned char*>(up);
+    for (int prob = blockIdx.x * nwarps + warp; prob < n_prob; prob += gridDim.x * nwarps) {
+        w.n_obs = 0;
+        for (int j = 0; j < n_obs; ++j)
+            tpe_insert(w, obs[(size_t)prob * n_obs + j], 0.0f, loss[(size_t)prob * n_obs + j], lane);
+        tpe_split(w, (int)fminf(ceilf(cfg.gamma * sqrtf((float)n_obs)), 25.0f), lane);
+        const int nb = tpe_build_model(w, 0, true, lo, hi, cfg, lane);
+        if (model_out != nullptr)
+            for (int q = lane; q < nb; q += 32) {
+                const float4 c = w.comp[q];
+                float* m = model_out + ((size_t)prob * 2 * (cap + 1) + q) * 3;
+                m[0] = c.w, m[1] = c.y, m[2] = 0.84932180028801904f / c.z;
+            }
+        __syncwarp();
+        float lg[8];
+        for (int q = 0; q < 8; ++q) {
+            const int j = q * 32 + lane;
+            lg[q] = j < n_cand ? tpe_mixture(w, nb, cand[(size_t)prob * n_cand + j]) : 1.0f;
+        }
+        __syncwarp();
+        const int na = tpe_build_model(w, 0, false, lo, hi, cfg, lane);
+        if (model_out != nullptr)
+            for (int q = lane; q < na; q += 32) {
+                const float4 c = w.comp[q];
+                float* m = model_out + ((size_t)prob * 2 * (cap + 1) + (cap + 1) + q) * 3;
+                m[0] = c.w, m[1] = c.y, m[2] = 0.84932180028801904f / c.z;
+            }
+        __syncwarp();
+        for (int q = 0; q < 8; ++q) {
+            const int j = q * 32 + lane;
+            if (j < n_cand)
+                score_out[(size_t)prob * n_cand + j] =
+                    0.69314718055994531f * (fast_lg2(lg[q]) - fast_lg2(tpe_mixture(w, na, cand[(size_t)prob * n_cand + j])));
+        }
+        __syncwarp();
+    }
+}
+
+int fill_tpe(const at2_tpe_config* t, TpeDev* d) {
+    AT2_REQUIRE(t != nullptr, "NULL tpe config");
+    AT2_REQUIRE(t->n_candidates >= 1 && t->n_candidates <= 32, "n_candidates %d outside [1,32]", t->n_candidates);
+    AT2_REQUIRE(t->n_startup >= 0 && t->lf >= 0 && t->gamma > 0 && t->prior_weight > 0, "bad TPE parameters");
+    AT2_REQUIRE(t->transfer >= AT2_TRANSFER_NONE && t->transfer <= AT2_TRANSFER_THRESHOLD, "unknown transfer mode %d", t->transfer);
+    d->enabled = t->enabled, d->n_startup = t->n_startup, d->n_cand = t->n_candidates, d->lf = t->lf;
+    d->transfer = t->transfer, d->threshold = t->threshold, d->gamma = (float)t->gamma, d->prior_weight = (float)t->prior_weight;
+    return AT2_OK;
+}
+
+template <bool HS, int CK>
+int launch_tpe(const TpeParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = tpe_sim_kernel<HS, CK>;
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<grid, block, smem, st>>>(p);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    return AT2_OK;
+}
+
+}  // namespace
+
+extern "C" int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resources, at2_plan* plan) {
+    AT2_REQUIRE(plan != nullptr, "at2_single_round_plan: plan is NULL");
+    AT2_REQUIRE(R >= 2 && n_evals >= 1 && n_evals < 65536, "at2_single_round_plan: need R >= 2 and 1 <= n_evals < 65536");
+    memset(plan, 0, sizeof(*plan));
+    // time = int(n_resources); python's fs[time-1] wraps for time <= 0 and raises beyond R
+    int t = n_resources >= 1 ? n_resources : R + n_resources;
+    AT2_REQUIRE(t >= 1 && t <= R, "list index out of range");
+    plan->R = R, plan->eta = 1, plan->n_brackets = 1, plan->n_rounds = 1, plan->n_arms = n_evals, plan->n_ckpts = 1;
+    plan->n_surv = 0;
+    plan->bracket_n[0] = n_evals, plan->bracket_first_arm[0] = 0, plan->bracket_first_round[0] = 0;
+    plan->bracket_first_round[1] = 1;
+    plan->round_n_eval[0] = n_evals, plan->round_keep[0] = 0, plan->round_time[0] = t, plan->round_ckpt[0] = 0;
+    plan->ckpt_time[0] = t;
+    plan->bracket_r0[0] = (double)n_resources;
+    return AT2_OK;
+}
+
+extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe,
+                               const void* d_tables, int64_t n_reps, int64_t rep_offset, uint64_t seed,
+                               const at2_hb_outputs* out, float* d_arm_xy, void* stream) {
+    at2_reset_launch_count();
+    AT2_REQUIRE(plan && cfg && d_tables && out, "at2_tpe_sim_f32: NULL plan/config/tables/outputs");
+    AT2_REQUIRE(n_reps > 0 && rep_offset >= 0, "at2_tpe_sim_f32: n_reps must be positive and rep_offset >= 0");
+    AT2_REQUIRE(plan->n_arms > 0 && plan->n_arms < 65536 && plan->n_rounds > 0 && plan->n_ckpts > 0 &&
+                    plan->n_ckpts <= AT2_MAX_CKPTS, "at2_tpe_sim_f32: plan is empty or malformed");
+    AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_tpe_sim_f32: n_families %d outside [1,%d]",
+                cfg->n_families, AT2_MAX_FAMILIES);
+    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_tpe_sim_f32: unknown func id %d", cfg->func);
+    const int has_smooth = at2_cfg_has_smooth(cfg);
+    AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
+                "If mode is 'interp', window_length must be less than or equal to the size of x.");
+    TpeParams p = {};
+    int rc = fill_tpe(tpe, &p.tpe);
+    if (rc != AT2_OK) return rc;
+    p.plan = *plan;
+    for (int f = 0; f < cfg->n_families; ++f) {
+        p.fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
+        p.fam[f].up = (float)cfg->fam[f].up_spik;
+        p.fam[f].s0 = (float)cfg->fam[f].start_shift;
+        p.fam[f].s1 = (float)cfg->fam[f].end_shift;
+        p.fam[f].smooth = cfg->fam[f].is_smooth;
+        p.fam[f].pw_off = f * (plan->R + 1);
+    }
+    p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
+    p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
+    p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);
+    p.sp.noise = (float)cfg->init_noise;
+    p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    p.tables = (const float*)d_tables;
+    p.n_reps = n_reps, p.rep_offset = rep_offset;
+    p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
+    p.round_best = (float*)out->d_round_best, p.round_best_arm = out->d_round_best_arm;
+    p.survivors = out->d_survivors, p.ckpt_loss = (float*)out->d_ckpt_loss, p.arm_xy = d_arm_xy;
+    p.npad = halving_npad(plan);
+    p.cap = (plan->n_arms + 31) & ~31;
+    const int C = plan->n_ckpts;
+    size_t wb = (size_t)p.cap * ((C + 7) * 4 + 4 * 2 + 3) + 16 * (size_t)(p.cap + 4) + (size_t)p.npad * (8 + 4);
+    p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
+    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    int dev = 0, max_smem = 0, sms = 0;
+    AT2_CUDA_CHECK(cudaGetDevice(&dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int nwarps = 4;
+    while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
+    const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
+    if (smem > (size_t)max_smem) {
+        at2_set_error("at2_tpe_sim_f32 needs %zu B of shared memory per CTA (%d arms); device limit %d B", smem, plan->n_arms, max_smem);
+        return AT2_ELIMIT;
+    }
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16 / nwarps * 4) per_sm = 16 / nwarps * 4;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (n_reps + nwarps - 1) / nwarps;
+    if (grid > need) grid = need;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!has_smooth) return launch_tpe<false, 1>(p, (int)grid, nwarps * 32, smem, st);
+    if (C <= 4) return launch_tpe<true, 4>(p, (int)grid, nwarps * 32, smem, st);
+    if (C <= 8) return launch_tpe<true, 8>(p, (int)grid, nwarps * 32, smem, st);
+    return launch_tpe<true, 16>(p, (int)grid, nwarps * 32, smem, st);
+}
+
+extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low,
+                                 double high, const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates,
+                                 float* d_scores, float* d_models, void* stream) {
+    at2_reset_launch_count();
+    TpeDev cfg;
+    const int rc = fill_tpe(tpe, &cfg);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(d_obs && d_loss && d_candidates && d_scores, "at2_tpe_score_f32: NULL pointer");
+    AT2_REQUIRE(n_obs >= 1 && n_obs <= 4096 && n_problems >= 1 && n_candidates >= 1 && n_candidates <= 256 && high > low,
+                "at2_tpe_score_f32: bad sizes (1 <= n_obs <= 4096, 1 <= n_candidates <= 256, low < high)");
+    const int cap = (n_obs + 31) & ~31;
+    const size_t warp_bytes = (((size_t)cap * (3 * 4 + 4 * 2 + 1) + 16 * (size_t)(cap + 4) + 64) + 15) & ~(size_t)15;
+    const int nwarps = 4;
+    const size_t smem = warp_bytes * nwarps;
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(tpe_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (n_problems + nwarps - 1) / nwarps;
+    tpe_score_kernel<<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(d_obs, d_loss, n_obs, (float)low, (float)high, cfg,
+                                                                         d_candidates, n_candidates, d_scores, d_models, cap,
+                                                                         n_problems);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    return AT2_OK;
+}

@@ -67,6 +67,8 @@ typedef struct at2_plan {
                                                    is 0 (python fs[-1]; e.g. R=729, eta=3) */
     int32_t round_ckpt[AT2_MAX_ROUNDS];         /* index of round_time in ckpt_time */
     int32_t ckpt_time[AT2_MAX_CKPTS];           /* ascending */
+    double bracket_r0[AT2_MAX_BRACKETS];        /* r = R*eta**(-s) as the float the reference computes (transfer
+                                                   predicates compare against it un-truncated) */
 } at2_plan;
 
 /* One shape family, core/shape_family_scheduler.py:10-17. */
@@ -145,6 +147,48 @@ int at2_hb_sim_predrawn_f64(const at2_plan* plan, const at2_sim_config* cfg, con
 int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                             const float* d_f1, const float* d_fn, const int32_t* d_family, const float* d_gamma,
                             const float* d_xy, const at2_hb_outputs* out, void* stream);
+
+/* ---- (c): TPE / Hyperband-TPE hybrids on the simulation problem ----------------------------------------------------- */
+
+#define AT2_TRANSFER_NONE 0       /* HybridHyperbandTpeOptimiser / ...NoTransferOptimiser */
+#define AT2_TRANSFER_ALL 1        /* ...TransferAllOptimiser      (hybrid_hyperband_tpe_with_transfer.py:177-186) */
+#define AT2_TRANSFER_LONGEST 2    /* ...TransferLongestOptimiser  (:170-174) */
+#define AT2_TRANSFER_SAME 3       /* ...TransferSameOptimiser     (:189-198) */
+#define AT2_TRANSFER_THRESHOLD 4  /* ...TransferThresholdOptimiser (:201-209) */
+
+/* hyperopt.tpe.suggest parameters as the reference uses them (tpe_optimiser.py:51-53 passes only n_startup_jobs;
+ * the rest are hyperopt 0.2.4 defaults: gamma 0.25, 24 candidates, prior weight 1, linear forgetting 25). */
+typedef struct at2_tpe_config {
+    int32_t enabled;       /* 0: first-round arms are random (plain Hyperband / random search) */
+    int32_t n_startup;     /* 10; injected trials are added on top (tpe_optimiser.py:52) */
+    int32_t n_candidates;  /* 24 (<= 32: one candidate per lane) */
+    int32_t lf;            /* 25 */
+    int32_t transfer;      /* AT2_TRANSFER_* */
+    int32_t threshold;     /* n_res_transfer_threshold of the Threshold variant */
+    double gamma;          /* 0.25 */
+    double prior_weight;   /* 1.0 */
+} at2_tpe_config;
+
+/* Plan of a stand-alone optimiser that evaluates n_evals arms once at n_resources: TpeOptimiser
+ * (tpe_optimiser.py:40-60) with tpe.enabled = 1, RandomOptimiser (random_optimiser.py:39-58) with enabled = 0. */
+int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resources, at2_plan* plan);
+
+/* Hyperband whose first round of every bracket is a TPE run (+ history transfer), fused with simulation and halving:
+ * replaces the repetition loop of experiments/run_simulation.py:147-157 for methods sim(hb+tpe), sim(hb+tpe+transfer+*),
+ * sim(tpe), sim(random).  Same tables/outputs as at2_hb_sim_f32; with tpe->enabled == 0 and a Hyperband plan the results
+ * are bit-identical to at2_hb_sim_f32.  d_arm_xy (optional): float[n_reps][n_arms][2] hyperparameters of every arm. */
+int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe, const void* d_tables,
+                    int64_t n_reps, int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* d_arm_xy,
+                    void* stream);
+
+/* Parzen-estimator scoring alone (parity of the estimator arithmetic): for each of n_problems independent 1-D
+ * hp.uniform(low, high) problems with n_obs observations (d_obs, d_loss: float[n_problems][n_obs], trial order), build the
+ * good/bad adaptive Parzen models and return log l(x) - log g(x) for the given candidates
+ * (d_candidates, d_scores: float[n_problems][n_candidates]).  d_models (optional):
+ * float[n_problems][2][cap+1][3] = (weight, mu, sigma) of the good then the bad model, cap = n_obs rounded up to 32. */
+int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low, double high,
+                      const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates, float* d_scores,
+                      float* d_models, void* stream);
 
 /* ---- (d): closest-known-loss-function approximation ------------------------------------------------------------------ */
 
