@@ -6,6 +6,8 @@ import torch
 
 from tests.helpers import GOLDEN, hb_case_names, load_hb_case
 
+import autotune.b200  # noqa: F401,E402  (registers torch.ops.at2.*)
+
 pytestmark = pytest.mark.gpu
 
 FAM6 = [(1.5, 10, 15, False, 0, 200), (0.5, 7, 10, False, 0, 200), (0.2, 4, 7, True, 0, 200),

@@ -6,6 +6,8 @@ import torch
 from oracle.kde import epdf
 from tests.helpers import GOLDEN
 
+import autotune.b200  # noqa: F401,E402  (registers torch.ops.at2.*)
+
 pytestmark = pytest.mark.gpu
 
 CFG = {

@@ -7,6 +7,8 @@ import torch
 from oracle import known_fn as okf
 from tests.helpers import GOLDEN
 
+import autotune.b200  # noqa: F401,E402  (registers torch.ops.at2.*)
+
 pytestmark = pytest.mark.gpu
 
 DOMS = {'mnist': (okf.MNIST_DOMAIN, 425, ()), 'cifar': (okf.CIFAR_DOMAIN, 300,
