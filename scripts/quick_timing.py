@@ -15,11 +15,11 @@ EGG = [(1.5, 10, 15, False, 0, 1000), (0.5, 7, 10, False, 0, 1000), (0.2, 4, 7, 
 for name, spec, n in [('branin-flat R81', HyperbandSimSpec('branin', FLAT, 81, 3, 0), 100000),
                       ('rastrigin-6fam R81', HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10), 100000),
                       ('egg-3fam R243', HyperbandSimSpec('egg', EGG, 243, 3, 10), 20000)]:
-    for _ in range(3):
+    for _ in range(30):          # ~100 ms of work: lets the clocks ramp up before timing
         run_hyperband_repetitions(spec, n, seed=0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 20
     e0.record()
     for i in range(reps):
         out = run_hyperband_repetitions(spec, n, seed=i)
