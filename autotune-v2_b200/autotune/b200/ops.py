@@ -234,3 +234,24 @@ def tpe_score(obs: torch.Tensor, loss: torch.Tensor, low: float, high: float, tp
                                             candidates.data_ptr(), candidates.shape[1], scores.data_ptr(),
                                             models.data_ptr(), _stream_ptr(obs.device)))
     return [scores, models]
+
+
+@torch.library.custom_op('at2::sim_trajectories', mutates_args=(), device_types='cuda')
+def sim_trajectories(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, f1: torch.Tensor,
+                     fn: torch.Tensor, family: torch.Tensor, stream_id: torch.Tensor, seed: int) -> torch.Tensor:
+    """Raw trajectories [n_arms, R] of the given arms (at2_sim_trajectories_f32)."""
+    for name, t, dt in (('tables', tables, torch.float32), ('f1', f1, torch.float32), ('fn', fn, torch.float32),
+                        ('family', family, torch.int32), ('stream_id', stream_id, torch.int64)):
+        _require_cuda(t, name)
+        if t.dtype != dt or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be contiguous {dt}')
+    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
+    n = f1.numel()
+    if fn.numel() != n or family.numel() != n or stream_id.numel() != n:
+        raise RuntimeError('f1, fn, family and stream_id must have the same length')
+    with torch.cuda.device(f1.device):
+        raw = torch.empty(n, plan.R, device=f1.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_sim_trajectories_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n, f1.data_ptr(),
+                                                   fn.data_ptr(), family.data_ptr(), stream_id.data_ptr(),
+                                                   seed & 0xFFFFFFFFFFFFFFFF, raw.data_ptr(), _stream_ptr(f1.device)))
+    return raw

@@ -243,6 +243,14 @@ int64_t at2_kde_workspace_floats(int64_t n, int32_t G);
 int at2_kde_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
                 float* d_density, float* d_workspace, int64_t workspace_floats, void* stream);
 
+/* Full-trajectory output (inspection / per-evaluator API, core/simulation_evaluator.py:84-116): raw trajectory
+ * d_raw[a][0..R-1] of n_arms arms given their first value d_f1[a], target d_fn[a], family index and Philox stream id.
+ * Arm `a` of repetition `rep` in at2_hb_sim_f32 has stream id (rep_offset + rep) * n_arms + a; for that id the values
+ * at the Hyperband checkpoints are bit-identical to the fused kernel's. */
+int at2_sim_trajectories_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_arms,
+                             const float* d_f1, const float* d_fn, const int32_t* d_family, const uint64_t* d_stream_id,
+                             uint64_t seed, float* d_raw, void* stream);
+
 /* Number of kernel launches the last at2_* call on this thread enqueued (for bench.py's gpu_launches). */
 int32_t at2_last_launch_count(void);
 
