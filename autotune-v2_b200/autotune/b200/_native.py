@@ -87,7 +87,7 @@ def _load():
         'at2_hb_sim_predrawn_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, vp,
                                               C.POINTER(HbOutputs), vp]),
         'at2_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
-        'at2_fma_peak_probe': (C.c_int, [i32, i32, i64, vp, vp]),
+        'at2_fma_peak_probe': (C.c_int, [i32, i32, i64, i32, vp, vp]),
         'at2_sim_trajectories_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, u64, vp, vp]),
         'at2_single_round_plan': (C.c_int, [i32, i32, i32, C.POINTER(Plan)]),
         'at2_tpe_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), C.POINTER(TpeConfig), vp, i64, i64, u64,

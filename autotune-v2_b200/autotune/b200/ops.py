@@ -98,10 +98,10 @@ def hb_sim_predrawn(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: t
 
 
 @torch.library.custom_op('at2::fma_peak_probe', mutates_args=('sink',), device_types='cuda')
-def fma_peak_probe(sink: torch.Tensor, blocks: int, threads: int, iters: int) -> None:
+def fma_peak_probe(sink: torch.Tensor, blocks: int, threads: int, iters: int, variant: int) -> None:
     _require_cuda(sink, 'sink')
     with torch.cuda.device(sink.device):
-        nat.check(nat.lib.at2_fma_peak_probe(blocks, threads, iters, sink.data_ptr(), _stream_ptr(sink.device)))
+        nat.check(nat.lib.at2_fma_peak_probe(blocks, threads, iters, variant, sink.data_ptr(), _stream_ptr(sink.device)))
 
 
 @torch.library.custom_op('at2::kde', mutates_args=(), device_types='cuda')

@@ -377,22 +377,37 @@ extern "C" int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_confi
 }
 
 // ---- FP32 FMA micro-benchmark (roofline denominator measured in the same run) -----------------------------------------
+// 16 independent accumulator chains per thread; variant 0: a = a*m + c with m, c in registers (3 distinct sources),
+// variant 1: a = a*m + a (2 distinct sources), variant 2: a = a*1.0000001f + 1e-9f (immediate operands).  The caller
+// takes the best of the variants as the FFMA peak.
+template <int VARIANT>
 __global__ void fma_probe_kernel(long long iters, float* sink) {
-    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
-          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = threadIdx.x * 1e-3f + k;
     const float m = 0.999f + blockIdx.x * 1e-9f, c = 1e-3f;
     for (long long i = 0; i < iters; ++i) {
-        a0 = fmaf(a0, m, c), a1 = fmaf(a1, m, c), a2 = fmaf(a2, m, c), a3 = fmaf(a3, m, c);
-        a4 = fmaf(a4, m, c), a5 = fmaf(a5, m, c), a6 = fmaf(a6, m, c), a7 = fmaf(a7, m, c);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (VARIANT == 0) a[k] = fmaf(a[k], m, c);
+            if (VARIANT == 1) a[k] = fmaf(a[k], m, a[k]);
+            if (VARIANT == 2) a[k] = fmaf(a[k], 0.99999988f, 1e-9f);
+        }
     }
-    const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-    if (s == 123.456f) sink[0] = s;  // never true; keeps the chain alive
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 123.456f) sink[0] = s;  // never true; keeps the chains alive
 }
 
-extern "C" int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, float* d_sink, void* stream) {
+extern "C" int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, int32_t variant, float* d_sink, void* stream) {
     at2_reset_launch_count();
     AT2_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && d_sink, "at2_fma_peak_probe: bad argument");
-    fma_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, d_sink);
+    AT2_REQUIRE(variant >= 0 && variant <= 2, "at2_fma_peak_probe: variant must be 0, 1 or 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (variant == 0) fma_probe_kernel<0><<<blocks, threads, 0, st>>>(iters, d_sink);
+    if (variant == 1) fma_probe_kernel<1><<<blocks, threads, 0, st>>>(iters, d_sink);
+    if (variant == 2) fma_probe_kernel<2><<<blocks, threads, 0, st>>>(iters, d_sink);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
     return AT2_OK;

@@ -258,9 +258,9 @@ int32_t at2_last_launch_count(void);
 void at2_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 
 /* FP32 FMA-only micro-benchmark used as the roofline denominator of the simulation kernel: launches a kernel doing
- * `iters` dependent-chain-free FFMAs per thread on `blocks` x `threads`; the caller times it with CUDA events.
- * flops = 2 * iters * 8 * blocks * threads (8 independent accumulators per thread). */
-int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, float* d_sink, void* stream);
+ * `iters` x 16 independent FFMAs per thread on `blocks` x `threads`; the caller times it with CUDA events and takes the
+ * best of the operand-shape variants 0..2.  flops = 2 * iters * 16 * blocks * threads. */
+int at2_fma_peak_probe(int32_t blocks, int32_t threads, int64_t iters, int32_t variant, float* d_sink, void* stream);
 
 #ifdef __cplusplus
 }
