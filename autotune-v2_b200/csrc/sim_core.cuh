@@ -71,7 +71,7 @@ __device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc
 }
 
 // ---- test functions in FP32 (benchmarks/opt_function_problem.py:49-138) ------------------------------------------------
-__device__ float base_function(int func, float x, float y) {
+__device__ __noinline__ float base_function(int func, float x, float y) {
     switch (func) {
         case AT2_FUNC_EGG:
             return -(y + 47.0f) * sinf(sqrtf(fabsf(y + 0.5f * x + 47.0f))) - x * sinf(sqrtf(fabsf(x - y - 47.0f)));
@@ -125,7 +125,7 @@ struct ArmDraw {
     float x, y, z;
     int fam;
 };
-__device__ __forceinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long gid, int arm) {
+__device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long gid, int arm) {
     const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
     ArmDraw d;
     d.x = fmaf((float)(r.x >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);

@@ -64,7 +64,7 @@ struct TpeWarp {
 __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
 // append observation (x, y, l) and keep the per-dimension sorted index lists sorted (stable: after equal values)
-__device__ void tpe_insert(TpeWarp& w, float x, float y, float l, int lane) {
+__device__ __forceinline__ void tpe_insert(TpeWarp& w, float x, float y, float l, int lane) {
     const int n = w.n_obs;
     if (lane == 0) w.ox[n] = x, w.oy[n] = y, w.ol[n] = l;
     __syncwarp();
@@ -92,7 +92,7 @@ __device__ void tpe_insert(TpeWarp& w, float x, float y, float l, int lane) {
 
 // flag the n_below observations with the lowest losses (ties: older first) and rank every observation by age inside
 // its own set (tpe.ap_filter_trials keeps both sets in trial order; linear forgetting weighs by that order)
-__device__ void tpe_split(TpeWarp& w, int n_below, int lane) {
+__device__ __forceinline__ void tpe_split(TpeWarp& w, int n_below, int lane) {
     const int n = w.n_obs;
     for (int j = lane; j < n; j += 32) w.below[j] = 0;
     __syncwarp();
@@ -140,7 +140,7 @@ __device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
 // Adaptive Parzen estimator (tpe.adaptive_parzen_normal + the truncation mass of tpe.GMM1_lpdf) over the observations
 // of dimension d whose `below` flag equals want_below.  Leaves comp[0..m] = {coef, mu, sqrt(log2(e)/2)/sigma, weight}
 // with coef = weight / (sigma * p_accept) (the common 1/sqrt(2 pi) cancels in l/g) and returns m + 1.
-__device__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane) {
+__device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane) {
     const int n = w.n_obs;
     const float* vals = d ? w.oy : w.ox;
     const unsigned short* srt = d ? w.srt1 : w.srt0;
@@ -216,33 +216,37 @@ __device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) 
 
 // One hyperparameter of one suggestion: candidates from the good model, argmax of log l - log g
 // (tpe.build_posterior, ap_uniform_sampler, GMM1, GMM1_lpdf, broadcast_best).
-__device__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, unsigned long long gid,
+__device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, unsigned long long gid,
                                  uint32_t key0, uint32_t key1, int lane) {
-    const int nb = tpe_build_model(w, d, true, lo, hi, cfg, lane);
-    // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection
     float cand = 0.5f * (lo + hi);
-    if (lane < cfg.n_cand) {
-        for (int attempt = 0; attempt < 64; ++attempt) {
-            const At2U4 r = at2_philox10(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
-                                               (uint32_t)(gid >> 32), AT2_STREAM_TPE}, key0, key1);
-            const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f;
-            int pick = 0;
-            float cum = w.comp[0].w;
-            while (pick < nb - 1 && u >= cum) cum += w.comp[++pick].w;
-            const float u1 = fmaf((float)(r.y >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-            const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r.z >> 8) * 1.1920928955078125e-7f);
-            const float4 c = w.comp[pick];
-            const float v = fmaf(0.84932180028801904f / c.z, z, c.y);
-            if (v >= lo && v < hi) {
-                cand = v;
-                break;
+    float lik[2] = {1.0f, 1.0f};
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {                   // 0: good model (sample from it), 1: bad model
+        const int nc = tpe_build_model(w, d, which == 0, lo, hi, cfg, lane);
+        if (which == 0 && lane < cfg.n_cand) {
+            // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection
+            for (int attempt = 0; attempt < 64; ++attempt) {
+                const At2U4 r = at2_philox10(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
+                                                   (uint32_t)(gid >> 32), AT2_STREAM_TPE}, key0, key1);
+                const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f;
+                int pick = 0;
+                float cum = w.comp[0].w;
+                while (pick < nc - 1 && u >= cum) cum += w.comp[++pick].w;
+                const float u1 = fmaf((float)(r.y >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+                const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r.z >> 8) * 1.1920928955078125e-7f);
+                const float4 c = w.comp[pick];
+                const float v = fmaf(0.84932180028801904f / c.z, z, c.y);
+                if (v >= lo && v < hi) {
+                    cand = v;
+                    break;
+                }
             }
         }
+        __syncwarp();
+        lik[which] = tpe_mixture(w, nc, cand);
+        __syncwarp();
     }
-    const float l_good = tpe_mixture(w, nb, cand);
-    __syncwarp();
-    const int na = tpe_build_model(w, d, false, lo, hi, cfg, lane);
-    const float l_bad = tpe_mixture(w, na, cand);
+    const float l_good = lik[0], l_bad = lik[1];
     float score = lane < cfg.n_cand ? fast_lg2(l_good) - fast_lg2(l_bad) : -FLT_MAX;
     if (score != score) score = -FLT_MAX;
     int who = lane;
@@ -267,7 +271,7 @@ __device__ __forceinline__ bool transferable(int mode, int r_arm, double r_brack
 }
 
 template <bool HAS_SMOOTH, int CK>
-__global__ void __launch_bounds__(128) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
+__global__ void __launch_bounds__(256) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, cap = p.cap;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
@@ -335,54 +339,72 @@ __global__ void __launch_bounds__(128) tpe_sim_kernel(const __grid_constant__ Tp
             const int rd0 = p.plan.bracket_first_round[b];
             const int c0 = p.plan.round_ckpt[rd0];
             const double r0 = p.plan.bracket_r0[b];   // the un-truncated float the reference compares against
-            // ---- observations injected from earlier brackets (hybrid_hyperband_tpe_with_transfer.py:116-158) ----
+            // One loop walks (1) the arms of earlier brackets that may be injected as TPE history
+            // (hybrid_hyperband_tpe_with_transfer.py:116-158), (2) the bracket's own arms one after the other (suggest ->
+            // evaluate at the first resource level -> observe), (3) the full-trajectory passes, one arm per lane.  Each big
+            // routine (insert, suggest, trajectory) is instantiated exactly once: with them duplicated the kernel was
+            // instruction-fetch bound (ncu: 49 % of stall samples in no_instructions).
             w.n_obs = 0;
-            if (p.tpe.enabled && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE) {
-                for (int a = 0; a < first; ++a) {
+            const bool inject = p.tpe.enabled && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE;
+            const bool use_tpe = p.tpe.enabled && n_b > p.tpe.n_startup;
+            const int n_prev = inject ? first : 0;
+            const int n_full = (n_b + 31) >> 5;
+            int n_startup = p.tpe.n_startup;                          // + injected, tpe_optimiser.py:52
+#pragma unroll 1
+            for (int step = -n_prev; step < n_b + n_full; ++step) {
+                bool do_insert = false, do_traj = false, t_active = false, t_smooth = false;
+                float ix = 0.0f, iy = 0.0f, il = 0.0f;
+                float t_f1 = 0.0f, t_fn = 0.0f, t_ml = 0.0f, t_up = 0.0f;
+                int t_pw = 0, t_stop = 1, t_arm = first, obs_arm = -1;
+                if (step < 0) {                                      // (1) candidate for injection
+                    const int a = first + step;
                     const int lc = w.latest[a];
                     if (transferable(p.tpe.transfer, p.plan.ckpt_time[lc], r0, R, p.tpe.threshold))
-                        tpe_insert(w, w.ax[a], w.ay[a], sign * w.ck[lc * cap + a], lane);
-                }
-            }
-            const int n_startup = p.tpe.n_startup + w.n_obs;         // tpe_optimiser.py:52
-            const bool use_tpe = p.tpe.enabled && n_b > p.tpe.n_startup;
-            // ---- round 0 arms, one after the other ----
-            for (int k = 0; k < n_b; ++k) {
-                const int arm = first + k;
-                const unsigned long long gid = gid0 + arm;
-                const ArmDraw d = draw_arm(p.sp, gid, arm);          // warp-uniform
-                float x = d.x, y = d.y;
-                if (use_tpe && w.n_obs >= n_startup) {
-                    const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
-                    tpe_split(w, (int)g, lane);
-                    x = tpe_suggest_dim(w, 0, x_lo, x_hi, p.tpe, gid, p.sp.key0, p.sp.key1, lane);
-                    y = tpe_suggest_dim(w, 1, y_lo, y_hi, p.tpe, gid, p.sp.key0, p.sp.key1, lane);
-                }
-                const Fam<float> fam = p.fam[d.fam];
-                const float f = base_function(p.sp.func, x, y);
-                const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
-                if (lane == 0) w.ax[arm] = x, w.ay[arm] = y, w.af1[arm] = f1, w.afn[arm] = fn, w.afam[arm] = (unsigned char)d.fam;
-                __syncwarp();
-                if (use_tpe && k + 1 < n_b) {
-                    // the loss TPE sees: the arm's read-out at the bracket's first resource level - simulate just far
-                    // enough (all lanes redundantly walk the same stream; the full trajectory is redone below)
-                    const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-                    const int stop_t = (smooth ? s_sglast[c0] : s_ckpos[c0]) + 1;
-                    philox_trajectory<float, HAS_SMOOTH, CK>(tb, true, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
-                                                             p.sp.key0, p.sp.key1, stop_t, w.ck + arm, cap, C);
+                        do_insert = true, ix = w.ax[a], iy = w.ay[a], il = sign * w.ck[lc * cap + a];
+                } else if (step < n_b) {                             // (2) next arm of the bracket
+                    if (step == 0) n_startup += w.n_obs;
+                    const int arm = first + step;
+                    const unsigned long long gid = gid0 + arm;
+                    const ArmDraw d = draw_arm(p.sp, gid, arm);      // warp-uniform
+                    float xy[2] = {d.x, d.y};
+                    if (use_tpe && w.n_obs >= n_startup) {
+                        const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
+                        tpe_split(w, (int)g, lane);
+#pragma unroll 1
+                        for (int dd = 0; dd < 2; ++dd)
+                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.key0,
+                                                     p.sp.key1, lane);
+                    }
+                    const Fam<float> fam = p.fam[d.fam];
+                    const float f = base_function(p.sp.func, xy[0], xy[1]);
+                    const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
+                    if (lane == 0)
+                        w.ax[arm] = xy[0], w.ay[arm] = xy[1], w.af1[arm] = f1, w.afn[arm] = fn, w.afam[arm] = (unsigned char)d.fam;
+                    if (use_tpe && step + 1 < n_b) {
+                        // the loss TPE sees: the arm's read-out at the bracket's first resource level - simulate just far
+                        // enough (all lanes redundantly walk the same stream; the full trajectory is redone in (3))
+                        t_smooth = HAS_SMOOTH && fam.smooth != 0;
+                        do_traj = true, t_active = true, t_arm = arm;
+                        t_f1 = f1, t_fn = fn, t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off;
+                        t_stop = (t_smooth ? s_sglast[c0] : s_ckpos[c0]) + 1;
+                        obs_arm = arm, ix = xy[0], iy = xy[1];
+                    }
+                } else {                                             // (3) full trajectories, one arm per lane
+                    const int k = ((step - n_b) << 5) + lane;
+                    t_active = k < n_b;
+                    t_arm = first + (t_active ? k : 0);
                     __syncwarp();
-                    tpe_insert(w, x, y, sign * w.ck[c0 * cap + arm], lane);
+                    const Fam<float> fam = p.fam[w.afam[t_arm]];
+                    do_traj = true, t_smooth = HAS_SMOOTH && fam.smooth != 0;
+                    t_f1 = w.af1[t_arm], t_fn = w.afn[t_arm], t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off, t_stop = R;
                 }
-            }
-            // ---- full trajectories of the bracket's arms, one arm per lane ----
-            for (int base = 0; base < n_b; base += 32) {
-                const int k = base + lane;
-                const bool active = k < n_b;
-                const int arm = first + (active ? k : 0);
-                const Fam<float> fam = p.fam[w.afam[arm]];
-                philox_trajectory<float, HAS_SMOOTH, CK>(tb, active, HAS_SMOOTH && fam.smooth != 0, w.af1[arm], w.afn[arm],
-                                                         fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.key0, p.sp.key1, R,
-                                                         w.ck + arm, cap, C);
+                __syncwarp();
+                if (do_traj)
+                    philox_trajectory<float, HAS_SMOOTH, CK>(tb, t_active, t_smooth, t_f1, t_fn, t_ml, t_up, t_pw, gid0 + t_arm,
+                                                             p.sp.key0, p.sp.key1, t_stop, w.ck + t_arm, cap, C);
+                __syncwarp();
+                if (obs_arm >= 0) do_insert = true, il = sign * w.ck[c0 * cap + obs_arm];
+                if (do_insert) tpe_insert(w, ix, iy, il, lane);
             }
             __syncwarp();
             warp_halving_bracket<float>(p.plan, b, w.ck, cap, keys, ids_a, ids_b, desc, lane, rep, ho, st, w.latest);
@@ -541,7 +563,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int nwarps = 4;
+    int nwarps = 8;
     while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
     const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
     if (smem > (size_t)max_smem) {
@@ -550,7 +572,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     }
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16 / nwarps * 4) per_sm = 16 / nwarps * 4;
+    if (per_sm * nwarps > 48) per_sm = 48 / nwarps > 0 ? 48 / nwarps : 1;
     long long grid = (long long)sms * per_sm;
     const long long need = (n_reps + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
