@@ -97,6 +97,9 @@ def _load():
         'at2_nn_lookup_f64': (C.c_int, [C.POINTER(DomainDesc), vp, i32, vp, i64, vp, vp, vp, i32, vp, vp, vp, i64, vp]),
         'at2_hb_knownfn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(DomainDesc), vp, i32, vp, i32, i32, i64, i64, u64,
                                          vp, C.POINTER(HbOutputs), vp, vp, vp]),
+        'at2_nn_lookup_excluding_f64': (C.c_int, [C.POINTER(DomainDesc), vp, i32, vp, i64, vp, vp, vp, vp, i64, vp]),
+        'at2_order_profile_f32': (C.c_int, [vp, i32, i32, vp, vp, vp]),
+        'at2_ks_statistic_f32': (C.c_int, [vp, i64, vp, i64, vp, vp]),
         'at2_kde_workspace_floats': (i64, [i64, i32]),
         'at2_kde_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, vp, vp, i64, vp]),
     }

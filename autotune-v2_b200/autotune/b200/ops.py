@@ -255,3 +255,56 @@ def sim_trajectories(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: 
                                                    fn.data_ptr(), family.data_ptr(), stream_id.data_ptr(),
                                                    seed & 0xFFFFFFFFFFFFFFFF, raw.data_ptr(), _stream_ptr(f1.device)))
     return raw
+
+
+@torch.library.custom_op('at2::nn_lookup_excluding', mutates_args=(), device_types='cuda')
+def nn_lookup_excluding(domain_bytes: torch.Tensor, db: torch.Tensor, queries: torch.Tensor,
+                        exclude: torch.Tensor) -> List[torch.Tensor]:
+    """Nearest recorded arm with a per-query held-out index range exclude[i] = (lo, hi) (at2_nn_lookup_excluding_f64)."""
+    for name, t in (('db', db), ('queries', queries)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float64 or t.dim() != 2 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 2-D float64 tensor')
+    _require_cuda(exclude, 'exclude')
+    dom = _struct(nat.DomainDesc, domain_bytes)
+    A, D = db.shape
+    nq = queries.shape[0]
+    if exclude.dtype != torch.int32 or tuple(exclude.shape) != (nq, 2) or not exclude.is_contiguous():
+        raise RuntimeError('exclude must be contiguous int32 [nq, 2]')
+    with torch.cuda.device(db.device):
+        idx = torch.empty(nq, device=db.device, dtype=torch.int32)
+        dist = torch.empty(nq, device=db.device, dtype=torch.float64)
+        ws = torch.empty(nq * 12 + 16, device=db.device, dtype=torch.uint8)
+        nat.check(nat.lib.at2_nn_lookup_excluding_f64(C.byref(dom), db.data_ptr(), A, queries.data_ptr(), nq,
+                                                      exclude.data_ptr(), idx.data_ptr(), dist.data_ptr(), ws.data_ptr(),
+                                                      ws.numel(), _stream_ptr(db.device)))
+    return [idx, dist]
+
+
+@torch.library.custom_op('at2::order_profile', mutates_args=(), device_types='cuda')
+def order_profile(curves: torch.Tensor) -> List[torch.Tensor]:
+    """[dynamic order profile [T-1], ends order profile [1]] of loss curves [n, T] (at2_order_profile_f32)."""
+    _require_cuda(curves, 'curves')
+    if curves.dtype != torch.float32 or curves.dim() != 2 or not curves.is_contiguous():
+        raise RuntimeError('curves must be a contiguous 2-D float32 tensor')
+    n, T = curves.shape
+    with torch.cuda.device(curves.device):
+        dyn = torch.empty(T - 1, device=curves.device, dtype=torch.float32)
+        ends = torch.empty(1, device=curves.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_order_profile_f32(curves.data_ptr(), n, T, dyn.data_ptr(), ends.data_ptr(),
+                                                _stream_ptr(curves.device)))
+    return [dyn, ends]
+
+
+@torch.library.custom_op('at2::ks_statistic', mutates_args=(), device_types='cuda')
+def ks_statistic(a_sorted: torch.Tensor, b_sorted: torch.Tensor) -> torch.Tensor:
+    """Two-sample KS statistic D of two sorted float32 samples (at2_ks_statistic_f32)."""
+    for name, t in (('a_sorted', a_sorted), ('b_sorted', b_sorted)):
+        _require_cuda(t, name)
+        if t.dtype != torch.float32 or t.dim() != 1 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 1-D float32 tensor')
+    with torch.cuda.device(a_sorted.device):
+        d = torch.zeros(1, device=a_sorted.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_ks_statistic_f32(a_sorted.data_ptr(), a_sorted.numel(), b_sorted.data_ptr(),
+                                               b_sorted.numel(), d.data_ptr(), _stream_ptr(a_sorted.device)))
+    return d

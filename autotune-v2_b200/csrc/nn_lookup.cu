@@ -71,7 +71,8 @@ constexpr int NN_TILE_BYTES = 32 * 1024;
 __global__ void __launch_bounds__(NN_BLOCK) nn_lookup_kernel(const __grid_constant__ DomainDev dom, const double* __restrict__ db,
                                                             int A, const double* __restrict__ queries, long long nq,
                                                             int n_chunks, int chunk_len, int tile_a,
-                                                            double* __restrict__ part_dist, int* __restrict__ part_idx) {
+                                                            double* __restrict__ part_dist, int* __restrict__ part_idx,
+                                                            const int* __restrict__ exclude) {
     extern __shared__ __align__(16) double s_db[];   // [tile_a][D] normalised
     const int D = dom.D;
     const long long qi = (long long)blockIdx.x * NN_BLOCK + threadIdx.x;
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(NN_BLOCK) nn_lookup_kernel(const __grid_consta
 #pragma unroll
     for (int h = 0; h < AT2_MAX_PARAMS; ++h) q[h] = (h < D && active) ? normalise(queries[qi * D + h], h, dom) : 0.0;
     const int a_lo = blockIdx.y * chunk_len, a_hi = min(A, a_lo + chunk_len);
+    const int ex_lo = (exclude != nullptr && active) ? exclude[2 * qi] : 0;
+    const int ex_hi = (exclude != nullptr && active) ? exclude[2 * qi + 1] : 0;
     double best = CUDART_INF;
     int best_i = -1;
     for (int base = a_lo; base < a_hi; base += tile_a) {
@@ -89,7 +92,8 @@ __global__ void __launch_bounds__(NN_BLOCK) nn_lookup_kernel(const __grid_consta
         __syncthreads();
         for (int a = 0; a < cnt; ++a) {
             const double e = sq_error(q, s_db + a * D, dom);
-            if (e < best) best = e, best_i = base + a;       // strict <: first minimum wins
+            const int ga = base + a;
+            if (e < best && !(ga >= ex_lo && ga < ex_hi)) best = e, best_i = ga;   // strict <: first minimum wins
         }
     }
     if (active) {
@@ -265,10 +269,39 @@ extern "C" int at2_nn_lookup_f64(const at2_domain* domain, const double* d_db, i
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)tile_a * D * sizeof(double);
     nn_lookup_kernel<<<dim3((unsigned)qblocks, n_chunks), NN_BLOCK, smem, st>>>(dom, d_db, A, d_queries, nq, n_chunks,
-                                                                                 chunk_len, tile_a, part_dist, part_idx);
+                                                                                 chunk_len, tile_a, part_dist, part_idx,
+                                                                                 nullptr);
     AT2_CUDA_CHECK(cudaGetLastError());
     nn_finish_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(part_dist, part_idx, nq, n_chunks, d_idx, d_dist,
                                                                    d_curves, L, d_time, d_loss);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(2);
+    return AT2_OK;
+}
+
+extern "C" int at2_nn_lookup_excluding_f64(const at2_domain* domain, const double* d_db, int32_t A, const double* d_queries,
+                                           int64_t nq, const int32_t* d_exclude, int32_t* d_idx, double* d_dist,
+                                           void* d_workspace, int64_t workspace_bytes, void* stream) {
+    at2_reset_launch_count();
+    DomainDev dom;
+    const int rc = make_domain(domain, &dom);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(d_db && d_queries && d_idx && d_workspace && d_exclude, "at2_nn_lookup_excluding_f64: NULL pointer");
+    AT2_REQUIRE(A > 0 && nq > 0, "at2_nn_lookup_excluding_f64: need A > 0 recorded arms and nq > 0 queries");
+    const int D = dom.D;
+    const long long qblocks = (nq + NN_BLOCK - 1) / NN_BLOCK;
+    int tile_a = NN_TILE_BYTES / (D * (int)sizeof(double));
+    if (tile_a > A) tile_a = A;
+    const int64_t need = nq * (int64_t)(sizeof(double) + sizeof(int));
+    AT2_REQUIRE(workspace_bytes >= need, "at2_nn_lookup_excluding_f64: workspace too small");
+    double* part_dist = (double*)d_workspace;
+    int* part_idx = (int*)(part_dist + nq);
+    cudaStream_t st = (cudaStream_t)stream;
+    nn_lookup_kernel<<<dim3((unsigned)qblocks, 1), NN_BLOCK, (size_t)tile_a * D * sizeof(double), st>>>(
+        dom, d_db, A, d_queries, nq, 1, A, tile_a, part_dist, part_idx, d_exclude);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    nn_finish_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(part_dist, part_idx, nq, 1, d_idx, d_dist, nullptr, 0,
+                                                                   nullptr, nullptr);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(2);
     return AT2_OK;

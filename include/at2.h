@@ -221,6 +221,12 @@ int at2_nn_lookup_f64(const at2_domain* domain, const double* d_db, int32_t A, c
                       int32_t* d_idx, double* d_dist, const double* d_curves, int32_t L, const int32_t* d_time,
                       double* d_loss, void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* Same, but query i ignores the recorded arms d_exclude[2i] <= a < d_exclude[2i+1]: the held-out fold of
+ * experiments/known_functions_evaluation/cross_validate_approximation.py:57-66 without rebuilding the database. */
+int at2_nn_lookup_excluding_f64(const at2_domain* domain, const double* d_db, int32_t A, const double* d_queries,
+                                int64_t nq, const int32_t* d_exclude, int32_t* d_idx, double* d_dist, void* d_workspace,
+                                int64_t workspace_bytes, void* stream);
+
 /* Hyperband repetitions on the closest-known-function problem, fused: replaces the loop of
  * experiments/run_closest_loss_fn_approximation.py:183-194 for method sim(hb).  Per repetition: draw the arms
  * (core/arm.py:44-55) or take them from d_predrawn_arms[n_reps][n_arms][D], find each one's nearest recorded arm,
@@ -250,6 +256,19 @@ int at2_kde_f32(const float* d_x, int64_t n, double start, double end, int32_t G
 int at2_sim_trajectories_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_arms,
                              const float* d_f1, const float* d_fn, const int32_t* d_family, const uint64_t* d_stream_id,
                              uint64_t seed, float* d_raw, void* stream);
+
+/* ---- post-processing statistics ("next" rows) ------------------------------------------------------------------------ */
+
+/* Order profiles of a family of loss curves d_curves[n_curves][T] (experiments/simulation_evaluation/profiles.py):
+ * d_dynamic[t-1], t = 1..T-1: mean over curves i of the fraction of other curves whose strict order relative to i is the
+ * same at epochs t-1 and t (get_dynamic_order_profile, :29-53); d_ends[0]: the same between epochs 0 and T-1
+ * (get_ends_order_profile, :56-81).  Either output may be NULL. */
+int at2_order_profile_f32(const float* d_curves, int32_t n_curves, int32_t T, float* d_dynamic, float* d_ends, void* stream);
+
+/* Two-sample Kolmogorov-Smirnov statistic of two SORTED samples (scipy.stats.ks_2samp's two-sided D, as used at
+ * experiments/simulation_evaluation/plot_run_simulations_results.py:69-73). */
+int at2_ks_statistic_f32(const float* d_a_sorted, int64_t n1, const float* d_b_sorted, int64_t n2, float* d_statistic,
+                         void* stream);
 
 /* Number of kernel launches the last at2_* call on this thread enqueued (for bench.py's gpu_launches). */
 int32_t at2_last_launch_count(void);

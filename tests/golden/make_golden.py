@@ -417,6 +417,44 @@ def make_knownfn():
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def make_postprocessing():
+    """Goldens of the post-processing layer: loss-curve family profiles (simulation_evaluation/profiles.py) and the k-fold
+    cross-validation of the closest-known-function approximation (known_functions_evaluation/cross_validate_approximation.py),
+    both computed by the reference's own functions."""
+    from autotune.benchmarks.mnist_problem import HYPERPARAMS_DOMAIN as MNIST_DOM
+    from autotune.experiments.known_functions_evaluation.cross_validate_approximation import cross_validate
+    from autotune.experiments.simulation_evaluation import profiles as ref_prof
+
+    sys.path.insert(0, ROOT)
+    from oracle import known_fn as okf
+    out = {}
+    rng = np.random.default_rng(42)
+    base = np.linspace(100, -100, 27)[None, :]
+    curves = (base + rng.normal(0, 25, (40, 27))).astype(np.float32).astype(np.float64)
+    curves[3] = curves[5]                                   # exact ties must count as neither less nor greater
+    out['prof_curves'] = curves
+    out['prof_avg'] = ref_prof.get_avg_profile(curves)
+    out['prof_med'] = ref_prof.get_med_profile(curves)
+    out['prof_std'] = ref_prof.get_std_profile(curves)
+    out['prof_dynamic'] = np.asarray(ref_prof.get_dynamic_order_profile(curves))
+    out['prof_ends'] = np.float64(ref_prof.get_ends_order_profile(curves))
+
+    class RealProblem(HyperparameterOptimisationProblem):
+        def get_evaluator(self, arm=None):
+            raise NotImplementedError
+    with redirect_stdout(io.StringIO()):
+        real = RealProblem(MNIST_DOM, ())
+        db_dicts, db_curves = okf.synthetic_db(okf.MNIST_DOMAIN, 103, 60, seed=1)   # 103 arms: a ragged last fold
+        names = okf.attribute_order(okf.MNIST_DOMAIN)
+        known_fs = {Arm(**{n: d[n] for n in names}): list(c) for d, c in zip(db_dicts, db_curves)}
+        res, min_len = cross_validate(10, known_fs, real)
+    out['cv_res'] = res
+    out['cv_min_len'] = np.int32(min_len)
+    path = os.path.join(HERE, 'postprocessing.npz')
+    np.savez_compressed(path, **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB', res.shape)
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1:
         for fn in sys.argv[1:]:
@@ -424,6 +462,7 @@ if __name__ == '__main__':
         sys.exit(0)
     make_seeded_ofes()
     make_knownfn()
+    make_postprocessing()
     make_bracket_tables()
     make_hyperband_cases()
     make_epdf_vectors()
