@@ -82,6 +82,8 @@ def _load():
         'at2_hb_tables_build': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), i32, vp]),
         'at2_hb_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
                                      C.POINTER(HbOutputs), vp]),
+        'at2_hb_sim_early_stop_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
+                                                C.POINTER(HbOutputs), vp]),
         'at2_hb_sim_predrawn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, vp,
                                               C.POINTER(HbOutputs), vp]),
         'at2_hb_sim_predrawn_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, vp,

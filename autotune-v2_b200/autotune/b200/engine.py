@@ -108,13 +108,18 @@ def _cuda_device(device):
     return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
 
-def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False):
+def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False, early_stop=False):
     """`n_reps` independent Hyperband repetitions on the simulation problem of `spec`, one fused kernel launch.
 
     Returns a dict of device tensors: ofe[n], ofe_arm[n], best_xy[n,2] and, with details=True, round_best[n,rounds],
     round_best_arm, survivors[n, n_surv], ckpt_loss[n, arms, ckpts].  Repetition i is keyed by (seed, rep_offset+i).
     """
     device = _cuda_device(device)
+    if early_stop:
+        # arms are simulated only as far as the round that reads them needs; same streams, bit-identical outputs
+        outs = torch.ops.at2.hb_sim_early_stop(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes,
+                                               int(n_reps), int(rep_offset), int(seed), bool(details))
+        return dict(zip([k for k in ops.HB_OUTPUT_NAMES if k != 'ckpt_loss'], outs))
     outs = torch.ops.at2.hb_sim_f32(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes, int(n_reps),
                                     int(rep_offset), int(seed), bool(details))
     return dict(zip(ops.HB_OUTPUT_NAMES, outs))

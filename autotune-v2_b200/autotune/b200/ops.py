@@ -31,7 +31,7 @@ def struct_tensor(obj) -> torch.Tensor:
     return torch.frombuffer(bytearray(bytes(obj)), dtype=torch.uint8).clone()
 
 
-def _outputs(plan, n_reps, device, dtype, details):
+def _outputs(plan, n_reps, device, dtype, details, ckpt_loss=True):
     o = {'ofe': torch.empty(n_reps, device=device, dtype=dtype),
          'ofe_arm': torch.empty(n_reps, device=device, dtype=torch.int32),
          'best_xy': torch.empty(n_reps, 2, device=device, dtype=dtype)}
@@ -39,7 +39,8 @@ def _outputs(plan, n_reps, device, dtype, details):
         o['round_best'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=dtype)
         o['round_best_arm'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=torch.int32)
         o['survivors'] = torch.empty(n_reps, plan.n_surv, device=device, dtype=torch.int32)
-        o['ckpt_loss'] = torch.empty(n_reps, plan.n_arms, plan.n_ckpts, device=device, dtype=dtype)
+        if ckpt_loss:
+            o['ckpt_loss'] = torch.empty(n_reps, plan.n_arms, plan.n_ckpts, device=device, dtype=dtype)
     ptr = lambda k: o[k].data_ptr() if k in o else None  # noqa: E731
     outs = nat.HbOutputs(ptr('ofe'), ptr('ofe_arm'), ptr('best_xy'), ptr('round_best'), ptr('round_best_arm'),
                          ptr('survivors'), ptr('ckpt_loss'))
@@ -60,6 +61,20 @@ def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
         nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
                                          seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
+    return tensors
+
+
+@torch.library.custom_op('at2::hb_sim_early_stop', mutates_args=(), device_types='cuda')
+def hb_sim_early_stop(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
+                      seed: int, details: bool) -> List[torch.Tensor]:
+    """at2::hb_sim_f32 with early stopping (at2_hb_sim_early_stop_f32): identical outputs (minus ckpt_loss) at a fraction
+    of the simulated epochs."""
+    _require_cuda(tables, 'tables')
+    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
+    with torch.cuda.device(tables.device):
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=False)
+        nat.check(nat.lib.at2_hb_sim_early_stop_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
+                                                    seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
     return tensors
 
 

@@ -1,0 +1,261 @@
+// (a)+(b) with early stopping: the same Hyperband repetitions as hb_sim.cu, but an arm is only simulated as far as the
+// round that reads it needs - arms eliminated at r = 1 never leave their first point, the survivor of a bracket is the
+// only arm simulated to R.  The reference simulates every arm to R on its first evaluate()
+// (benchmarks/opt_function_simulation_problem.py:67-69) although it only ever reads the checkpoints
+// ("results are unaffected by lazy simulation"); with counter-based streams per arm the values read are
+// bit-identical to the full simulation's, so OFEs, survivor sets and round-bests are the same - at ~1/12 of the epochs.
+//
+// Mapping: a warp owns a tile of G repetitions and walks the plan round by round.  In a round, the (repetition, alive
+// arm) pairs of the whole tile are spread flat over the lanes (G is chosen so that every round fills whole warps),
+// each lane re-simulates its arm from its stream's start up to the position the round reads (raw arms) or the end of the
+// Savitzky-Golay window of that read-out (smooth arms), and the round's losses land in shared memory; then the warp runs
+// that round of successive halving for each repetition.  Nothing is carried between rounds except the survivor ids.
+#include <cfloat>
+#include <climits>
+#include <cstdlib>
+
+#include "at2_common.cuh"
+#include "halving.cuh"
+#include "sim_core.cuh"
+
+namespace {
+
+struct LazyParams {
+    at2_plan plan;
+    Fam<float> fam[AT2_MAX_FAMILIES];
+    ArmSpace sp;
+    int descending;
+    const float* tables;
+    long long n_reps, rep_offset, n_tiles;
+    int G, npad, widest, keep_max, warp_bytes;
+    float* ofe;
+    int* ofe_arm;
+    float* best_xy;
+    float* round_best;
+    int* round_best_arm;
+    int* survivors;
+};
+
+template <bool HAS_SMOOTH, int CK>
+__global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
+    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    const int tab_elems = (L.total() + 3) & ~3;
+    float* s_tab = reinterpret_cast<float*>(smem_raw);
+    int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);
+    int* s_sglast = s_ckpos + AT2_MAX_CKPTS + 4;
+    unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_sglast + AT2_MAX_CKPTS + 4);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
+    __syncthreads();
+    const float* s_rec = s_tab + L.off_rec();
+    const float* s_sg = s_tab + L.off_sg();
+    if (tid < AT2_MAX_CKPTS + 4) {
+        int last = tid < C ? p.plan.ckpt_time[tid] - 1 : 0;
+        if (HAS_SMOOTH && tid < C)
+            for (int t = 0; t < R; ++t)
+                if (s_sg[t * L.sg_stride + tid] != 0.0f) last = max(last, t);
+        s_sglast[tid] = last;
+    }
+    __syncthreads();
+    const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
+                       L.sg_stride};
+    // warp-private: losses of the current round [G][widest], survivor ids [G][2][keep_max], per-repetition state, sort scratch
+    unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
+    float* cur = reinterpret_cast<float*>(mine);
+    float* best = cur + (size_t)G * p.widest;                       // [G] running OFE
+    int* best_arm = reinterpret_cast<int*>(best + G);               // [G]
+    int* surv_w = best_arm + G;                                     // [G] survivors written so far
+    Key32* keys = reinterpret_cast<Key32*>(surv_w + G);             // [npad]
+    unsigned short* ids = reinterpret_cast<unsigned short*>(keys + p.npad);   // [G][2][keep_max]
+    const bool desc = p.descending != 0;
+    const int km = p.keep_max;
+
+    for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (long long)gridDim.x * nwarps) {
+        const long long rep0 = tile * G;
+        const int g_eff = (int)min((long long)G, p.n_reps - rep0);
+        for (int g = lane; g < G; g += 32) best_arm[g] = -1, surv_w[g] = 0, best[g] = 0.0f;
+        __syncwarp();
+        for (int b = 0; b < p.plan.n_brackets; ++b) {
+            const int first = p.plan.bracket_first_arm[b];
+            int n_cur = p.plan.bracket_n[b];
+            int flip = 0;
+            for (int rd = p.plan.bracket_first_round[b]; rd < p.plan.bracket_first_round[b + 1]; ++rd) {
+                const int c = p.plan.round_ckpt[rd];
+                const bool first_round = rd == p.plan.bracket_first_round[b];
+                const int keep = min(p.plan.round_keep[rd], n_cur);
+                // ---- simulate the alive arms of the whole tile up to what this round reads ----
+                const int n_items = g_eff * n_cur;
+#pragma unroll 1
+                for (int base = 0; base < n_items; base += 32) {
+                    const int q = base + lane;
+                    const bool active = q < n_items;
+                    const int g = active ? q / n_cur : 0, j = active ? q - g * n_cur : 0;
+                    const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                    const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
+                    const ArmDraw d = draw_arm(p.sp, gid, arm);
+                    const Fam<float> fam = p.fam[d.fam];
+                    const float f = base_function(p.sp.func, d.x, d.y);
+                    const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
+                    const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+                    const int stop_t = (smooth ? s_sglast[c] : s_ckpos[c]) + 1;
+                    philox_trajectory<float, HAS_SMOOTH, CK, true>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
+                                                                   p.sp.key0, p.sp.key1, stop_t, cur + g * p.widest + j, 0, C, c);
+                }
+                __syncwarp();
+                // ---- this round of successive halving, repetition by repetition ----
+                for (int g = 0; g < g_eff; ++g) {
+                    const long long rep_g = rep0 + g;
+                    const float* loss = cur + g * p.widest;
+                    const unsigned short* in = ids + (g * 2 + flip) * km;
+                    unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
+                    float rb_loss;
+                    int rb_arm;
+                    if (n_cur <= 32) {
+                        Key32 mine_k = Key32::pad();
+                        float my_loss = 0.0f;
+                        int my_id = 0;
+                        if (lane < n_cur) {
+                            my_id = first_round ? first + lane : (int)in[lane];
+                            my_loss = loss[lane];
+                            mine_k = Key32::make(my_loss, lane, desc);
+                        }
+                        mine_k = warp_bitonic_shfl(mine_k, lane, n_cur);
+                        const int src = mine_k.pos() & 31;
+                        const int sid = __shfl_sync(0xffffffffu, my_id, src);
+                        const float sl = __shfl_sync(0xffffffffu, my_loss, src);
+                        rb_loss = __shfl_sync(0xffffffffu, sl, 0);
+                        rb_arm = __shfl_sync(0xffffffffu, sid, 0);
+                        if (lane < keep) out[lane] = (unsigned short)sid;
+                    } else {
+                        int npad = 64;
+                        while (npad < n_cur) npad <<= 1;
+                        for (int j = lane; j < npad; j += 32) keys[j] = j < n_cur ? Key32::make(loss[j], j, desc) : Key32::pad();
+                        __syncwarp();
+                        warp_bitonic_smem(keys, npad, lane);
+                        for (int j = lane; j < keep; j += 32) {
+                            const int pos = keys[j].pos();
+                            out[j] = (unsigned short)(first_round ? first + pos : (int)in[pos]);
+                        }
+                        const int pos0 = keys[0].pos();
+                        rb_arm = first_round ? first + pos0 : (int)in[pos0];
+                        rb_loss = loss[pos0];
+                    }
+                    __syncwarp();
+                    const int sw = surv_w[g];
+                    if (p.survivors != nullptr)
+                        for (int j = lane; j < keep; j += 32) p.survivors[rep_g * p.plan.n_surv + sw + j] = (int)out[j];
+                    if (lane == 0) {
+                        surv_w[g] = sw + keep;
+                        if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = rb_loss;
+                        if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = rb_arm;
+                        const int ba = best_arm[g];
+                        const float bl = best[g];
+                        if (ba < 0 || (desc ? rb_loss > bl : rb_loss < bl)) best[g] = rb_loss, best_arm[g] = rb_arm;
+                    }
+                    __syncwarp();
+                }
+                flip ^= 1;
+                n_cur = keep;
+            }
+        }
+        for (int g = lane; g < g_eff; g += 32) {
+            const long long rep_g = rep0 + g;
+            if (p.ofe != nullptr) p.ofe[rep_g] = best[g];
+            if (p.ofe_arm != nullptr) p.ofe_arm[rep_g] = best_arm[g];
+            if (p.best_xy != nullptr) {
+                const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm[g];
+                const ArmDraw d = draw_arm(p.sp, gid, best_arm[g]);
+                p.best_xy[2 * rep_g] = d.x, p.best_xy[2 * rep_g + 1] = d.y;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <bool HS, int CK>
+int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = hb_lazy_kernel<HS, CK>;
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    kern<<<grid, block, smem, st>>>(p);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    return AT2_OK;
+}
+
+}  // namespace
+
+extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                                         int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream) {
+    at2_reset_launch_count();
+    AT2_REQUIRE(plan && cfg && d_tables && out, "at2_hb_sim_early_stop_f32: NULL plan/config/tables/outputs");
+    AT2_REQUIRE(n_reps > 0 && rep_offset >= 0, "at2_hb_sim_early_stop_f32: n_reps must be positive and rep_offset >= 0");
+    AT2_REQUIRE(plan->n_arms > 0 && plan->n_arms < 65536 && plan->n_rounds > 0 && plan->n_ckpts > 0 &&
+                    plan->n_ckpts <= AT2_MAX_CKPTS, "at2_hb_sim_early_stop_f32: plan is empty or malformed");
+    AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_hb_sim_early_stop_f32: n_families %d outside [1,%d]",
+                cfg->n_families, AT2_MAX_FAMILIES);
+    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_hb_sim_early_stop_f32: unknown func id %d", cfg->func);
+    AT2_REQUIRE(out->d_ckpt_loss == nullptr, "at2_hb_sim_early_stop_f32: checkpoint losses of unread arms do not exist in this mode");
+    const int has_smooth = at2_cfg_has_smooth(cfg);
+    AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
+                "If mode is 'interp', window_length must be less than or equal to the size of x.");
+    LazyParams p = {};
+    p.plan = *plan;
+    for (int f = 0; f < cfg->n_families; ++f) {
+        p.fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
+        p.fam[f].up = (float)cfg->fam[f].up_spik;
+        p.fam[f].s0 = (float)cfg->fam[f].start_shift;
+        p.fam[f].s1 = (float)cfg->fam[f].end_shift;
+        p.fam[f].smooth = cfg->fam[f].is_smooth;
+        p.fam[f].pw_off = f * (plan->R + 1);
+    }
+    p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
+    p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
+    p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);
+    p.sp.noise = (float)cfg->init_noise;
+    p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    p.tables = (const float*)d_tables;
+    p.n_reps = n_reps, p.rep_offset = rep_offset;
+    p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
+    p.round_best = (float*)out->d_round_best, p.round_best_arm = out->d_round_best_arm, p.survivors = out->d_survivors;
+    p.npad = halving_npad(plan);
+    int widest = 0, keep_max = 1;
+    for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
+    for (int r = 0; r < plan->n_rounds; ++r) keep_max = plan->round_keep[r] > keep_max ? plan->round_keep[r] : keep_max;
+    p.widest = widest, p.keep_max = keep_max;
+    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
+    int G = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 16;
+    if ((long long)G > n_reps) G = (int)n_reps;
+    p.G = G;
+    size_t wb = (size_t)G * widest * 4 + (size_t)G * 12 + (size_t)p.npad * 8 + (size_t)G * 2 * keep_max * 2;
+    p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
+    p.n_tiles = (n_reps + G - 1) / G;
+    const int C = plan->n_ckpts;
+    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    int dev = 0, max_smem = 0, sms = 0;
+    AT2_CUDA_CHECK(cudaGetDevice(&dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int nwarps = 8;
+    while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
+    const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
+    if (smem > (size_t)max_smem) {
+        at2_set_error("at2_hb_sim_early_stop_f32 needs %zu B of shared memory per CTA; device limit %d B", smem, max_smem);
+        return AT2_ELIMIT;
+    }
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm * nwarps > 32) per_sm = 32 / nwarps > 0 ? 32 / nwarps : 1;
+    long long grid = (long long)sms * per_sm;
+    const long long need = (p.n_tiles + nwarps - 1) / nwarps;
+    if (grid > need) grid = need;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!has_smooth) return launch_lazy<false, 1>(p, (int)grid, nwarps * 32, smem, st);
+    if (C <= 4) return launch_lazy<true, 4>(p, (int)grid, nwarps * 32, smem, st);
+    if (C <= 8) return launch_lazy<true, 8>(p, (int)grid, nwarps * 32, smem, st);
+    return launch_lazy<true, 16>(p, (int)grid, nwarps * 32, smem, st);
+}

@@ -155,10 +155,14 @@ struct SimTables {
 // padding) lane sits on the sentinel record whose NaN slope fails every acceptance test - so the attempt is branch-free
 // and needs no bounds check.  The rare checkpoint capture is tested once per Philox block.  The next block is issued
 // before the current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
-template <typename T, bool HAS_SMOOTH, int CK>
+//
+// PARTIAL = true (early-stopping evaluation): every lane has its own stop_t and stops advancing there, and only checkpoint
+// `only_c` is produced, into ck[0].  The stream and the arithmetic are the same as in the full run, so the value equals
+// the one the full run reads at that checkpoint, bit for bit.
+template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
                                                   float mlc, float upc, int pw_off, unsigned long long gid, uint32_t key0,
-                                                  uint32_t key1, int stop_t, T* ck, int stride, int C) {
+                                                  uint32_t key1, int stop_t, T* ck, int stride, int C, int only_c = 0) {
     const int R = tb.R;
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
     uint32_t sg_base = tb.sg_addr;
@@ -168,7 +172,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
     int nc = 0;                                                                // next checkpoint to capture
-    int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[0];              // padding lanes never capture
+    int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[PARTIAL ? only_c : 0];   // padding lanes never capture
     float ff = f1;
     float acc[CK];
 #pragma unroll
@@ -187,7 +191,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     if (active && next_pos == 0) {
         ck[0] = (T)ff;
         nc = 1;
-        next_pos = tb.ckpos[1];
+        next_pos = PARTIAL ? INT_MAX : tb.ckpos[1];
     }
     uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
@@ -198,7 +202,8 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         const float v3 = v * v * v;
         // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
         const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-        const bool ok = v > 0.0f && fast_lg2(u) < rhs;
+        bool ok = v > 0.0f && fast_lg2(u) < rhs;
+        if constexpr (PARTIAL) ok = ok && addr < end_addr;
         const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y);
         ff = ok ? fnew : ff;
         if constexpr (HAS_SMOOTH) {
@@ -228,9 +233,9 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         // checkpoint capture (raw arms): position cap was produced by the first attempt if the epoch had already moved
         // past it in between, by the second otherwise
         while (addr > cap_addr) {
-            ck[nc * stride] = (T)(addr_mid > cap_addr ? f_mid : ff);
+            ck[PARTIAL ? 0 : nc * stride] = (T)(addr_mid > cap_addr ? f_mid : ff);
             ++nc;
-            const int np = tb.ckpos[nc];
+            const int np = PARTIAL ? INT_MAX : tb.ckpos[nc];
             cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
         }
     };
@@ -249,8 +254,13 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     if constexpr (HAS_SMOOTH) {
         if (active && smooth) {
 #pragma unroll
-            for (int c = 0; c < CK; ++c)
-                if (c < C) ck[c * stride] = (T)acc[c];
+            for (int c = 0; c < CK; ++c) {
+                if (PARTIAL) {
+                    if (c == only_c) ck[0] = (T)acc[c];
+                } else if (c < C) {
+                    ck[c * stride] = (T)acc[c];
+                }
+            }
         }
     }
 }

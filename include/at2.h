@@ -134,6 +134,13 @@ typedef struct at2_hb_outputs {
 int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                    int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
 
+/* Same repetitions with early stopping: an arm is only simulated as far as the round that reads it needs (the reference
+ * simulates every arm to R on its first evaluate() but only ever reads the checkpoints - SURVEY D5).  Streams and
+ * arithmetic are those of at2_hb_sim_f32, so every output is bit-identical to it; out->d_ckpt_loss must be NULL (the
+ * losses of unread checkpoints are never computed). */
+int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                              int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
+
 /* Pre-drawn inputs (parity paths): nothing is sampled; the kernel only runs the recurrence, the checkpoint read-out
  * and successive halving.  Per arm: first and target values f_1, f_n (opt_function_simulation_problem.py:61-64),
  * the family index, and the R-1 Gamma values of its (effective) trajectory.

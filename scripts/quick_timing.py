@@ -29,3 +29,14 @@ for name, spec, n in [('branin-flat R81', HyperbandSimSpec('branin', FLAT, 81, 3
     ae = spec.arm_epochs_per_repetition * n
     print(f'{name}: {n} reps in {ms:.3f} ms -> {n / ms * 1e3:.3e} runs/s, {ae / ms * 1e3:.3e} arm-epochs/s, '
           f'{ae * 32 / ms * 1e3 / 1e12:.2f} alg-TFLOP/s; ofe mean {out["ofe"].mean().item():.4f}', flush=True)
+    if '--lazy' in sys.argv:
+        for _ in range(10):
+            run_hyperband_repetitions(spec, n, seed=0, early_stop=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            out = run_hyperband_repetitions(spec, n, seed=i, early_stop=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        print(f'   early-stop: {ms:.3f} ms -> {n / ms * 1e3:.3e} runs/s; ofe mean {out["ofe"].mean().item():.4f}', flush=True)

@@ -206,3 +206,21 @@ def test_device_errors_are_loud():
         HyperbandSimSpec('branin', FAM6, 6, 3, 10)          # the reference fails the same way inside scipy
     with pytest.raises(ValueError):
         HyperbandSimSpec('branin', FLAT, 81, 3, 0, min_or_max='median')
+
+
+@pytest.mark.parametrize('func,families,R,eta,noise,mom', [('rastrigin', FAM6, 81, 3, 10, 'min'), ('branin', FLAT, 81, 3, 0, 'min'),
+                                                          ('egg', FAM6[:3], 243, 3, 10, 'min'), ('wave', FAM6, 27, 3, 10, 'max'),
+                                                          ('camel', FAM6, 16, 2, 1, 'min'), ('rastrigin', FAM6, 100, 3, 10, 'min')])
+def test_early_stopping_is_bit_identical_to_full_simulation(func, families, R, eta, noise, mom):
+    """Early stopping only skips epochs nobody reads: with per-arm counter-based streams every output (OFE, winning arm,
+    round-bests, survivor sets) equals the full simulation's bit for bit, for any repetition range."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    spec = HyperbandSimSpec(func, families, R, eta, noise, 'uniform', mom)
+    n = 1500 if R < 243 else 300
+    full = run_hyperband_repetitions(spec, n, seed=13, rep_offset=7, details=True)
+    lazy = run_hyperband_repetitions(spec, n, seed=13, rep_offset=7, details=True, early_stop=True)
+    for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors'):
+        assert torch.equal(full[k], lazy[k]), k
+    assert 'ckpt_loss' not in lazy
+    part = run_hyperband_repetitions(spec, 37, seed=13, rep_offset=7 + 100, early_stop=True)
+    assert torch.equal(part['ofe'], full['ofe'][100:137])
