@@ -292,6 +292,21 @@ def main():
             extras['hb_egg_3families_R243_2e4reps']['runs_per_s'] * s_e.arm_epochs_per_repetition
         extras['hybrid_tpe_transfer_all_rastrigin_R81_2e4reps'] = timed(
             lambda sd: run_hybrid_repetitions(s_r, 20000, 'all', seed=sd, device=dev), 20000, steps=4)
+        extras['hb_flat_branin_R81_1e5reps_early_stop'] = timed(
+            lambda sd: run_hyperband_repetitions(spec, 100000, seed=sd, device=dev, early_stop=True), 100000)
+        extras['hb_flat_branin_R81_1e5reps_early_stop']['note'] = (
+            'same outputs bit for bit (tested); arms are simulated only as far as the round that reads them needs - '
+            'NOT the headline: the headline simulates every arm to R as the reference does')
+        extras['hb_rastrigin_6families_R81_1e5reps_early_stop'] = timed(
+            lambda sd: run_hyperband_repetitions(s_r, 100000, seed=sd, device=dev, early_stop=True), 100000)
+        try:
+            from autotune.b200.engine import KnownFnSpec, run_knownfn_hyperband
+            from autotune.benchmarks.mnist_like import synthetic_mnist_database
+            kspec = KnownFnSpec(*synthetic_mnist_database(425, 300, seed=0), device=dev)
+            extras['hb_closest_known_fn_mnist_shape_A425_D4_R81_1e4reps'] = timed(
+                lambda sd: run_knownfn_hyperband(kspec, 81, 3, 10000, seed=sd), 10000, steps=4)
+        except Exception as e:  # noqa: BLE001
+            extras['hb_closest_known_fn_mnist_shape_A425_D4_R81_1e4reps'] = {'error': repr(e)}
         big = torch.randn(1000000, device=dev)
         extras['kde_epanechnikov_1e6_samples_1000_grid'] = timed(lambda sd: density(big, -4.0, 4.0, 0.3, 1000), 1000000)
 
