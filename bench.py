@@ -126,6 +126,15 @@ class ClockSampler(threading.Thread):
                 'samples': len(inside)}
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the simulation kernel from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')) as f:
+            return json.load(f)['hb_sim_kernel<float, 0, 0, 1>']['dram_bytes_per_launch_avg']
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -328,7 +337,9 @@ def main():
             'gpu_launches': launches,
             'roofline': {'kernel': 'hb_sim_kernel<float,PHILOX> (fused simulation + successive halving)',
                          'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
-                         'frac': achieved_tflops / fma_peak_tflops, 'traffic': None,
+                         'frac': achieved_tflops / fma_peak_tflops, 'traffic': measured_traffic(),
+                         'traffic_note': 'DRAM bytes per launch from the committed ncu capture (profiles/r01_dram_traffic.json); '
+                                         'the kernel has no HBM inputs, its 1.6 MB of outputs stay in L2 during the launch',
                          'peak_source': 'best of 3 FFMA micro-benchmark variants measured in this run '
                                         '(at2_fma_peak_probe); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s',
                          'fma_probe_variants_tflops': fma_variants,
