@@ -31,7 +31,7 @@ void at2_reset_launch_count();
     } while (0)
 
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
-// rec[f][t] f in [0,F), t in [0,R]: 8 reals {d, c, d*log2(e), d*scale, P, P11, 0, 0}
+// rec[f][t] f in [0,F), t in [0,R]: 8 reals {d, c, d*log2(e), d*scale, P, P11, 1-P, 0}
 //          Marsaglia-Tsang constants of the Gamma draw of step t and the two time-aggressiveness powers
 //          (t/(R-1))**nec, (t/(R-1))**(1.1*nec) of family f - one 32-byte (float) record per (family, step), so a lane
 //          fetches everything step t needs from one address.  Row 0 is unused; row R is a sentinel whose c is NaN, so

@@ -240,11 +240,12 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
             row[3] = (T)(d * scale);
             row[4] = (T)pow(frac, cfg->fam[f].nec_agg);          // :105
             row[5] = (T)pow(frac, 1.1 * cfg->fam[f].nec_agg);    // :112
+            row[6] = (T)(1.0 - pow(frac, cfg->fam[f].nec_agg));  // 1 - P, for the fused form of :103-107
         }
     }
     for (int f = 0; f < F; ++f) {   // sentinel row R: NaN slope -> the acceptance test can never pass
         T* row = rec + (size_t)AT2_REC * (f * rows + R);
-        row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)1.4426950408889634, row[3] = (T)1, row[4] = (T)1, row[5] = (T)1;
+        row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)1.4426950408889634, row[3] = (T)1, row[4] = (T)1, row[5] = (T)1, row[6] = (T)0;
     }
     if (L.has_smooth) {
         int32_t rows[AT2_MAX_CKPTS];

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
                                           (double)P, (double)P11);
                     else
                         f = (T)step_fast((float)f, (float)g, (float)fn, (float)fam.ml, (float)fam.up, (float)P,
-                                         (float)P11);
+                                         (float)P11, (float)s_rec[AT2_REC * (fam.pw_off + tt) + 6]);
                     if (HAS_SMOOTH && smooth) {
 #pragma unroll
                         for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[tt * L.sg_stride + c], f, acc[c]);

@@ -60,11 +60,13 @@ __device__ __forceinline__ float fast_cos(float x) {
     return r;
 }
 
-__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11) {
-    // production arithmetic of simulation_evaluator.py:99-115; at the last step P = P11 = 1 so both branches land on
-    // f_n to within one rounding (the reference's float64 path has the same property on its down branch)
-    const float ml = fmaf((g - 2.0f) * mlc, fn - f, f);
-    const float dn = fmaf(fn - ml, P, ml);
+__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11, float Q) {
+    // production arithmetic of simulation_evaluator.py:99-115.  Down branch (:103-107) in fused form:
+    //   ml = f + a (fn - f), a = (g - 2) ml_agg / 100;  f' = ml + (fn - ml) P = f + (fn - f) (a (1 - P) + P),  Q = 1 - P.
+    // At the last step P = P11 = 1, so both branches land on f_n to within one rounding (the reference's float64 path has
+    // the same property on its down branch).
+    const float a = fmaf(g, mlc, -2.0f * mlc);
+    const float dn = fmaf(fn - f, fmaf(a, Q, P), f);
     const float up = fmaf(upc, fast_rcp(1.0f + g), f);
     const float un = fmaf(fn - up, P11, up);
     return g > 2.0f ? dn : (g < 2.0f ? un : f);
@@ -197,14 +199,15 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
     auto attempt = [&](float x, float u) {
         const float4 gm = lds128(addr);                               // d, c, d*log2e, d*scale
-        const float2 pw = lds64(addr + 16u);                          // P, P11
+        const float4 pw = lds128(addr + 16u);                         // P, P11, 1 - P, -
         const float v = fmaf(gm.y, x, 1.0f);
         const float v3 = v * v * v;
         // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
         const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-        bool ok = v > 0.0f && fast_lg2(u) < rhs;
+        // v <= 0 needs no test of its own: lg2 of a non-positive v^3 is NaN / -inf and the comparison fails
+        bool ok = fast_lg2(u) < rhs;
         if constexpr (PARTIAL) ok = ok && addr < end_addr;
-        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y);
+        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y, pw.z);
         ff = ok ? fnew : ff;
         if constexpr (HAS_SMOOTH) {
             const float fs = (ok && smooth) ? ff : 0.0f;

@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
                 const float v = fmaf(g[1], x, 1.0f);
                 const float v3 = v * v * v;
                 const float rhs = fmaf(g[0], fast_lg2(v3), fmaf(-g[2], v3, fmaf(0.72134752044448170f, x * x, g[2])));
-                if (v > 0.0f && fast_lg2(u) < rhs) {
-                    ff = step_fast(ff, g[3] * v3, fn, mlc, upc, g[4], g[5]);
+                if (fast_lg2(u) < rhs) {
+                    ff = step_fast(ff, g[3] * v3, fn, mlc, upc, g[4], g[5], g[6]);
                     out[t] = ff;
                     ++t;
                 }
