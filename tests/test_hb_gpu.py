@@ -224,3 +224,21 @@ def test_early_stopping_is_bit_identical_to_full_simulation(func, families, R, e
     assert 'ckpt_loss' not in lazy
     part = run_hyperband_repetitions(spec, 37, seed=13, rep_offset=7 + 100, early_stop=True)
     assert torch.equal(part['ofe'], full['ofe'][100:137])
+
+
+@pytest.mark.parametrize('func,families,R,eta', [('branin', FAM6[:2], 6, 3), ('camel', FAM6, 16, 2), ('rastrigin', FAM6, 729, 3),
+                                                 ('wave', FAM6, 1121, 3), ('egg', FAM6, 100, 3), ('branin', FAM6[:2], 2, 2),
+                                                 ('rastrigin', FAM6, 64, 4)])
+def test_unusual_plans_run_and_agree_with_independent_halving(func, families, R, eta):
+    """Bracket tables far from the R=81 default: tiny (R=2, 6), eta=2/4, non-powers (R=100), wide first rounds (729 arms
+    at R=1121) and the R=729 quirk where the first round reads the last trajectory point (python's fs[-1])."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    spec = HyperbandSimSpec(func, families, R, eta, 10, 'round-robin', 'min')
+    n = 64 if R > 300 else 400
+    out = run_hyperband_repetitions(spec, n, seed=3, details=True)
+    surv, rb, ofe = _torch_halving(spec, out['ckpt_loss'])
+    assert torch.equal(surv, out['survivors']) and torch.equal(rb, out['round_best']) and torch.equal(ofe, out['ofe'])
+    lazy = run_hyperband_repetitions(spec, n, seed=3, details=True, early_stop=True)
+    assert torch.equal(lazy['ofe'], out['ofe']) and torch.equal(lazy['survivors'], out['survivors'])
+    if R == 729:
+        assert spec.rounds()[0]['time'] == 729     # int(0.9999999999999999) == 0 -> python index -1 -> the last point
