@@ -36,22 +36,23 @@ struct LazyParams {
     int* survivors;
 };
 
-template <bool HAS_SMOOTH, int CK>
+template <bool HAS_SMOOTH, int CK, bool GTAB>
 __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
-    const int tab_elems = (L.total() + 3) & ~3;
+    const int tab_elems = GTAB ? 0 : (L.total() + 3) & ~3;   // GTAB: tables stay in global memory (sim_core.cuh tab128)
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);
     int* s_sglast = s_ckpos + AT2_MAX_CKPTS + 4;
     unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_sglast + AT2_MAX_CKPTS + 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    if constexpr (!GTAB)
+        for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
     if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
-    const float* s_rec = s_tab + L.off_rec();
-    const float* s_sg = s_tab + L.off_sg();
+    const float* s_rec = (GTAB ? p.tables : s_tab) + L.off_rec();
+    const float* s_sg = (GTAB ? p.tables : s_tab) + L.off_sg();
     if (tid < AT2_MAX_CKPTS + 4) {
         int last = tid < C ? p.plan.ckpt_time[tid] - 1 : 0;
         if (HAS_SMOOTH && tid < C)
@@ -60,8 +61,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
         s_sglast[tid] = last;
     }
     __syncthreads();
-    const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
-                       L.sg_stride};
+    const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * 4) : (uint32_t)__cvta_generic_to_shared(s_rec),
+                       GTAB ? (uint32_t)(L.off_sg() * 4) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R, L.sg_stride,
+                       reinterpret_cast<const unsigned char*>(p.tables)};
     // warp-private: losses of the current round [G][widest], survivor ids [G][2][keep_max], per-repetition state, sort scratch
     unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
     float* cur = reinterpret_cast<float*>(mine);
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                     const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
                     const bool smooth = HAS_SMOOTH && fam.smooth != 0;
                     const int stop_t = (smooth ? s_sglast[c] : s_ckpos[c]) + 1;
-                    philox_trajectory<float, HAS_SMOOTH, CK, true>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
+                    philox_trajectory<float, HAS_SMOOTH, CK, true, GTAB>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
                                                                    p.sp.key0, p.sp.key1, stop_t, cur + g * p.widest + j, 0, C, c);
                 }
                 __syncwarp();
@@ -175,9 +177,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     }
 }
 
-template <bool HS, int CK>
+template <bool HS, int CK, bool GTAB = false>
 int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = hb_lazy_kernel<HS, CK>;
+    auto kern = hb_lazy_kernel<HS, CK, GTAB>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<grid, block, smem, st>>>(p);
@@ -226,20 +228,28 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
     for (int r = 0; r < plan->n_rounds; ++r) keep_max = plan->round_keep[r] > keep_max ? plan->round_keep[r] : keep_max;
     p.widest = widest, p.keep_max = keep_max;
-    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
-    int G = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 16;
-    if ((long long)G > n_reps) G = (int)n_reps;
-    p.G = G;
-    size_t wb = (size_t)G * widest * 4 + (size_t)G * 12 + (size_t)p.npad * 8 + (size_t)G * 2 * keep_max * 2;
-    p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
-    p.n_tiles = (n_reps + G - 1) / G;
-    const int C = plan->n_ckpts;
-    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
-    const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
+    int G = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 16;
+    if ((long long)G > n_reps) G = (int)n_reps;
+    // a warp's tile state: round losses [G][widest], per-repetition state, sort scratch, survivor ids; wide plans get
+    // fewer repetitions per tile so that four warps still fit
+    auto warp_bytes_of = [&](int g) {
+        return (size_t)g * widest * 4 + (size_t)g * 12 + (size_t)p.npad * 8 + (size_t)g * 2 * keep_max * 2;
+    };
+    while (G > 1 && warp_bytes_of(G) > 40 * 1024) G = (G + 1) / 2;
+    p.G = G;
+    p.warp_bytes = (int)((warp_bytes_of(G) + 15) & ~(size_t)15);
+    p.n_tiles = (n_reps + G - 1) / G;
+    const int C = plan->n_ckpts;
+    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    // plans whose tables do not fit beside two warps' state read them from global memory
+    const bool gtab = fixed + 2 * (size_t)p.warp_bytes > (size_t)max_smem;
+    if (gtab) fixed = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     int nwarps = 8;
     while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
     const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
@@ -254,6 +264,9 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     const long long need = (p.n_tiles + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
     cudaStream_t st = (cudaStream_t)stream;
+    if (gtab)
+        return has_smooth ? launch_lazy<true, 16, true>(p, (int)grid, nwarps * 32, smem, st)
+                          : launch_lazy<false, 1, true>(p, (int)grid, nwarps * 32, smem, st);
     if (!has_smooth) return launch_lazy<false, 1>(p, (int)grid, nwarps * 32, smem, st);
     if (C <= 4) return launch_lazy<true, 4>(p, (int)grid, nwarps * 32, smem, st);
     if (C <= 8) return launch_lazy<true, 8>(p, (int)grid, nwarps * 32, smem, st);

@@ -39,6 +39,7 @@ struct Params {
     int G;            // repetitions per tile
     long long n_tiles;
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
+    int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
     int n_teams;      // teams per CTA
     int npad;         // power of two >= widest bracket
     int stride;       // G * n_arms rounded up to 32
@@ -62,32 +63,35 @@ struct Params {
 #ifndef AT2_HB_MIN_BLOCKS
 #define AT2_HB_MIN_BLOCKS 4
 #endif
-template <typename T, int MODE, bool HAS_SMOOTH, int CK>
+template <typename T, int MODE, bool HAS_SMOOTH, int CK, bool GTAB>
 __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __grid_constant__ Params<T> p) {
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
-    const int tab_elems = (L.total() + 3) & ~3;
+    // GTAB: the tables stay in global memory (plans too large for shared memory), see sim_core.cuh tab128
+    const int tab_elems = GTAB ? 0 : (L.total() + 3) & ~3;
     T* s_tab = reinterpret_cast<T*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4] positions, then INT_MAX
     unsigned char* team_base = reinterpret_cast<unsigned char*>(s_ckpos + AT2_MAX_CKPTS + 4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int team = warp / p.team_warps, wteam = warp - team * p.team_warps;
-    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    if constexpr (!GTAB)
+        for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
     if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
-    const T* s_rec = s_tab + L.off_rec();
-    const T* s_sg = s_tab + L.off_sg();
-    const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
-                       L.sg_stride};
+    const T* s_rec = (GTAB ? p.tables : s_tab) + L.off_rec();
+    const T* s_sg = (GTAB ? p.tables : s_tab) + L.off_sg();
+    const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_rec),
+                       GTAB ? (uint32_t)(L.off_sg() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
+                       L.sg_stride, reinterpret_cast<const unsigned char*>(p.tables)};
 
     unsigned char* my_team = team_base + (size_t)team * p.team_bytes;
     T* s_ck = reinterpret_cast<T*>(my_team);                                          // [C][stride]
-    K* keys = reinterpret_cast<K*>(s_ck + (size_t)C * p.stride) + (size_t)wteam * p.npad;   // [team_warps][npad]
+    K* keys = reinterpret_cast<K*>(s_ck + (size_t)C * p.stride) + (size_t)wteam * p.npad;   // [sort_warps][npad]
     unsigned short* ids_a = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride) +
-                                                              (size_t)p.team_warps * p.npad) + (size_t)wteam * 2 * p.npad;
+                                                              (size_t)p.sort_warps * p.npad) + (size_t)wteam * 2 * p.npad;
     unsigned short* ids_b = ids_a + p.npad;
     const bool desc = p.descending != 0;
 
@@ -112,9 +116,9 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
                 const float f = base_function(p.sp.func, d.x, d.y);
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
-                philox_trajectory<T, HAS_SMOOTH, CK>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
-                                                     (float)fam.up, fam.pw_off, gid, p.sp.key0, p.sp.key1, R, s_ck + ii,
-                                                     p.stride, C);
+                philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
+                                                                  (float)fam.up, fam.pw_off, gid, p.sp.key0, p.sp.key1, R,
+                                                                  s_ck + ii, p.stride, C);
             } else {
                 const long long a_g = rep_g * A + arm;
                 const T f1 = active ? p.f1[a_g] : (T)0;
@@ -197,6 +201,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
 template <typename T>
 struct LaunchCfg {
     int G, team_warps, n_teams, block, grid, npad, stride, team_bytes;
+    int gtab;   // tables read from global memory instead of being staged into shared memory
     size_t smem;
 };
 
@@ -214,7 +219,7 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     int npad = 64;
     while (npad < widest) npad <<= 1;
     At2TableLayout L{R, F, has_smooth, at2_sg_stride(C)};
-    const size_t fixed = (size_t)((L.total() + 3) & ~3) * sizeof(T) + (AT2_MAX_CKPTS + 4) * sizeof(int);
+    size_t fixed = (size_t)((L.total() + 3) & ~3) * sizeof(T) + (AT2_MAX_CKPTS + 4) * sizeof(int);
     const size_t sort_per_warp = (size_t)npad * (sizeof(K) + 2 * sizeof(unsigned short));
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
@@ -233,7 +238,8 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
             const int per_warp = (groups + tw - 1) / tw;
             const double packing = (double)items / ((double)per_warp * tw * 32);
             const int stride = (items + 31) & ~31;
-            const size_t team_bytes = (size_t)C * stride * sizeof(T) + tw * sort_per_warp;
+            // halving is one warp per repetition: only min(tw, g) warps of a team ever sort
+            const size_t team_bytes = (size_t)C * stride * sizeof(T) + (tw < g ? tw : g) * sort_per_warp;
             if (team_bytes > per_warp_budget * tw && !(tw == 8 && g == 1)) continue;
             // halving wants at least one repetition per warp of the team
             const double sh_balance = (double)g / ((double)((g + tw - 1) / tw) * tw);
@@ -246,8 +252,11 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     best_g = env_int("AT2_HB_REPS_PER_TILE", best_g);
     if ((long long)best_g > n_reps) best_g = (int)n_reps;
     const int stride = (best_g * A + 31) & ~31;
-    size_t team_bytes = (size_t)C * stride * sizeof(T) + best_tw * sort_per_warp;
+    size_t team_bytes = (size_t)C * stride * sizeof(T) + (best_tw < best_g ? best_tw : best_g) * sort_per_warp;
     team_bytes = (team_bytes + 15) & ~(size_t)15;
+    // plans whose tables do not fit beside one team's state (R ~ 1000 with six families) read them from global memory
+    out->gtab = fixed + team_bytes > (size_t)max_smem ? 1 : 0;
+    if (out->gtab) fixed = (AT2_MAX_CKPTS + 4) * sizeof(int);
     int warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", 8);
     if (warps_per_cta < best_tw) warps_per_cta = best_tw;
     if (warps_per_cta > 8) warps_per_cta = 8;
@@ -272,9 +281,9 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     return AT2_OK;
 }
 
-template <typename T, int MODE, bool HS, int CK>
+template <typename T, int MODE, bool HS, int CK, bool GTAB = false>
 int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
-    auto kern = hb_sim_kernel<T, MODE, HS, CK>;
+    auto kern = hb_sim_kernel<T, MODE, HS, CK, GTAB>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<lc.grid, lc.block, lc.smem, st>>>(p);
@@ -285,6 +294,7 @@ int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
 
 template <typename T, int MODE>
 int launch_dispatch(const Params<T>& p, const LaunchCfg<T>& lc, int has_smooth, cudaStream_t st) {
+    if (lc.gtab) return has_smooth ? launch_one<T, MODE, true, 16, true>(p, lc, st) : launch_one<T, MODE, false, 1, true>(p, lc, st);
     if (!has_smooth) return launch_one<T, MODE, false, 1>(p, lc, st);
     const int C = p.plan.n_ckpts;
     if (C <= 4) return launch_one<T, MODE, true, 4>(p, lc, st);
@@ -329,6 +339,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     if (rc != AT2_OK) return rc;
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
+    p->sort_warps = lc->team_warps < lc->G ? lc->team_warps : lc->G;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     return AT2_OK;
 }

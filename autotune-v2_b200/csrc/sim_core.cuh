@@ -106,6 +106,16 @@ __device__ __forceinline__ float2 lds64(uint32_t addr) {
     asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
 }
+// Table fetch of the trajectory loop.  GTAB = false: the tables were staged into shared memory and `addr` is a shared-space
+// address.  GTAB = true (plans whose tables do not fit beside the per-warp state: R ~ 1000 with six families): `addr` is a
+// byte offset into the table in global memory, read through the read-only path (L1/L2 resident: <= 300 KB per launch).
+template <bool GTAB>
+__device__ __forceinline__ float4 tab128(const unsigned char* gbase, uint32_t addr) {
+    if constexpr (GTAB)
+        return __ldg(reinterpret_cast<const float4*>(gbase + addr));
+    else
+        return lds128(addr);
+}
 __device__ __forceinline__ void team_barrier(int team, int team_warps) {
     if (team_warps == 1)
         __syncwarp();
@@ -141,10 +151,11 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
 
 // Shared-memory tables of one CTA as the trajectory loop sees them.
 struct SimTables {
-    uint32_t rec_addr;     // shared-space address of rec[0][0]
-    uint32_t sg_addr;      // shared-space address of sg[0][0]
+    uint32_t rec_addr;     // shared-space address of rec[0][0]  (GTAB: byte offset of rec in the global table)
+    uint32_t sg_addr;      // shared-space address of sg[0][0]   (GTAB: byte offset of sg)
     const int* ckpos;      // checkpoint positions (ckpt_time - 1), INT_MAX-terminated, in shared memory
     int R, sg_stride;
+    const unsigned char* gbase = nullptr;   // GTAB only: the table in global memory
 };
 
 // One arm per lane: runs the lane's Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang -> recurrence until every
@@ -161,11 +172,12 @@ struct SimTables {
 // PARTIAL = true (early-stopping evaluation): every lane has its own stop_t and stops advancing there, and only checkpoint
 // `only_c` is produced, into ck[0].  The stream and the arithmetic are the same as in the full run, so the value equals
 // the one the full run reads at that checkpoint, bit for bit.
-template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false>
+template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
                                                   float mlc, float upc, int pw_off, unsigned long long gid, uint32_t key0,
                                                   uint32_t key1, int stop_t, T* ck, int stride, int C, int only_c = 0) {
     const int R = tb.R;
+    const unsigned char* const gbase = tb.gbase;
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
     uint32_t sg_base = tb.sg_addr;
     uint32_t k0 = key0, k1 = key1;
@@ -183,7 +195,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         const float f0 = (active && smooth) ? ff : 0.0f;
 #pragma unroll
         for (int c4 = 0; c4 < CK; c4 += 4) {                                  // sg[0][c] * fs[0]
-            const float4 w = lds128(sg_base + c4 * 4u);
+            const float4 w = tab128<GTAB>(gbase, sg_base + c4 * 4u);
             acc[c4] = w.x * f0;
             if (c4 + 1 < CK) acc[c4 + 1] = w.y * f0;
             if (c4 + 2 < CK) acc[c4 + 2] = w.z * f0;
@@ -198,8 +210,8 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
     auto attempt = [&](float x, float u) {
-        const float4 gm = lds128(addr);                               // d, c, d*log2e, d*scale
-        const float4 pw = lds128(addr + 16u);                         // P, P11, 1 - P, -
+        const float4 gm = tab128<GTAB>(gbase, addr);                               // d, c, d*log2e, d*scale
+        const float4 pw = tab128<GTAB>(gbase, addr + 16u);                         // P, P11, 1 - P, -
         const float v = fmaf(gm.y, x, 1.0f);
         const float v3 = v * v * v;
         // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
@@ -214,7 +226,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
             const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4);
 #pragma unroll
             for (int c4 = 0; c4 < CK; c4 += 4) {
-                const float4 w = lds128(a + c4 * 4u);
+                const float4 w = tab128<GTAB>(gbase, a + c4 * 4u);
                 acc[c4] = fmaf(w.x, fs, acc[c4]);
                 if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
                 if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
