@@ -30,6 +30,21 @@ void at2_reset_launch_count();
         }                               \
     } while (0)
 
+// CTAs of `kern` resident per SM as far as registers and threads go (shared memory is budgeted by the caller): a
+// persistent grid must not exceed what is resident at once, or the surplus CTAs form a half-empty second wave.
+template <typename Kern>
+static int at2_resident_by_regs(Kern kern, int block, int* out) {
+    cudaFuncAttributes fa;
+    AT2_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+    const int warps = (block + 31) / 32;
+    const int regs_per_warp = ((fa.numRegs * 32 + 511) / 512) * 512;
+    int by_regs = regs_per_warp > 0 ? 65536 / (regs_per_warp * warps) : 32;
+    const int by_threads = 2048 / (warps * 32);
+    if (by_regs > by_threads) by_regs = by_threads;
+    *out = by_regs < 1 ? 1 : by_regs;
+    return AT2_OK;
+}
+
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
 // rec[f][t] f in [0,F), t in [0,R]: 8 reals {d, c, d*log2(e), d*scale, P, P11, 1-P, 0}
 //          Marsaglia-Tsang constants of the Gamma draw of step t and the two time-aggressiveness powers

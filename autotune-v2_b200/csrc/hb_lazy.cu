@@ -182,6 +182,12 @@ int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStrea
     auto kern = hb_lazy_kernel<HS, CK, GTAB>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // persistent grid: never more CTAs than are resident at once (registers can bind before shared memory does)
+    int by_regs = 0, dev = 0, sms = 0;
+    if (at2_resident_by_regs(kern, block, &by_regs) != AT2_OK) return AT2_ECUDA;
+    AT2_CUDA_CHECK(cudaGetDevice(&dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if ((long long)by_regs * sms < grid) grid = by_regs * sms;
     kern<<<grid, block, smem, st>>>(p);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);

@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
 template <typename T>
 struct LaunchCfg {
     int G, team_warps, n_teams, block, grid, npad, stride, team_bytes;
+    int sms;
     int gtab;   // tables read from global memory instead of being staged into shared memory
     size_t smem;
 };
@@ -276,6 +277,7 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     long long grid = (long long)sms * per_sm;
     const long long ctas_needed = (n_tiles + n_teams - 1) / n_teams;
     if (grid > ctas_needed) grid = ctas_needed;
+    out->sms = sms;
     out->G = best_g, out->team_warps = best_tw, out->n_teams = n_teams, out->block = n_teams * best_tw * 32;
     out->grid = (int)grid, out->npad = npad, out->stride = stride, out->team_bytes = (int)team_bytes, out->smem = smem;
     return AT2_OK;
@@ -286,7 +288,13 @@ int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
     auto kern = hb_sim_kernel<T, MODE, HS, CK, GTAB>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lc.smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    kern<<<lc.grid, lc.block, lc.smem, st>>>(p);
+    // persistent grid: exactly the CTAs that are resident at once (registers can bind before shared memory does), so
+    // every CTA walks the same number of tiles and there is no half-empty second wave
+    int by_regs = 0;
+    if (at2_resident_by_regs(kern, lc.block, &by_regs) != AT2_OK) return AT2_ECUDA;
+    int grid = lc.grid;
+    if ((long long)by_regs * lc.sms < grid) grid = by_regs * lc.sms;
+    kern<<<grid, lc.block, lc.smem, st>>>(p);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
     return AT2_OK;

@@ -41,7 +41,7 @@ struct TpeParams {
     int descending;
     const float* tables;
     long long n_reps, rep_offset;
-    int npad, cap, warp_bytes;
+    int npad, cap, warp_bytes, scratch_floats;
     float* ofe;
     int* ofe_arm;
     float* best_xy;
@@ -54,10 +54,10 @@ struct TpeParams {
 
 // warp-private working set
 struct TpeWarp {
-    float *ck, *ax, *ay, *af1, *afn, *ox, *oy, *ol;
-    float4* comp;
-    unsigned short *srt0, *srt1, *cmp, *age;
-    unsigned char *afam, *latest, *below;
+    float *ck, *ax, *ay, *ox, *oy, *ol;
+    float4* comp;                    // mixture components {coef, sqrt(log2(e)/2)/sigma, mu, weight}
+    unsigned short *srt0, *srt1, *age;
+    unsigned char *latest, *below;
     int n_obs;
 };
 
@@ -137,33 +137,48 @@ __device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
     return 0.5f * (1.0f + erff((x - mu) / fmaxf(1.41421356237f * sigma, 1e-12f)));
 }
 
-// Adaptive Parzen estimator (tpe.adaptive_parzen_normal + the truncation mass of tpe.GMM1_lpdf) over the observations
-// of dimension d whose `below` flag equals want_below.  Leaves comp[0..m] = {coef, mu, sqrt(log2(e)/2)/sigma, weight}
-// with coef = weight / (sigma * p_accept) (the common 1/sqrt(2 pi) cancels in l/g) and returns m + 1.
-__device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane) {
+// Adaptive Parzen estimator (tpe.adaptive_parzen_normal) over the observations of dimension d whose `below` flag equals
+// want_below.  Leaves comp[0..m] = {coef, sqrt(log2(e)/2)/sigma, mu, weight} in sorted order with the prior inserted
+// and returns m + 1; *sum_w receives the sum of the weights.
+//   FULL = true  (stand-alone scoring entry): weights normalised, coef = weight / (sigma * p_accept) with the truncation
+//                mass p_accept of tpe.GMM1_lpdf (the common 1/sqrt(2 pi) cancels in l/g).
+//   FULL = false (suggestions inside the simulation kernel): weights left un-normalised and coef = weight / sigma.
+//                log(sum_w) and log(p_accept) shift the scores of all candidates of a model alike, so the arg-max over the
+//                candidates (all a suggestion keeps, tpe.broadcast_best) does not depend on them - and the two erf per
+//                component they cost are most of the model build; the sampler scales its uniform by sum_w instead.
+template <bool FULL>
+__device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane,
+                                               float* sum_w_out) {
     const int n = w.n_obs;
     const float* vals = d ? w.oy : w.ox;
     const unsigned short* srt = d ? w.srt1 : w.srt0;
-    int m = 0;
-    for (int base = 0; base < n; base += 32) {                 // members in sorted order
+    const float prior_mu = 0.5f * (hi + lo), prior_sigma = hi - lo;
+    // pass 1: members in sorted order straight into comp[].z (centre) / comp[].w (age rank inside the set); the prior goes
+    // to position pp = np.searchsorted(sorted members, prior_mu) = #members < prior_mu, members >= prior_mu shift by one
+    int m = 0, ge = 0;
+    for (int base = 0; base < n; base += 32) {
         const int j = base + lane;
         const int idx = j < n ? srt[j] : 0;
+        const float v = vals[idx];
         const bool f = j < n && (w.below[idx] != 0) == want_below;
-        const unsigned mask = __ballot_sync(0xffffffffu, f);
-        if (f) w.cmp[m + __popc(mask & lanemask_lt(lane))] = (unsigned short)idx;
-        m += __popc(mask);
+        const bool g = f && !(v < prior_mu);
+        const unsigned mask = __ballot_sync(0xffffffffu, f), gmask = __ballot_sync(0xffffffffu, g);
+        if (f) {
+            float4* c = w.comp + (m + __popc(mask & lanemask_lt(lane)) + (g ? 1 : 0));
+            c->z = v, c->w = (float)w.age[idx];
+        }
+        m += __popc(mask), ge += __popc(gmask);
     }
+    const int pp = m - ge, nc = m + 1;
+    if (lane == 0) w.comp[pp].z = prior_mu;
     __syncwarp();
-    const float prior_mu = 0.5f * (hi + lo), prior_sigma = hi - lo;
-    int pp = 0;                                                  // np.searchsorted(sorted, prior_mu): members < prior_mu
-    for (int j = lane; j < m; j += 32) pp += vals[w.cmp[j]] < prior_mu ? 1 : 0;
-    pp = __reduce_add_sync(0xffffffffu, pp);
-    const int nc = m + 1;
     const float minsigma = prior_sigma / fminf(100.0f, 1.0f + (float)nc), maxsigma = prior_sigma;
-    auto mu_at = [&](int p) { return p < pp ? vals[w.cmp[p]] : (p == pp ? prior_mu : vals[w.cmp[p - 1]]); };
+    const bool forget = cfg.lf > 0 && cfg.lf < m;
     float sum_w = 0.0f, sum_acc = 0.0f;
+    // pass 2: bandwidths from the neighbouring centres, weights.  (Reads of .z of the neighbours race with nobody: this
+    // pass only writes .x/.y/.w of its own component.)
     for (int p = lane; p < nc; p += 32) {
-        const float mu = mu_at(p);
+        const float mu = w.comp[p].z;
         float sigma, wt;
         if (p == pp) {
             sigma = prior_sigma, wt = cfg.prior_weight;
@@ -171,33 +186,42 @@ __device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_belo
             if (m == 1)
                 sigma = 0.5f * prior_sigma;
             else if (p == 0)
-                sigma = mu_at(1) - mu;
+                sigma = w.comp[1].z - mu;
             else if (p == nc - 1)
-                sigma = mu - mu_at(p - 1);
+                sigma = mu - w.comp[p - 1].z;
             else
-                sigma = fmaxf(mu - mu_at(p - 1), mu_at(p + 1) - mu);
+                sigma = fmaxf(mu - w.comp[p - 1].z, w.comp[p + 1].z - mu);
             sigma = fminf(fmaxf(sigma, minsigma), maxsigma);
-            const int idx = w.cmp[p < pp ? p : p - 1];
-            wt = (cfg.lf > 0 && cfg.lf < m) ? lf_weight(w.age[idx], m, cfg.lf) : 1.0f;
+            wt = forget ? lf_weight((int)w.comp[p].w, m, cfg.lf) : 1.0f;
         }
-        w.comp[p] = make_float4(wt, mu, sigma, 0.0f);
         sum_w += wt;
-        sum_acc += wt * (normal_cdf(hi, mu, sigma) - normal_cdf(lo, mu, sigma));
+        if constexpr (FULL) {
+            w.comp[p].x = sigma, w.comp[p].w = wt;
+            sum_acc += wt * (normal_cdf(hi, mu, sigma) - normal_cdf(lo, mu, sigma));
+        } else {
+            const float inv_sigma = fast_rcp(sigma);
+            float4* c = w.comp + p;
+            c->x = wt * inv_sigma, c->y = 0.84932180028801904f * inv_sigma, c->w = wt;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum_w += __shfl_xor_sync(0xffffffffu, sum_w, o);
-        sum_acc += __shfl_xor_sync(0xffffffffu, sum_acc, o);
-    }
-    const float inv_w = 1.0f / sum_w;
-    const float inv_acc = sum_w / sum_acc;                       // 1 / p_accept
-    __syncwarp();
-    for (int p = lane; p < nc; p += 32) {
-        const float4 c = w.comp[p];
-        const float wn = c.x * inv_w;
-        w.comp[p] = make_float4(wn * inv_acc / c.z, c.y, 0.84932180028801904f / c.z, wn);
+        if constexpr (FULL) sum_acc += __shfl_xor_sync(0xffffffffu, sum_acc, o);
     }
     __syncwarp();
+    if constexpr (FULL) {
+        const float inv_w = 1.0f / sum_w;
+        const float inv_acc = sum_w / sum_acc;                   // 1 / p_accept
+        for (int p = lane; p < nc; p += 32) {
+            const float4 c = w.comp[p];
+            const float wn = c.w * inv_w;
+            w.comp[p] = make_float4(wn * inv_acc / c.x, 0.84932180028801904f / c.x, c.z, wn);
+        }
+        __syncwarp();
+        sum_w = 1.0f;
+    }
+    *sum_w_out = sum_w;
     return nc;
 }
 
@@ -206,7 +230,7 @@ __device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) 
     float s = 0.0f;
     for (int p = 0; p < nc; ++p) {
         const float4 c = w.comp[p];
-        const float z = (x - c.y) * c.z;
+        const float z = (x - c.z) * c.y;
         float e;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z));
         s = fmaf(c.x, e, s);
@@ -222,20 +246,22 @@ __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, fl
     float lik[2] = {1.0f, 1.0f};
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {                   // 0: good model (sample from it), 1: bad model
-        const int nc = tpe_build_model(w, d, which == 0, lo, hi, cfg, lane);
+        float sum_w;
+        const int nc = tpe_build_model<false>(w, d, which == 0, lo, hi, cfg, lane, &sum_w);
         if (which == 0 && lane < cfg.n_cand) {
             // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection
             for (int attempt = 0; attempt < 64; ++attempt) {
                 const At2U4 r = at2_philox10(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
                                                    (uint32_t)(gid >> 32), AT2_STREAM_TPE}, key0, key1);
-                const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f;
+                const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f * sum_w;
                 int pick = 0;
                 float cum = w.comp[0].w;
                 while (pick < nc - 1 && u >= cum) cum += w.comp[++pick].w;
                 const float u1 = fmaf((float)(r.y >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-                const float z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r.z >> 8) * 1.1920928955078125e-7f);
+                const float z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) *
+                                fast_cos((float)(int32_t)r.z * 1.4629180792671596e-9f);      // sqrt(-2 ln u1) cos([-pi, pi))
                 const float4 c = w.comp[pick];
-                const float v = fmaf(0.84932180028801904f / c.z, z, c.y);
+                const float v = fmaf(0.84932180028801904f * fast_rcp(c.y), z, c.z);
                 if (v >= lo && v < hi) {
                     cand = v;
                     break;
@@ -271,7 +297,12 @@ __device__ __forceinline__ bool transferable(int mode, int r_arm, double r_brack
 }
 
 template <bool HAS_SMOOTH, int CK>
-__global__ void __launch_bounds__(256) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
+#ifndef AT2_TPE_MAX_WARPS
+#define AT2_TPE_MAX_WARPS 24
+#endif
+// one CTA per SM, up to 24 warps (80 registers per thread): the kernel is a long chain of small dependent warp-wide
+// steps, so resident warps are what hides its latency
+__global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, cap = p.cap;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
@@ -297,31 +328,27 @@ __global__ void __launch_bounds__(256) tpe_sim_kernel(const __grid_constant__ Tp
     const SimTables tb{(uint32_t)__cvta_generic_to_shared(s_rec), (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
                        L.sg_stride};
 
-    // carve the warp's working set
+    // carve the warp's working set (the sort scratch of the halving rounds aliases the mixture components: a bracket's
+    // TPE phase is over before its halving starts)
     unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
     TpeWarp w;
     float* fp = reinterpret_cast<float*>(mine);
     w.ck = fp, fp += (size_t)C * cap;
     w.ax = fp, fp += cap;
     w.ay = fp, fp += cap;
-    w.af1 = fp, fp += cap;
-    w.afn = fp, fp += cap;
     w.ox = fp, fp += cap;
     w.oy = fp, fp += cap;
     w.ol = fp, fp += cap;
-    w.comp = reinterpret_cast<float4*>(fp), fp += 4 * (cap + 4);
+    w.comp = reinterpret_cast<float4*>(fp);
     Key32* keys = reinterpret_cast<Key32*>(fp);
-    unsigned short* up = reinterpret_cast<unsigned short*>(keys + p.npad);
-    unsigned short* ids_a = up;
-    up += p.npad;
-    unsigned short* ids_b = up;
-    up += p.npad;
+    unsigned short* ids_a = reinterpret_cast<unsigned short*>(keys + p.npad);
+    unsigned short* ids_b = ids_a + p.npad;
+    fp += p.scratch_floats;
+    unsigned short* up = reinterpret_cast<unsigned short*>(fp);
     w.srt0 = up, up += cap;
     w.srt1 = up, up += cap;
-    w.cmp = up, up += cap;
     w.age = up, up += cap;
     unsigned char* bp = reinterpret_cast<unsigned char*>(up);
-    w.afam = bp, bp += cap;
     w.latest = bp, bp += cap;
     w.below = bp, bp += cap;
     w.n_obs = 0;
@@ -375,12 +402,11 @@ __global__ void __launch_bounds__(256) tpe_sim_kernel(const __grid_constant__ Tp
                             xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.key0,
                                                      p.sp.key1, lane);
                     }
-                    const Fam<float> fam = p.fam[d.fam];
-                    const float f = base_function(p.sp.func, xy[0], xy[1]);
-                    const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
-                    if (lane == 0)
-                        w.ax[arm] = xy[0], w.ay[arm] = xy[1], w.af1[arm] = f1, w.afn[arm] = fn, w.afam[arm] = (unsigned char)d.fam;
+                    if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
                     if (use_tpe && step + 1 < n_b) {
+                        const Fam<float> fam = p.fam[d.fam];
+                        const float f = base_function(p.sp.func, xy[0], xy[1]);
+                        const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
                         // the loss TPE sees: the arm's read-out at the bracket's first resource level - simulate just far
                         // enough (all lanes redundantly walk the same stream; the full trajectory is redone in (3))
                         t_smooth = HAS_SMOOTH && fam.smooth != 0;
@@ -394,9 +420,14 @@ __global__ void __launch_bounds__(256) tpe_sim_kernel(const __grid_constant__ Tp
                     t_active = k < n_b;
                     t_arm = first + (t_active ? k : 0);
                     __syncwarp();
-                    const Fam<float> fam = p.fam[w.afam[t_arm]];
+                    // family and initial noise come back from the arm's own stream, the base function from the (possibly
+                    // suggested) hyperparameters - cheaper than keeping f_1 / f_n / family of every arm in shared memory
+                    const ArmDraw d = draw_arm(p.sp, gid0 + t_arm, t_arm);
+                    const Fam<float> fam = p.fam[d.fam];
+                    const float f = base_function(p.sp.func, w.ax[t_arm], w.ay[t_arm]);
                     do_traj = true, t_smooth = HAS_SMOOTH && fam.smooth != 0;
-                    t_f1 = w.af1[t_arm], t_fn = w.afn[t_arm], t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off, t_stop = R;
+                    t_fn = f - fam.s1, t_f1 = (f + p.sp.noise * d.z) - fam.s0;
+                    t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off, t_stop = R;
                 }
                 __syncwarp();
                 if (do_traj)
@@ -425,7 +456,7 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
                                  float* __restrict__ model_out, int cap, int n_prob) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const size_t warp_bytes = (size_t)cap * (3 * 4 + 4 * 2 + 1) + 16 * (cap + 4) + 64;
+    const size_t warp_bytes = (size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (cap + 4) + 64;
     unsigned char* mine = smem_raw + (size_t)warp * ((warp_bytes + 15) & ~(size_t)15);
     TpeWarp w = {};
     float* fp = reinterpret_cast<float*>(mine);
@@ -436,7 +467,6 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
     unsigned short* up = reinterpret_cast<unsigned short*>(fp);
     w.srt0 = up, up += cap;
     w.srt1 = up, up += cap;
-    w.cmp = up, up += cap;
     w.age = up, up += cap;
     w.below = reinterpret_cast<unsigned char*>(up);
     for (int prob = blockIdx.x * nwarps + warp; prob < n_prob; prob += gridDim.x * nwarps) {
@@ -444,12 +474,13 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
         for (int j = 0; j < n_obs; ++j)
             tpe_insert(w, obs[(size_t)prob * n_obs + j], 0.0f, loss[(size_t)prob * n_obs + j], lane);
         tpe_split(w, (int)fminf(ceilf(cfg.gamma * sqrtf((float)n_obs)), 25.0f), lane);
-        const int nb = tpe_build_model(w, 0, true, lo, hi, cfg, lane);
+        float unused;
+        const int nb = tpe_build_model<true>(w, 0, true, lo, hi, cfg, lane, &unused);
         if (model_out != nullptr)
             for (int q = lane; q < nb; q += 32) {
                 const float4 c = w.comp[q];
                 float* m = model_out + ((size_t)prob * 2 * (cap + 1) + q) * 3;
-                m[0] = c.w, m[1] = c.y, m[2] = 0.84932180028801904f / c.z;
+                m[0] = c.w, m[1] = c.z, m[2] = 0.84932180028801904f / c.y;
             }
         __syncwarp();
         float lg[8];
@@ -458,12 +489,12 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
             lg[q] = j < n_cand ? tpe_mixture(w, nb, cand[(size_t)prob * n_cand + j]) : 1.0f;
         }
         __syncwarp();
-        const int na = tpe_build_model(w, 0, false, lo, hi, cfg, lane);
+        const int na = tpe_build_model<true>(w, 0, false, lo, hi, cfg, lane, &unused);
         if (model_out != nullptr)
             for (int q = lane; q < na; q += 32) {
                 const float4 c = w.comp[q];
                 float* m = model_out + ((size_t)prob * 2 * (cap + 1) + (cap + 1) + q) * 3;
-                m[0] = c.w, m[1] = c.y, m[2] = 0.84932180028801904f / c.z;
+                m[0] = c.w, m[1] = c.z, m[2] = 0.84932180028801904f / c.y;
             }
         __syncwarp();
         for (int q = 0; q < 8; ++q) {
@@ -491,6 +522,12 @@ int launch_tpe(const TpeParams& p, int grid, int block, size_t smem, cudaStream_
     auto kern = tpe_sim_kernel<HS, CK>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    // persistent grid: never more CTAs than are resident at once (registers can bind before shared memory does)
+    int by_regs = 0, dev = 0, sms = 0;
+    if (at2_resident_by_regs(kern, block, &by_regs) != AT2_OK) return AT2_ECUDA;
+    AT2_CUDA_CHECK(cudaGetDevice(&dev));
+    AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if ((long long)by_regs * sms < grid) grid = by_regs * sms;
     kern<<<grid, block, smem, st>>>(p);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
@@ -555,7 +592,12 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     p.npad = halving_npad(plan);
     p.cap = (plan->n_arms + 31) & ~31;
     const int C = plan->n_ckpts;
-    size_t wb = (size_t)p.cap * ((C + 7) * 4 + 4 * 2 + 3) + 16 * (size_t)(p.cap + 4) + (size_t)p.npad * (8 + 4);
+    // mixture components [cap + 4] float4, aliased by the halving sort scratch (npad keys + 2 npad ids)
+    size_t scratch = 16 * (size_t)(p.cap + 4);
+    if (scratch < (size_t)p.npad * (8 + 4)) scratch = (size_t)p.npad * (8 + 4);
+    scratch = (scratch + 15) & ~(size_t)15;
+    p.scratch_floats = (int)(scratch / 4);
+    size_t wb = (size_t)p.cap * ((C + 5) * 4 + 3 * 2 + 2) + scratch;
     p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
     const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
@@ -563,8 +605,13 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    int nwarps = 8;
-    while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
+    int nwarps = AT2_TPE_MAX_WARPS;
+    {
+        const char* env_w = getenv("AT2_TPE_WARPS_PER_CTA");
+        if (env_w != nullptr && atoi(env_w) > 0 && atoi(env_w) <= AT2_TPE_MAX_WARPS) nwarps = atoi(env_w);
+    }
+    while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) --nwarps;
+    if ((long long)nwarps > n_reps) nwarps = (int)n_reps;
     const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
     if (smem > (size_t)max_smem) {
         at2_set_error("at2_tpe_sim_f32 needs %zu B of shared memory per CTA (%d arms); device limit %d B", smem, plan->n_arms, max_smem);
@@ -572,7 +619,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     }
     int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm * nwarps > 48) per_sm = 48 / nwarps > 0 ? 48 / nwarps : 1;
+    if (per_sm * nwarps > 64) per_sm = 64 / nwarps > 0 ? 64 / nwarps : 1;
     long long grid = (long long)sms * per_sm;
     const long long need = (n_reps + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
@@ -594,7 +641,7 @@ extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_
     AT2_REQUIRE(n_obs >= 1 && n_obs <= 4096 && n_problems >= 1 && n_candidates >= 1 && n_candidates <= 256 && high > low,
                 "at2_tpe_score_f32: bad sizes (1 <= n_obs <= 4096, 1 <= n_candidates <= 256, low < high)");
     const int cap = (n_obs + 31) & ~31;
-    const size_t warp_bytes = (((size_t)cap * (3 * 4 + 4 * 2 + 1) + 16 * (size_t)(cap + 4) + 64) + 15) & ~(size_t)15;
+    const size_t warp_bytes = (((size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (size_t)(cap + 4) + 64) + 15) & ~(size_t)15;
     const int nwarps = 4;
     const size_t smem = warp_bytes * nwarps;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(tpe_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
