@@ -96,6 +96,31 @@ __host__ __device__ __forceinline__ At2U4 at2_philox10(At2U4 c, uint32_t k0, uin
     return c;
 }
 
+// Same function with the key schedule precomputed on the host (rk[2 r], rk[2 r + 1] = keys of round r).  When rk points
+// into a __grid_constant__ kernel parameter the round keys are constant-bank operands of the XORs: no key-bump
+// instructions and no registers for the schedule.
+__device__ __forceinline__ At2U4 at2_philox10_rk(At2U4 c, const uint32_t* __restrict__ rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)AT2_PHILOX_M0 * c.x;
+        const uint64_t p1 = (uint64_t)AT2_PHILOX_M1 * c.z;
+        At2U4 n;
+        n.x = (uint32_t)(p1 >> 32) ^ c.y ^ rk[2 * r];
+        n.y = (uint32_t)p1;
+        n.z = (uint32_t)(p0 >> 32) ^ c.w ^ rk[2 * r + 1];
+        n.w = (uint32_t)p0;
+        c = n;
+    }
+    return c;
+}
+static inline void at2_round_keys(uint64_t seed, uint32_t* rk) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk[2 * r] = k0, rk[2 * r + 1] = k1;
+        k0 += AT2_PHILOX_W0, k1 += AT2_PHILOX_W1;
+    }
+}
+
 // RNG stream tags (4th counter word)
 #define AT2_STREAM_ARM 0u   // arm initialisation: x, y, family, z
 #define AT2_STREAM_TRAJ 1u  // trajectory attempts

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                     const bool smooth = HAS_SMOOTH && fam.smooth != 0;
                     const int stop_t = (smooth ? s_sglast[c] : s_ckpos[c]) + 1;
                     philox_trajectory<float, HAS_SMOOTH, CK, true, GTAB>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
-                                                                   p.sp.key0, p.sp.key1, stop_t, cur + g * p.widest + j, 0, C, c);
+                                                                   p.sp.rk, stop_t, cur + g * p.widest + j, 0, C, c);
                 }
                 __syncwarp();
                 // ---- this round of successive halving, repetition by repetition ----
@@ -225,6 +225,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);
     p.sp.noise = (float)cfg->init_noise;
     p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    at2_round_keys(seed, p.sp.rk);
     p.tables = (const float*)d_tables;
     p.n_reps = n_reps, p.rep_offset = rep_offset;
     p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
                 philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
-                                                                  (float)fam.up, fam.pw_off, gid, p.sp.key0, p.sp.key1, R,
+                                                                  (float)fam.up, fam.pw_off, gid, p.sp.rk, R,
                                                                   s_ck + ii, p.stride, C);
             } else {
                 const long long a_g = rep_g * A + arm;
@@ -364,6 +364,7 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
     AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
     p.rep_offset = rep_offset;
     p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    at2_round_keys(seed, p.sp.rk);
     return launch_dispatch<float, MODE_PHILOX>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
 }
 

@@ -129,6 +129,7 @@ struct ArmSpace {
     int func, F, scheduler;
     float x_min, x_rng, y_min, y_rng, noise;
     uint32_t key0, key1;
+    uint32_t rk[20];   // Philox key schedule of (key0, key1), at2_round_keys
 };
 
 // arm draw of the Philox path: x, y uniform on the domain (core/params.py:36), family
@@ -174,14 +175,14 @@ struct SimTables {
 // the one the full run reads at that checkpoint, bit for bit.
 template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
-                                                  float mlc, float upc, int pw_off, unsigned long long gid, uint32_t key0,
-                                                  uint32_t key1, int stop_t, T* ck, int stride, int C, int only_c = 0) {
+                                                  float mlc, float upc, int pw_off, unsigned long long gid,
+                                                  const uint32_t* __restrict__ rk, int stop_t, T* ck, int stride, int C,
+                                                  int only_c = 0) {
     const int R = tb.R;
     const unsigned char* const gbase = tb.gbase;
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
     uint32_t sg_base = tb.sg_addr;
-    uint32_t k0 = key0, k1 = key1;
-    asm volatile("" : "+r"(rec_base), "+r"(sg_base), "+r"(k0), "+r"(k1));   // keep them in registers
+    asm volatile("" : "+r"(rec_base), "+r"(sg_base));   // keep them in registers
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
     const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
@@ -255,14 +256,14 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         }
     };
     uint32_t ctr = 1;
-    At2U4 ra = at2_philox10(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1), rb;
+    At2U4 ra = at2_philox10_rk(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, rk), rb;
     while (true) {
         if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-        rb = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+        rb = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
         ++ctr;
         consume(ra);
         if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-        ra = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, k0, k1);
+        ra = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
         ++ctr;
         consume(rb);
     }

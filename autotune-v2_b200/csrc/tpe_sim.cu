@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                 __syncwarp();
                 if (do_traj)
                     philox_trajectory<float, HAS_SMOOTH, CK>(tb, t_active, t_smooth, t_f1, t_fn, t_ml, t_up, t_pw, gid0 + t_arm,
-                                                             p.sp.key0, p.sp.key1, t_stop, w.ck + t_arm, cap, C);
+                                                             p.sp.rk, t_stop, w.ck + t_arm, cap, C);
                 __syncwarp();
                 if (obs_arm >= 0) do_insert = true, il = sign * w.ck[c0 * cap + obs_arm];
                 if (do_insert) tpe_insert(w, ix, iy, il, lane);
@@ -584,6 +584,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);
     p.sp.noise = (float)cfg->init_noise;
     p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    at2_round_keys(seed, p.sp.rk);
     p.tables = (const float*)d_tables;
     p.n_reps = n_reps, p.rep_offset = rep_offset;
     p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
