@@ -1,0 +1,25 @@
+#!/bin/bash
+# Profiling recipe of one round, to be run on the GPU box through gpurun (one GPU):
+#   bash scripts/profile_round.sh r01
+# 1. the bench command runs plainly and must exit 0;  2. the launch list of the same command
+# (gpu__time_duration, --clock-control none);  3. one --set full capture of the headline kernels with source;
+# 4. one --set full capture of the TPE kernel.  Outputs land in gpurun_out/; scripts/ncu_summary.py turns them
+# into the tracked summaries under profiles/.
+set -u
+tag=${1:-r01}
+out=gpurun_out
+mkdir -p $out
+cmd="python bench.py --steps 6 --warmup 3 --no-cpu-baseline"
+$cmd > $out/${tag}_plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $out/${tag}_plain_bench.log; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'hb_sim_kernel|kde_partial_kernel|kde_finish_kernel' -s 6 -c 6 -f \
+    -o $out/${tag}_prof_bench $cmd > $out/${tag}_ncu_full.log 2>&1
+# SASS-counted FP32 work of one simulation launch (not part of --set full)
+ncu --clock-control none -k regex:hb_sim_kernel -s 6 -c 1 --csv --log-file $out/${tag}_sass_flops.csv --metrics \
+smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_executed_op_fmul_pred_on.sum,smsp__sass_thread_inst_executed_op_ffma_pred_on.sum,smsp__thread_inst_executed.sum,smsp__inst_executed_pipe_xu.sum \
+    $cmd > $out/${tag}_ncu_sass.log 2>&1
+python scripts/tpe_timing.py 8000 > $out/${tag}_plain_tpe.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:tpe_sim_kernel -s 9 -c 1 -f -o $out/${tag}_prof_tpe \
+    python scripts/tpe_timing.py 8000 > $out/${tag}_ncu_tpe.log 2>&1
+tail -2 $out/${tag}_plain_bench.log | cut -c1-400
+ls -la $out | grep ${tag}_
