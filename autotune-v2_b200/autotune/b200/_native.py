@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(PKG_ROOT, 'lib', 'libat2_b200.so')
 
 MAX_BRACKETS, MAX_ROUNDS, MAX_CKPTS, MAX_FAMILIES = 16, 64, 16, 8
 MAX_PARAMS = 16
-FUNC_IDS = {'egg': 0, 'branin': 1, 'camel': 2, 'wave': 3, 'rastrigin': 4}
+FUNC_IDS = {'egg': 0, 'branin': 1, 'camel': 2, 'wave': 3, 'rastrigin': 4,
+            'egg4': 5}   # egg4: 4-D extension (include/at2.h AT2_FUNC_EGG4), Hyperband entry points only
 SCHED_UNIFORM, SCHED_ROUND_ROBIN = 0, 1
 
 
@@ -75,6 +76,7 @@ def _load():
         'at2_version': (C.c_char_p, []),
         'at2_last_error': (C.c_char_p, []),
         'at2_last_launch_count': (i32, []),
+        'at2_func_dims': (i32, [i32]),
         'at2_bracket_plan': (C.c_int, [i32, i32, C.POINTER(Plan)]),
         'at2_savgol_window': (i32, [i32]),
         'at2_savgol_rows': (C.c_int, [i32, i32, C.POINTER(i32), C.POINTER(C.c_double)]),

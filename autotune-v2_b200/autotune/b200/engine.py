@@ -14,7 +14,9 @@ from . import ops
 
 FUNC_DOMAINS = {  # benchmarks/opt_function_problem.py:15-46
     'egg': (-512, 512, -512, 512), 'branin': (-5, 10, 1, 15), 'camel': (-3, 3, -2, 2),
-    'wave': (-5.12, 5.12, -5.12, 5.12), 'rastrigin': (-5.12, 5.12, -5.12, 5.12)}
+    'wave': (-5.12, 5.12, -5.12, 5.12), 'rastrigin': (-5.12, 5.12, -5.12, 5.12),
+    # extension (include/at2.h AT2_FUNC_EGG4): 4-D Egg-holder, all four coordinates on [-512, 512]; no reference oracle
+    'egg4': (-512, 512, -512, 512)}
 
 
 def _family_tuple(f):
@@ -111,7 +113,7 @@ def _cuda_device(device):
 def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False, early_stop=False):
     """`n_reps` independent Hyperband repetitions on the simulation problem of `spec`, one fused kernel launch.
 
-    Returns a dict of device tensors: ofe[n], ofe_arm[n], best_xy[n,2] and, with details=True, round_best[n,rounds],
+    Returns a dict of device tensors: ofe[n], ofe_arm[n], best_xy[n,2] ([n,4] for the egg4 extension) and, with details=True, round_best[n,rounds],
     round_best_arm, survivors[n, n_surv], ckpt_loss[n, arms, ckpts].  Repetition i is keyed by (seed, rep_offset+i).
     """
     device = _cuda_device(device)

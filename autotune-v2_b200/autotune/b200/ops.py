@@ -31,10 +31,10 @@ def struct_tensor(obj) -> torch.Tensor:
     return torch.frombuffer(bytearray(bytes(obj)), dtype=torch.uint8).clone()
 
 
-def _outputs(plan, n_reps, device, dtype, details, ckpt_loss=True):
+def _outputs(plan, n_reps, device, dtype, details, ckpt_loss=True, dims=2):
     o = {'ofe': torch.empty(n_reps, device=device, dtype=dtype),
          'ofe_arm': torch.empty(n_reps, device=device, dtype=torch.int32),
-         'best_xy': torch.empty(n_reps, 2, device=device, dtype=dtype)}
+         'best_xy': torch.empty(n_reps, dims, device=device, dtype=dtype)}
     if details:
         o['round_best'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=dtype)
         o['round_best_arm'] = torch.empty(n_reps, plan.n_rounds, device=device, dtype=torch.int32)
@@ -58,7 +58,7 @@ def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.
     _require_cuda(tables, 'tables')
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     with torch.cuda.device(tables.device):
-        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, dims=nat.lib.at2_func_dims(cfg.func))
         nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
                                          seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
     return tensors
@@ -72,7 +72,8 @@ def hb_sim_early_stop(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes:
     _require_cuda(tables, 'tables')
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     with torch.cuda.device(tables.device):
-        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=False)
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=False,
+                                 dims=nat.lib.at2_func_dims(cfg.func))
         nat.check(nat.lib.at2_hb_sim_early_stop_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
                                                     seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
     return tensors

@@ -199,13 +199,18 @@ extern "C" int at2_savgol_rows(int32_t R, int32_t n_rows, const int32_t* rows, d
     return AT2_OK;
 }
 
+extern "C" int32_t at2_func_dims(int32_t func) {
+    if (func >= AT2_FUNC_EGG && func <= AT2_FUNC_RASTRIGIN) return 2;
+    return func == AT2_FUNC_EGG4 ? 4 : -1;
+}
+
 // ---- constant tables ----------------------------------------------------------------------------------------------------
 static int check_cfg(const at2_plan* plan, const at2_sim_config* cfg) {
     AT2_REQUIRE(plan && cfg, "NULL plan/config");
     AT2_REQUIRE(plan->R >= 2 && plan->n_arms > 0 && plan->n_rounds > 0, "plan is empty (call at2_bracket_plan)");
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
-    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "unknown func id %d", cfg->func);
+    AT2_REQUIRE(at2_func_dims(cfg->func) > 0, "unknown func id %d", cfg->func);
     return AT2_OK;
 }
 

@@ -27,7 +27,7 @@ struct LazyParams {
     int descending;
     const float* tables;
     long long n_reps, rep_offset, n_tiles;
-    int G, npad, widest, keep_max, warp_bytes;
+    int G, npad, widest, keep_max, warp_bytes, dims;
     float* ofe;
     int* ofe_arm;
     float* best_xy;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
                     const ArmDraw d = draw_arm(p.sp, gid, arm);
                     const Fam<float> fam = p.fam[d.fam];
-                    const float f = base_function(p.sp.func, d.x, d.y);
+                    const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                     const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
                     const bool smooth = HAS_SMOOTH && fam.smooth != 0;
                     const int stop_t = (smooth ? s_sglast[c] : s_ckpos[c]) + 1;
@@ -170,7 +170,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
             if (p.best_xy != nullptr) {
                 const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm[g];
                 const ArmDraw d = draw_arm(p.sp, gid, best_arm[g]);
-                p.best_xy[2 * rep_g] = d.x, p.best_xy[2 * rep_g + 1] = d.y;
+                float* bxy = p.best_xy + (size_t)p.dims * rep_g;
+                bxy[0] = d.x, bxy[1] = d.y;
+                if (p.dims == 4) bxy[2] = d.x2, bxy[3] = d.y2;
             }
         }
         __syncwarp();
@@ -205,7 +207,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
                     plan->n_ckpts <= AT2_MAX_CKPTS, "at2_hb_sim_early_stop_f32: plan is empty or malformed");
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_hb_sim_early_stop_f32: n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
-    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_hb_sim_early_stop_f32: unknown func id %d", cfg->func);
+    AT2_REQUIRE(at2_func_dims(cfg->func) > 0, "at2_hb_sim_early_stop_f32: unknown func id %d", cfg->func);
     AT2_REQUIRE(out->d_ckpt_loss == nullptr, "at2_hb_sim_early_stop_f32: checkpoint losses of unread arms do not exist in this mode");
     const int has_smooth = at2_cfg_has_smooth(cfg);
     AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
@@ -220,6 +222,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
         p.fam[f].smooth = cfg->fam[f].is_smooth;
         p.fam[f].pw_off = f * (plan->R + 1);
     }
+    p.dims = at2_func_dims(cfg->func);
     p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
     p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
     p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);

@@ -34,6 +34,7 @@ struct Params {
     Fam<T> fam[AT2_MAX_FAMILIES];
     ArmSpace sp;
     int descending;
+    int dims;         // hyperparameters per arm (2; 4 for the egg4 extension)
     const T* tables;
     long long n_reps, rep_offset;
     int G;            // repetitions per tile
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
             if constexpr (MODE == MODE_PHILOX) {
                 const ArmDraw d = draw_arm(p.sp, gid, arm);
                 const Fam<T> fam = p.fam[d.fam];
-                const float f = base_function(p.sp.func, d.x, d.y);
+                const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
                 philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
@@ -185,7 +186,9 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
                 if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm;
                     const ArmDraw d = draw_arm(p.sp, gid, best_arm);
-                    p.best_xy[2 * rep_g] = (T)d.x, p.best_xy[2 * rep_g + 1] = (T)d.y;
+                    T* bxy = p.best_xy + (size_t)p.dims * rep_g;
+                    bxy[0] = (T)d.x, bxy[1] = (T)d.y;
+                    if (p.dims == 4) bxy[2] = (T)d.x2, bxy[3] = (T)d.y2;
                 } else {
                     const long long a_g = rep_g * A + best_arm;
                     p.best_xy[2 * rep_g] = p.xy != nullptr ? p.xy[2 * a_g] : (T)0;
@@ -321,7 +324,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     AT2_REQUIRE(plan->n_arms < 65536, "at2_hb_sim: more than 65535 arms per repetition");
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_hb_sim: n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
-    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_hb_sim: unknown func id %d", cfg->func);
+    AT2_REQUIRE(at2_func_dims(cfg->func) > 0, "at2_hb_sim: unknown func id %d", cfg->func);
     const int has_smooth = at2_cfg_has_smooth(cfg);
     AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
                 "If mode is 'interp', window_length must be less than or equal to the size of x.");
@@ -334,6 +337,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
         p->fam[f].smooth = cfg->fam[f].is_smooth;
         p->fam[f].pw_off = f * (plan->R + 1);
     }
+    p->dims = at2_func_dims(cfg->func);
     p->sp.func = cfg->func, p->sp.F = cfg->n_families, p->sp.scheduler = cfg->scheduler, p->descending = cfg->descending;
     p->sp.x_min = (float)cfg->x_min, p->sp.x_rng = (float)(cfg->x_max - cfg->x_min);
     p->sp.y_min = (float)cfg->y_min, p->sp.y_rng = (float)(cfg->y_max - cfg->y_min);

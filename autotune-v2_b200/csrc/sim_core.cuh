@@ -73,8 +73,14 @@ __device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc
 }
 
 // ---- test functions in FP32 (benchmarks/opt_function_problem.py:49-138) ------------------------------------------------
-__device__ __noinline__ float base_function(int func, float x, float y) {
+__device__ __forceinline__ float egg_pair(float a, float b) {
+    return -(b + 47.0f) * sinf(sqrtf(fabsf(b + 0.5f * a + 47.0f))) - a * sinf(sqrtf(fabsf(a - b - 47.0f)));
+}
+// (x2, y2): third and fourth coordinate, used by the 4-D extension only
+__device__ __noinline__ float base_function(int func, float x, float y, float x2 = 0.0f, float y2 = 0.0f) {
     switch (func) {
+        case AT2_FUNC_EGG4:   // extension (include/at2.h): n-dimensional Egg-holder over consecutive coordinate pairs
+            return (egg_pair(x, y) + egg_pair(y, x2)) + egg_pair(x2, y2);
         case AT2_FUNC_EGG:
             return -(y + 47.0f) * sinf(sqrtf(fabsf(y + 0.5f * x + 47.0f))) - x * sinf(sqrtf(fabsf(x - y - 47.0f)));
         case AT2_FUNC_BRANIN: {
@@ -137,6 +143,7 @@ struct ArmSpace {
 struct ArmDraw {
     float x, y, z;
     int fam;
+    float x2, y2;   // AT2_FUNC_EGG4 only
 };
 __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long gid, int arm) {
     const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
@@ -147,6 +154,8 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
     const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
     const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
     d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+    d.x2 = fmaf((float)(r2.y >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
+    d.y2 = fmaf((float)(r2.z >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
     return d;
 }
 

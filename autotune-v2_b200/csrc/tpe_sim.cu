@@ -563,7 +563,8 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
                     plan->n_ckpts <= AT2_MAX_CKPTS, "at2_tpe_sim_f32: plan is empty or malformed");
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_tpe_sim_f32: n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
-    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN, "at2_tpe_sim_f32: unknown func id %d", cfg->func);
+    AT2_REQUIRE(cfg->func >= 0 && cfg->func <= AT2_FUNC_RASTRIGIN,
+                "at2_tpe_sim_f32: func id %d is not one of the reference's 2-D test functions (TPE suggestions are 2-D)", cfg->func);
     const int has_smooth = at2_cfg_has_smooth(cfg);
     AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
                 "If mode is 'interp', window_length must be less than or equal to the size of x.");

@@ -43,6 +43,10 @@ extern "C" {
 #define AT2_FUNC_CAMEL 2
 #define AT2_FUNC_WAVE 3
 #define AT2_FUNC_RASTRIGIN 4
+/* EXTENSION, no reference equivalent (the reference's Egg-holder is 2-D): the n-dimensional Egg-holder
+ * sum_{i<3} [-(x_{i+1}+47) sin sqrt|x_{i+1} + x_i/2 + 47| - x_i sin sqrt|x_i - (x_{i+1}+47)|] over four coordinates,
+ * each uniform on [x_min, x_max] x [y_min, y_max] alternately.  Hyperband entry points only (TPE suggestions are 2-D). */
+#define AT2_FUNC_EGG4 5
 
 #define AT2_SCHED_UNIFORM 0      /* UniformShapeFamilyScheduler,    core/shape_family_scheduler.py:68-77 */
 #define AT2_SCHED_ROUND_ROBIN 1  /* RoundRobinShapeFamilyScheduler, core/shape_family_scheduler.py:50-65 */
@@ -91,6 +95,9 @@ typedef struct at2_sim_config {
     at2_family fam[AT2_MAX_FAMILIES];
 } at2_sim_config;
 
+/* number of hyperparameters of a test function: 2 for the reference's functions, 4 for AT2_FUNC_EGG4; -1 if unknown */
+int32_t at2_func_dims(int32_t func);
+
 const char* at2_version(void);
 const char* at2_last_error(void);
 
@@ -119,7 +126,7 @@ int at2_hb_tables_build(const at2_plan* plan, const at2_sim_config* cfg, int32_t
 typedef struct at2_hb_outputs {
     void* d_ofe;            /* real[n_reps]            min/max over round-bests (core/optimiser.py:67-68) */
     int32_t* d_ofe_arm;     /* int32[n_reps]           arm id (creation order within the repetition) of the OFE */
-    void* d_best_xy;        /* real[n_reps][2]         hyperparameters of that arm */
+    void* d_best_xy;        /* real[n_reps][dims]      hyperparameters of that arm, dims = at2_func_dims(cfg->func) */
     void* d_round_best;     /* real[n_reps][n_rounds]  best-in-round (hyperband_optimiser.py:98-99) */
     int32_t* d_round_best_arm; /* int32[n_reps][n_rounds] */
     int32_t* d_survivors;   /* int32[n_reps][n_surv]   survivors of every round, sorted order, rounds concatenated */

@@ -48,6 +48,13 @@ def rastrigin(x, y):  # opt_function_problem.py:131-137 (python sum() starts fro
     return 10 * 2 + ((0 + tx) + ty)
 
 
+def egg4(x0, x1, x2, x3):
+    """EXTENSION - no reference equivalent (the reference's Egg-holder is 2-D; BASELINE.json config 5 asks
+    for a 4-D one): the n-dimensional Egg-holder, the 2-D form (:60) summed over consecutive coordinate pairs.  This is
+    the definition the device follows (include/at2.h AT2_FUNC_EGG4), not a restatement of reference code."""
+    return (egg(x0, x1) + egg(x1, x2)) + egg(x2, x3)
+
+
 FUNCS = {'egg': egg, 'branin': branin, 'camel': camel, 'wave': wave, 'rastrigin': rastrigin}
 
 

@@ -143,3 +143,8 @@ def test_savgol_rows_all_rows_and_window_error():
     rc = nat.lib.at2_savgol_rows(6, 1, rows.ctypes.data_as(C.POINTER(C.c_int32)),
                                  out.ctypes.data_as(C.POINTER(C.c_double)))
     assert rc == -1 and b'window_length' in nat.lib.at2_last_error()   # same failure the reference hits via scipy
+
+
+def test_func_dims():
+    assert [nat.lib.at2_func_dims(i) for i in range(-1, 7)] == [-1, 2, 2, 2, 2, 2, 4, -1]
+    assert nat.FUNC_IDS['egg4'] == 5

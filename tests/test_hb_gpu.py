@@ -242,3 +242,30 @@ def test_unusual_plans_run_and_agree_with_independent_halving(func, families, R,
     assert torch.equal(lazy['ofe'], out['ofe']) and torch.equal(lazy['survivors'], out['survivors'])
     if R == 729:
         assert spec.rounds()[0]['time'] == 729     # int(0.9999999999999999) == 0 -> python index -1 -> the last point
+
+
+def test_egg4_extension_flat_family_ofe_is_the_function_value():
+    """4-D Egg-holder of BASELINE.json config 5 - an EXTENSION with no reference equivalent, defined in
+    include/at2.h and oracle/opt_functions.egg4.  With the flat family (no noise, no shifts) every loss of an arm equals
+    its function value, so the OFE must be the oracle's float64 egg4 at the reported hyperparameters; the 2-D 'egg' is
+    untouched; early stopping and sharding keep their bit-identity."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    from oracle import opt_functions as of
+    spec = HyperbandSimSpec('egg4', FLAT, 81, 3, 0)
+    out = run_hyperband_repetitions(spec, 4000, seed=17, details=True)
+    xy = out['best_xy'].double().cpu().numpy()
+    assert xy.shape == (4000, 4) and (np.abs(xy) <= 512).all()
+    want = of.egg4(xy[:, 0], xy[:, 1], xy[:, 2], xy[:, 3])
+    np.testing.assert_allclose(out['ofe'].double().cpu().numpy(), want, rtol=2e-4, atol=0.25)   # FP32 sin(sqrt(.)) of |arg| < 1100
+    assert len(np.unique(xy[:, 2])) > 3900 and abs(np.corrcoef(xy[:, 0], xy[:, 2])[0, 1]) < 0.1   # own coordinates
+    # lower than the best of 117 random 2-D egg arms on average: three pair terms instead of one
+    egg2 = run_hyperband_repetitions(HyperbandSimSpec('egg', FLAT, 81, 3, 0), 4000, seed=17)
+    assert egg2['best_xy'].shape == (4000, 2) and out['ofe'].mean() < egg2['ofe'].mean()
+    lazy = run_hyperband_repetitions(spec, 4000, seed=17, details=True, early_stop=True)
+    for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'survivors'):
+        assert torch.equal(out[k], lazy[k]), k
+    part = run_hyperband_repetitions(spec, 100, seed=17, rep_offset=1234)
+    assert torch.equal(part['ofe'], out['ofe'][1234:1334]) and torch.equal(part['best_xy'], out['best_xy'][1234:1334])
+    from autotune.b200.engine import run_hybrid_repetitions
+    with pytest.raises(Exception, match='2-D'):
+        run_hybrid_repetitions(spec, 10, 'none')
