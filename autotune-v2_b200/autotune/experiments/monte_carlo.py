@@ -13,6 +13,7 @@ from autotune.optimisers import _device
 
 def _runner_for(optimiser, problem):
     """(spec, runner(spec, n, seed, rep_offset, device) -> ofe tensor) for an optimiser/problem pair."""
+    import torch
     from autotune.b200 import engine
     from autotune.benchmarks.known_loss_fn_problem import KnownFnProblem
     _device.require_fval_objective(optimiser.optimisation_func)
@@ -22,8 +23,10 @@ def _runner_for(optimiser, problem):
         db = problem.device_db()
 
         def runner(_spec, n, seed, off, dev):
+            # float64: the OFEs are recorded losses, returned exactly as the reference returns them
             return engine.run_knownfn_hyperband(db, optimiser.max_iter, optimiser.eta, n, seed=seed, rep_offset=off,
-                                                min_or_max=optimiser.min_or_max)['ofe'].float()
+                                                min_or_max=optimiser.min_or_max)['ofe']
+        runner.dtype = torch.float64
         return None, runner
     spec = _device.simulation_spec(optimiser, problem)
     if isinstance(optimiser, HyperbandOptimiser):
@@ -47,7 +50,8 @@ def _runner_for(optimiser, problem):
 
 def run_repetitions(optimiser, problem, n_repetitions, seed=0, device=None, group=None):
     """OFEs of `n_repetitions` independent runs of `optimiser` on `problem` (all ranks' results, in repetition order,
-    as a float32 CUDA tensor).  Equivalent to looping `optimiser.run_optimisation(problem)` with fresh objects as the
+    as a CUDA tensor: float32 for the simulation problems, the float64 recorded losses for the closest-known-function
+    problem).  Equivalent to looping `optimiser.run_optimisation(problem)` with fresh objects as the
     reference drivers do - the same kernels, one launch per rank."""
     from autotune.b200.engine import _cuda_device
     from autotune.b200.epdf import gather_slices, shard_range
@@ -58,7 +62,8 @@ def run_repetitions(optimiser, problem, n_repetitions, seed=0, device=None, grou
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_range(n_repetitions, rank, world)
-    local = runner(spec, hi - lo, seed, lo, device) if hi > lo else torch.empty(0, device=device)
+    local = runner(spec, hi - lo, seed, lo, device) if hi > lo else \
+        torch.empty(0, device=device, dtype=getattr(runner, 'dtype', torch.float32))
     return gather_slices(local, n_repetitions, group)
 
 

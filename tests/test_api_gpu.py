@@ -210,4 +210,43 @@ def test_knownfn_problem_through_hyperband_api():
     assert min(again.fvals) <= fval(best.optimisation_goals) <= max(again.fvals)
     from autotune.experiments.monte_carlo import run_repetitions
     ofe = run_repetitions(opt, problem, 2000, seed=5)
-    assert ofe.shape == (2000,) and np.isin(ofe.double().cpu().numpy(), curves.astype(np.float32).astype(np.float64)).all()
+    assert ofe.shape == (2000,) and ofe.dtype == torch.float64 and np.isin(ofe.cpu().numpy(), curves).all()
+
+
+def test_closest_known_function_driver_cli_and_pickle(tmp_path):
+    """experiments/run_closest_loss_fn_approximation.py: flags, synthetic fallback for the absent recorded arms, the
+    reference's result schema (:207-217) - and the OFE distribution against the oracle's python loop on the same DB."""
+    from scipy.stats import ks_2samp
+
+    from autotune.experiments import run_closest_loss_fn_approximation as drv
+    from oracle import known_fn as okf
+    for problem, n_arms in (('mnist', 425), ('cifar', 300)):
+        stats = _quiet(drv.main, ['-p', problem, '-m', 'sim(hb)', '-iter', '81', '-n', '3000', '-o', str(tmp_path), '--seed', '4',
+                                  '--known-functions-dir', str(tmp_path / 'absent')])
+        with open(tmp_path / 'known-fns-hist-sim(hb)-3000.pkl', 'rb') as f:
+            saved = pickle.load(f)
+        assert set(saved) == {'method', 'n_simulations', 'all_norm_optimums', 'avg_optimum', 'sample_std_dev', 'avg_top_25%'}
+        assert saved['n_simulations'] == 3000 and len(saved['all_norm_optimums']) == 3000
+        assert saved['avg_optimum'] == pytest.approx(np.mean(saved['all_norm_optimums']))
+        assert stats['avg_top_25%'] == pytest.approx(np.mean(sorted(saved['all_norm_optimums'])[:750]))
+        # every OFE is a recorded loss of the synthetic database the driver built
+        args = drv._get_args(['-p', problem, '--seed', '4'])
+        known = _quiet(drv.get_known_functions, args, str(tmp_path / 'absent'))
+        assert len(known) == n_arms
+        recorded = np.unique(np.asarray(list(known.values()), np.float64))
+        assert np.isin(np.asarray(saved['all_norm_optimums'], np.float64), recorded).all()      # exact float64 losses
+        # distribution vs the oracle's restatement of the reference loop on the same database
+        odom = okf.MNIST_DOMAIN if problem == 'mnist' else okf.CIFAR_DOMAIN
+        order = okf.attribute_order(odom)
+        arms = [{n: a[n] for n in order} for a in known]
+        curves = np.asarray(list(known.values()), np.float64)
+        np.random.seed(11)
+        want = [okf.run_hyperband(arms, curves, odom, 81, 3)['ofe'] for _ in range(60)]
+        assert ks_2samp(np.asarray(saved['all_norm_optimums']), np.asarray(want)).pvalue > 0.01
+    with pytest.raises(NotImplementedError):
+        _quiet(drv.main, ['-p', 'mnist', '-m', 'sim(hb+tpe+transfer+none)', '-n', '10', '-o', str(tmp_path)])
+    with pytest.raises(ValueError):
+        _quiet(drv.main, ['-p', 'nope', '-n', '10'])
+    # test-function problems: 1000 random arms with constant curves (reference :118-123)
+    stats = _quiet(drv.main, ['-p', 'branin', '-m', 'sim(hb)', '-iter', '6', '-n', '500', '-o', str(tmp_path)])
+    assert stats['n_simulations'] == 500 and stats['avg_optimum'] > 0.39
