@@ -290,4 +290,67 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     }
 }
 
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// The recurrence is affine in its two inputs: f_t = A_t f_1 + (1 - A_t) f_n + C_t, where (A_t, C_t) depend only on the arm's
+// Gamma stream and family (down step: f' = (1-k) f + k f_n; up step: f' = (1-P11)(f + up/(1+g)) + P11 f_n) - and so is the
+// Savitzky-Golay read-out (its rows sum to one).  Since f_1 = f + (noise z - start_shift) and f_n = f - end_shift, the loss
+// an arm shows at a checkpoint is  f(x, y) + offset  with an offset that is known BEFORE the arm's hyperparameters are.
+// This walks the lane's stream (same Philox blocks, same acceptance arithmetic as philox_trajectory, so the same Gamma
+// draws) up to the read-out of checkpoint c and returns that offset.  The TPE kernel computes it for all arms of a bracket
+// in parallel (one arm per lane) before its sequential suggest -> observe loop, instead of re-walking each arm's stream
+// with 32 redundant lanes once its hyperparameters have been suggested.  All 32 lanes must call it.
+//   dz = noise z - start_shift (f_1 - f), s1 = end_shift (f - f_n); stop_t: 1 + last position the read-out needs.
+template <bool HAS_SMOOTH>
+__device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool active, bool smooth, float mlc, float upc,
+                                                      int pw_off, unsigned long long gid, const uint32_t* __restrict__ rk,
+                                                      int stop_t, int c, float dz, float s1) {
+    const uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
+    const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
+    uint32_t addr = active ? rec_base + AT2_REC * 4u : end_addr;         // record of the step to produce next
+    const uint32_t sg_col = tb.sg_addr + (uint32_t)c * 4u;
+    const uint32_t sg_row = (uint32_t)(tb.sg_stride * 4);
+    float A = 1.0f, Cc = 0.0f, accA = 0.0f, accC = 0.0f;
+    if constexpr (HAS_SMOOTH) accA = smooth ? lds32(sg_col) : 0.0f;      // sg[0][c] * (A_0 = 1)
+    const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
+    auto attempt = [&](float x, float u) {
+        const float4 gm = lds128(addr);
+        const float4 pw = lds128(addr + 16u);
+        const float v = fmaf(gm.y, x, 1.0f);
+        const float v3 = v * v * v;
+        const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
+        const bool ok = fast_lg2(u) < rhs && addr < end_addr;
+        const float g = gm.w * v3;
+        const float k = fmaf(fmaf(g, mlc, -2.0f * mlc), pw.z, pw.x);
+        const float q = 1.0f - pw.y;
+        const bool dn = g > 2.0f, up = g < 2.0f;
+        const float An = dn ? fmaf(-k, A, A) : (up ? q * A : A);
+        const float Cn = dn ? fmaf(-k, Cc, Cc) : (up ? q * fmaf(upc, fast_rcp(1.0f + g), Cc) : Cc);
+        A = ok ? An : A, Cc = ok ? Cn : Cc;
+        if constexpr (HAS_SMOOTH) {
+            const float w = (ok && smooth) ? lds32(sg_col + ((addr - rec_base) >> 5) * sg_row) : 0.0f;
+            accA = fmaf(w, A, accA), accC = fmaf(w, Cc, accC);
+        }
+        addr += ok ? (AT2_REC * 4u) : 0u;
+    };
+    uint32_t ctr = 0;
+    while (__any_sync(0xffffffffu, addr < end_addr)) {
+        const At2U4 r = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
+        ++ctr;
+        const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));
+        const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;
+        const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));
+        const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
+        attempt(rad * fast_cos(ang), ua);
+        attempt(rad * fast_sin(ang), ub);
+    }
+    if (HAS_SMOOTH && smooth) A = accA, Cc = accC;
+    return fmaf(A, dz, fmaf(A, s1, -s1)) + Cc;                           // A dz - (1 - A) s1 + C
+}
+
 }  // namespace

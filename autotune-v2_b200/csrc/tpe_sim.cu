@@ -366,76 +366,79 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
             const int rd0 = p.plan.bracket_first_round[b];
             const int c0 = p.plan.round_ckpt[rd0];
             const double r0 = p.plan.bracket_r0[b];   // the un-truncated float the reference compares against
-            // One loop walks (1) the arms of earlier brackets that may be injected as TPE history
-            // (hybrid_hyperband_tpe_with_transfer.py:116-158), (2) the bracket's own arms one after the other (suggest ->
-            // evaluate at the first resource level -> observe), (3) the full-trajectory passes, one arm per lane.  Each big
-            // routine (insert, suggest, trajectory) is instantiated exactly once: with them duplicated the kernel was
-            // instruction-fetch bound (ncu: 49 % of stall samples in no_instructions).
+            // (0) one arm per lane: the start-up hyperparameters of every arm of the bracket and - when the bracket runs
+            //     TPE - the offset of its loss at the bracket's first resource level over f(x, y), which depends only on
+            //     the arm's own streams (sim_core.cuh philox_affine_offset), parked in row 0 of ck until (3) fills it;
+            // (1) arms of earlier brackets that may be injected as TPE history
+            //     (hybrid_hyperband_tpe_with_transfer.py:116-158);
+            // (2) the bracket's own arms one after the other: suggest -> loss = f(x, y) + offset -> observe;
+            // (3) the full trajectories, one arm per lane, exactly as the Hyperband kernel runs them.
+            // Each big routine (insert, suggest, trajectory) is instantiated exactly once: with them duplicated the kernel
+            // was instruction-fetch bound (ncu: 49 % of stall samples in no_instructions).
             w.n_obs = 0;
-            const bool inject = p.tpe.enabled && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE;
             const bool use_tpe = p.tpe.enabled && n_b > p.tpe.n_startup;
+            const bool inject = use_tpe && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE;
             const int n_prev = inject ? first : 0;
-            const int n_full = (n_b + 31) >> 5;
             int n_startup = p.tpe.n_startup;                          // + injected, tpe_optimiser.py:52
 #pragma unroll 1
-            for (int step = -n_prev; step < n_b + n_full; ++step) {
-                bool do_insert = false, do_traj = false, t_active = false, t_smooth = false;
+            for (int base = 0; base < n_b; base += 32) {
+                const bool act = base + lane < n_b;
+                const int arm = first + (act ? base + lane : 0);
+                const ArmDraw d = draw_arm(p.sp, gid0 + arm, arm);
+                float off = 0.0f;
+                if (use_tpe) {
+                    const Fam<float> fam = p.fam[d.fam];
+                    const bool sm = HAS_SMOOTH && fam.smooth != 0;
+                    off = philox_affine_offset<HAS_SMOOTH>(tb, act, sm, fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.rk,
+                                                           (sm ? s_sglast[c0] : s_ckpos[c0]) + 1, c0,
+                                                           p.sp.noise * d.z - fam.s0, fam.s1);
+                }
+                if (act) w.ax[arm] = d.x, w.ay[arm] = d.y, w.ck[arm] = off;
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int step = -n_prev; step < (use_tpe ? n_b : 0); ++step) {
+                bool do_insert = false;
                 float ix = 0.0f, iy = 0.0f, il = 0.0f;
-                float t_f1 = 0.0f, t_fn = 0.0f, t_ml = 0.0f, t_up = 0.0f;
-                int t_pw = 0, t_stop = 1, t_arm = first, obs_arm = -1;
                 if (step < 0) {                                      // (1) candidate for injection
                     const int a = first + step;
                     const int lc = w.latest[a];
                     if (transferable(p.tpe.transfer, p.plan.ckpt_time[lc], r0, R, p.tpe.threshold))
                         do_insert = true, ix = w.ax[a], iy = w.ay[a], il = sign * w.ck[lc * cap + a];
-                } else if (step < n_b) {                             // (2) next arm of the bracket
+                } else {                                             // (2) next arm of the bracket
                     if (step == 0) n_startup += w.n_obs;
                     const int arm = first + step;
-                    const unsigned long long gid = gid0 + arm;
-                    const ArmDraw d = draw_arm(p.sp, gid, arm);      // warp-uniform
-                    float xy[2] = {d.x, d.y};
-                    if (use_tpe && w.n_obs >= n_startup) {
+                    float xy[2] = {w.ax[arm], w.ay[arm]};
+                    if (w.n_obs >= n_startup) {
                         const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
                         tpe_split(w, (int)g, lane);
 #pragma unroll 1
                         for (int dd = 0; dd < 2; ++dd)
-                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.key0,
+                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid0 + arm, p.sp.key0,
                                                      p.sp.key1, lane);
+                        if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
                     }
-                    if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
-                    if (use_tpe && step + 1 < n_b) {
-                        const Fam<float> fam = p.fam[d.fam];
-                        const float f = base_function(p.sp.func, xy[0], xy[1]);
-                        const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
-                        // the loss TPE sees: the arm's read-out at the bracket's first resource level - simulate just far
-                        // enough (all lanes redundantly walk the same stream; the full trajectory is redone in (3))
-                        t_smooth = HAS_SMOOTH && fam.smooth != 0;
-                        do_traj = true, t_active = true, t_arm = arm;
-                        t_f1 = f1, t_fn = fn, t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off;
-                        t_stop = (t_smooth ? s_sglast[c0] : s_ckpos[c0]) + 1;
-                        obs_arm = arm, ix = xy[0], iy = xy[1];
-                    }
-                } else {                                             // (3) full trajectories, one arm per lane
-                    const int k = ((step - n_b) << 5) + lane;
-                    t_active = k < n_b;
-                    t_arm = first + (t_active ? k : 0);
-                    __syncwarp();
-                    // family and initial noise come back from the arm's own stream, the base function from the (possibly
-                    // suggested) hyperparameters - cheaper than keeping f_1 / f_n / family of every arm in shared memory
-                    const ArmDraw d = draw_arm(p.sp, gid0 + t_arm, t_arm);
-                    const Fam<float> fam = p.fam[d.fam];
-                    const float f = base_function(p.sp.func, w.ax[t_arm], w.ay[t_arm]);
-                    do_traj = true, t_smooth = HAS_SMOOTH && fam.smooth != 0;
-                    t_fn = f - fam.s1, t_f1 = (f + p.sp.noise * d.z) - fam.s0;
-                    t_ml = fam.ml, t_up = fam.up, t_pw = fam.pw_off, t_stop = R;
+                    if (step + 1 < n_b)                              // the loss TPE sees for this arm
+                        do_insert = true, ix = xy[0], iy = xy[1],
+                        il = sign * (base_function(p.sp.func, xy[0], xy[1]) + w.ck[arm]);
                 }
                 __syncwarp();
-                if (do_traj)
-                    philox_trajectory<float, HAS_SMOOTH, CK>(tb, t_active, t_smooth, t_f1, t_fn, t_ml, t_up, t_pw, gid0 + t_arm,
-                                                             p.sp.rk, t_stop, w.ck + t_arm, cap, C);
-                __syncwarp();
-                if (obs_arm >= 0) do_insert = true, il = sign * w.ck[c0 * cap + obs_arm];
                 if (do_insert) tpe_insert(w, ix, iy, il, lane);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int base = 0; base < n_b; base += 32) {              // (3) full trajectories
+                const bool act = base + lane < n_b;
+                const int arm = first + (act ? base + lane : 0);
+                // family and initial noise come back from the arm's own stream, the base function from the (possibly
+                // suggested) hyperparameters
+                const ArmDraw d = draw_arm(p.sp, gid0 + arm, arm);
+                const Fam<float> fam = p.fam[d.fam];
+                const float f = base_function(p.sp.func, w.ax[arm], w.ay[arm]);
+                __syncwarp();                                         // row 0 of ck is overwritten below
+                philox_trajectory<float, HAS_SMOOTH, CK>(tb, act, HAS_SMOOTH && fam.smooth != 0, (f + p.sp.noise * d.z) - fam.s0,
+                                                         f - fam.s1, fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.rk, R,
+                                                         w.ck + arm, cap, C);
             }
             __syncwarp();
             warp_halving_bracket<float>(p.plan, b, w.ck, cap, keys, ids_a, ids_b, desc, lane, rep, ho, st, w.latest);
