@@ -240,8 +240,10 @@ __device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) 
 
 // One hyperparameter of one suggestion: candidates from the good model, argmax of log l - log g
 // (tpe.build_posterior, ap_uniform_sampler, GMM1, GMM1_lpdf, broadcast_best).
+// r0: the lane's Philox block of this suggestion; words (2 d, 2 d + 1) serve the first draw of dimension d, re-draws after
+// a rejection take a block of their own.
 __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, unsigned long long gid,
-                                 uint32_t key0, uint32_t key1, int lane) {
+                                 const uint32_t* __restrict__ rk, const At2U4& r0, int lane) {
     float cand = 0.5f * (lo + hi);
     float lik[2] = {1.0f, 1.0f};
 #pragma unroll 1
@@ -249,17 +251,22 @@ __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, fl
         float sum_w;
         const int nc = tpe_build_model<false>(w, d, which == 0, lo, hi, cfg, lane, &sum_w);
         if (which == 0 && lane < cfg.n_cand) {
-            // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection
+            // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection.  One draw takes two
+            // words: 24 + 24 bits for the Box-Muller pair, the two low bytes for the component pick.
+            uint32_t wa = d ? r0.z : r0.x, wb = d ? r0.w : r0.y;
             for (int attempt = 0; attempt < 64; ++attempt) {
-                const At2U4 r = at2_philox10(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
-                                                   (uint32_t)(gid >> 32), AT2_STREAM_TPE}, key0, key1);
-                const float u = (float)(r.x >> 8) * 5.9604644775390625e-8f * sum_w;
+                if (attempt > 0) {
+                    const At2U4 r = at2_philox10_rk(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
+                                                          (uint32_t)(gid >> 32), AT2_STREAM_TPE}, rk);
+                    wa = r.x, wb = r.y;
+                }
+                const float u = (float)(((wa & 0xffu) << 8) | (wb & 0xffu)) * 1.52587890625e-5f * sum_w;
                 int pick = 0;
                 float cum = w.comp[0].w;
                 while (pick < nc - 1 && u >= cum) cum += w.comp[++pick].w;
-                const float u1 = fmaf((float)(r.y >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
+                const float u1 = fmaf((float)(wa >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
                 const float z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) *
-                                fast_cos((float)(int32_t)r.z * 1.4629180792671596e-9f);      // sqrt(-2 ln u1) cos([-pi, pi))
+                                fast_cos((float)(int32_t)(wb & 0xffffff00u) * 1.4629180792671596e-9f);   // sqrt(-2 ln u1) cos([-pi, pi))
                 const float4 c = w.comp[pick];
                 const float v = fmaf(0.84932180028801904f * fast_rcp(c.y), z, c.z);
                 if (v >= lo && v < hi) {
@@ -412,10 +419,12 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                     if (w.n_obs >= n_startup) {
                         const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
                         tpe_split(w, (int)g, lane);
+                        const unsigned long long gid = gid0 + arm;
+                        const At2U4 r0 = at2_philox10_rk(At2U4{(uint32_t)lane, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_TPE},
+                                                         p.sp.rk);
 #pragma unroll 1
                         for (int dd = 0; dd < 2; ++dd)
-                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid0 + arm, p.sp.key0,
-                                                     p.sp.key1, lane);
+                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.rk, r0, lane);
                         if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
                     }
                     if (step + 1 < n_b)                              // the loss TPE sees for this arm
