@@ -101,6 +101,141 @@ __device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane, int n) {
     return mine;
 }
 
+// ---- float losses: register-resident rounds ---------------------------------------------------------------------------
+// n <= 32 keys, one per lane: stable ascending rank of the lane's key by counting.  Equal keys (rare) are ranked by lane =
+// by position, python's stable sorted(): MATCH.ANY finds the lanes holding the same key, the ones below add to the rank.
+__device__ __forceinline__ int warp_rank_by_counting(uint32_t ord, int lane, int n) {
+    int rank = 0;
+#pragma unroll 1
+    for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, ord, j) < ord ? 1 : 0;
+    return rank + __popc(__match_any_sync(0xffffffffu, ord) & ((1u << lane) - 1u));
+}
+
+// ascending bitonic sort of KPL * 32 64-bit keys held KPL per lane (key i lives in lane i / KPL, register i % KPL):
+// compare-exchanges at distance < KPL stay inside a lane, the others are one 64-bit shuffle per register - no shared
+// memory, no barriers, KPL independent chains per stage.
+template <int KPL>
+__device__ __forceinline__ void warp_bitonic_regs(uint64_t (&k)[KPL], int lane) {
+    // sizes 2 .. KPL: inside a lane.  Block direction alternates with bit `size` of the index; for size == KPL that bit
+    // is the lowest lane bit.
+#pragma unroll
+    for (int size = 2; size <= KPL; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) {
+                if ((r & j) == 0) {
+                    const bool up = size < KPL ? (r & size) == 0 : ((lane * KPL) & size) == 0;
+                    const uint64_t a = k[r], b = k[r | j];
+                    const bool sw = (a > b) == up;
+                    k[r] = sw ? b : a, k[r | j] = sw ? a : b;
+                }
+            }
+        }
+    }
+#pragma unroll 1
+    for (int size = 2 * KPL; size <= 32 * KPL; size <<= 1) {
+        const bool up = ((lane * KPL) & size) == 0;            // ascending block (always, for the last size)
+#pragma unroll 1
+        for (int lm = size / (2 * KPL); lm > 0; lm >>= 1) {     // partner lane = lane ^ lm, same register
+            const bool lower = (lane & lm) == 0;
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) {
+                const uint64_t o = __shfl_xor_sync(0xffffffffu, k[r], lm);
+                k[r] = ((k[r] > o) == (up == lower)) ? o : k[r];
+            }
+        }
+#pragma unroll
+        for (int j = KPL >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < KPL; ++r) {
+                if ((r & j) == 0) {
+                    const uint64_t a = k[r], b = k[r | j];
+                    const bool sw = (a > b) == up;
+                    k[r] = sw ? b : a, k[r | j] = sw ? a : b;
+                }
+            }
+        }
+    }
+}
+
+// One successive-halving round of one repetition on float losses (hyperband_optimiser.py:46-57,93-100): ranks the n_cur
+// alive arms - arm id ids[j], or first + j in a bracket's first round - by loss_at(j, id) with python's stable order,
+// writes the ids of the `keep` best, in sorted order, to ids_next and returns the round's best (loss, arm id).
+// keys: npad sort keys of warp-private scratch, used only by rounds wider than 256.  All 32 lanes must call it.
+template <typename LossAt>
+__device__ __forceinline__ void warp_halving_round_f32(int n_cur, int keep, bool first_round, int first,
+                                                       const unsigned short* ids, unsigned short* ids_next, Key32* keys,
+                                                       bool desc, int lane, LossAt loss_at, float& rb_loss, int& rb_arm) {
+    if (n_cur <= 32) {
+        int my_id = 0;
+        float my_loss = 0.0f;
+        uint32_t ord = 0xffffffffu;
+        if (lane < n_cur) {
+            my_id = first_round ? first + lane : (int)ids[lane];
+            my_loss = loss_at(lane, my_id);
+            ord = orderable(my_loss, desc);
+        }
+        const int rank = warp_rank_by_counting(ord, lane, n_cur);
+        if (lane < n_cur && rank < keep) ids_next[rank] = (unsigned short)my_id;
+        const int src = __ffs(__ballot_sync(0xffffffffu, lane < n_cur && rank == 0)) - 1;
+        rb_loss = __shfl_sync(0xffffffffu, my_loss, src);
+        rb_arm = __shfl_sync(0xffffffffu, my_id, src);
+    } else if (n_cur <= 256) {
+        if (n_cur <= 128) {
+            uint64_t k[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = lane * 4 + r;
+                const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+                k[r] = j < n_cur ? Key32::make(loss_at(j, id), j, desc).v : ~0ull;
+            }
+            warp_bitonic_regs<4>(k, lane);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int j = lane * 4 + r, pos = (int)(uint32_t)k[r];
+                if (j < keep) ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+            }
+            const int pos0 = __shfl_sync(0xffffffffu, (int)(uint32_t)k[0], 0);
+            rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+            rb_loss = loss_at(pos0, rb_arm);
+        } else {
+            uint64_t k[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int j = lane * 8 + r;
+                const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+                k[r] = j < n_cur ? Key32::make(loss_at(j, id), j, desc).v : ~0ull;
+            }
+            warp_bitonic_regs<8>(k, lane);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const int j = lane * 8 + r, pos = (int)(uint32_t)k[r];
+                if (j < keep) ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+            }
+            const int pos0 = __shfl_sync(0xffffffffu, (int)(uint32_t)k[0], 0);
+            rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+            rb_loss = loss_at(pos0, rb_arm);
+        }
+    } else {
+        int npad = 512;
+        while (npad < n_cur) npad <<= 1;
+        for (int j = lane; j < npad; j += 32) {
+            const int id = first_round ? first + j : (int)ids[j < n_cur ? j : 0];
+            keys[j] = j < n_cur ? Key32::make(loss_at(j, id), j, desc) : Key32::pad();
+        }
+        __syncwarp();
+        warp_bitonic_smem(keys, npad, lane);
+        for (int j = lane; j < keep; j += 32) {
+            const int pos = keys[j].pos();
+            ids_next[j] = (unsigned short)(first_round ? first + pos : (int)ids[pos]);
+        }
+        const int pos0 = keys[0].pos();
+        rb_arm = first_round ? first + pos0 : (int)ids[pos0];
+        rb_loss = loss_at(pos0, rb_arm);
+    }
+}
+
 template <typename T>
 struct HalvingOut {
     T* ofe;
@@ -140,7 +275,10 @@ __device__ void warp_halving_bracket(const at2_plan& plan, int b, const T* ck, i
         int rb_arm;
         if (latest_ck != nullptr)
             for (int j = lane; j < n_cur; j += 32) latest_ck[first_round ? first + j : (int)ids[j]] = (unsigned char)c;
-        if (n_cur <= 32) {
+        if constexpr (sizeof(T) == 4) {
+            warp_halving_round_f32(n_cur, keep, first_round, first, ids, ids_next, keys, desc, lane,
+                                   [&](int, int id) { return col[id]; }, rb_loss, rb_arm);
+        } else if (n_cur <= 32) {
             K mine = K::pad();
             T my_loss = (T)0;
             int my_id = 0;

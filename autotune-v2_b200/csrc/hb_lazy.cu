@@ -115,36 +115,8 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                     unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
                     float rb_loss;
                     int rb_arm;
-                    if (n_cur <= 32) {
-                        Key32 mine_k = Key32::pad();
-                        float my_loss = 0.0f;
-                        int my_id = 0;
-                        if (lane < n_cur) {
-                            my_id = first_round ? first + lane : (int)in[lane];
-                            my_loss = loss[lane];
-                            mine_k = Key32::make(my_loss, lane, desc);
-                        }
-                        mine_k = warp_bitonic_shfl(mine_k, lane, n_cur);
-                        const int src = mine_k.pos() & 31;
-                        const int sid = __shfl_sync(0xffffffffu, my_id, src);
-                        const float sl = __shfl_sync(0xffffffffu, my_loss, src);
-                        rb_loss = __shfl_sync(0xffffffffu, sl, 0);
-                        rb_arm = __shfl_sync(0xffffffffu, sid, 0);
-                        if (lane < keep) out[lane] = (unsigned short)sid;
-                    } else {
-                        int npad = 64;
-                        while (npad < n_cur) npad <<= 1;
-                        for (int j = lane; j < npad; j += 32) keys[j] = j < n_cur ? Key32::make(loss[j], j, desc) : Key32::pad();
-                        __syncwarp();
-                        warp_bitonic_smem(keys, npad, lane);
-                        for (int j = lane; j < keep; j += 32) {
-                            const int pos = keys[j].pos();
-                            out[j] = (unsigned short)(first_round ? first + pos : (int)in[pos]);
-                        }
-                        const int pos0 = keys[0].pos();
-                        rb_arm = first_round ? first + pos0 : (int)in[pos0];
-                        rb_loss = loss[pos0];
-                    }
+                    warp_halving_round_f32(n_cur, keep, first_round, first, in, out, keys, desc, lane,
+                                           [&](int j, int) { return loss[j]; }, rb_loss, rb_arm);
                     __syncwarp();
                     const int sw = surv_w[g];
                     if (p.survivors != nullptr)
