@@ -213,7 +213,10 @@ class KnownFnSpec:
 
     def lookup(self, queries, times=None):
         """Nearest recorded arm of each query row (raw values in domain order); with `times` also the loss read-out."""
-        q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float64)).to(self.device)
+        if torch.is_tensor(queries):
+            q = queries.to(self.device, torch.float64).contiguous()
+        else:
+            q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float64)).to(self.device)
         if times is None:
             idx, dist, _ = torch.ops.at2.nn_lookup(self.domain_bytes, self.db, q, self.db.new_empty((0, 0)),
                                                    torch.empty(0, device=self.device, dtype=torch.int32))

@@ -49,15 +49,53 @@ int make_domain(const at2_domain* dom, DomainDev* d) {
     return AT2_OK;
 }
 
-// normalised squared error in the reference's operation order; q, a are already normalised
-__device__ __forceinline__ double sq_error(const double* q, const double* a, const DomainDev& dom) {
-    double s = 0.0;   // python sum() starts from int 0: 0 + t0 is exact
-    for (int k = 0; k < dom.D; ++k) {
-        const int h = dom.order[k];
-        const double diff = __dsub_rn(q[h], a[h]);
-        s = __dadd_rn(s, __dmul_rn(diff, diff));
+// Nearest row of a normalised table to a normalised query.  Both are laid out in SUMMATION order (position k holds
+// hyperparameter dom.order[k], the k-th attribute of a drawn arm), so the reference's left-to-right python sum() of squared
+// differences (known_loss_fn_problem.py:42-47; 0 + t0 is exact) is a straight walk: s[cnt][D] rows, qo[D] query.  Strict
+// `<` keeps the FIRST minimum; rows whose global index base + a falls in [ex_lo, ex_hi) are skipped (cross-validation).
+// DT = D at compile time: the query sits in registers and the row loop is unrolled (the scan is then FP64-pipe bound:
+// 3 D - 1 DP operations per row); DT = 0 is the generic fallback.
+template <int DT>
+__device__ __forceinline__ void scan_rows(const double* qo, const double* __restrict__ s, int cnt, int D, int base, int ex_lo,
+                                          int ex_hi, double& best, int& best_i) {
+    if constexpr (DT > 0) {
+        double q[DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) q[k] = qo[k];
+#pragma unroll 2
+        for (int a = 0; a < cnt; ++a) {
+            const double* r = s + a * DT;
+            double diff = __dsub_rn(q[0], r[0]);
+            double e = __dmul_rn(diff, diff);
+#pragma unroll
+            for (int k = 1; k < DT; ++k) {
+                diff = __dsub_rn(q[k], r[k]);
+                e = __dadd_rn(e, __dmul_rn(diff, diff));
+            }
+            const int ga = base + a;
+            if (e < best && !(ga >= ex_lo && ga < ex_hi)) best = e, best_i = ga;
+        }
+    } else {
+        for (int a = 0; a < cnt; ++a) {
+            const double* r = s + a * D;
+            double e = 0.0;
+            for (int k = 0; k < D; ++k) {
+                const double diff = __dsub_rn(qo[k], r[k]);
+                e = __dadd_rn(e, __dmul_rn(diff, diff));
+            }
+            const int ga = base + a;
+            if (e < best && !(ga >= ex_lo && ga < ex_hi)) best = e, best_i = ga;
+        }
     }
-    return s;
+}
+__device__ __forceinline__ void scan_rows_dispatch(const double* qo, const double* __restrict__ s, int cnt, int D, int base,
+                                                   int ex_lo, int ex_hi, double& best, int& best_i) {
+    switch (D) {   // the reference's recorded-arm shapes: MNIST D = 4, CIFAR D = 9; test functions D = 2
+        case 2: return scan_rows<2>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
+        case 4: return scan_rows<4>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
+        case 9: return scan_rows<9>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
+        default: return scan_rows<0>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
+    }
 }
 
 __device__ __forceinline__ double normalise(double v, int h, const DomainDev& dom) {
@@ -77,9 +115,11 @@ __global__ void __launch_bounds__(NN_BLOCK) nn_lookup_kernel(const __grid_consta
     const int D = dom.D;
     const long long qi = (long long)blockIdx.x * NN_BLOCK + threadIdx.x;
     const bool active = qi < nq;
-    double q[AT2_MAX_PARAMS];
-#pragma unroll
-    for (int h = 0; h < AT2_MAX_PARAMS; ++h) q[h] = (h < D && active) ? normalise(queries[qi * D + h], h, dom) : 0.0;
+    double q[AT2_MAX_PARAMS];   // summation order
+    for (int k = 0; k < D; ++k) {
+        const int h = dom.order[k];
+        q[k] = active ? normalise(queries[qi * D + h], h, dom) : 0.0;
+    }
     const int a_lo = blockIdx.y * chunk_len, a_hi = min(A, a_lo + chunk_len);
     const int ex_lo = (exclude != nullptr && active) ? exclude[2 * qi] : 0;
     const int ex_hi = (exclude != nullptr && active) ? exclude[2 * qi + 1] : 0;
@@ -88,13 +128,12 @@ __global__ void __launch_bounds__(NN_BLOCK) nn_lookup_kernel(const __grid_consta
     for (int base = a_lo; base < a_hi; base += tile_a) {
         const int cnt = min(tile_a, a_hi - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt * D; i += NN_BLOCK) s_db[i] = normalise(db[(size_t)base * D + i], i % D, dom);
-        __syncthreads();
-        for (int a = 0; a < cnt; ++a) {
-            const double e = sq_error(q, s_db + a * D, dom);
-            const int ga = base + a;
-            if (e < best && !(ga >= ex_lo && ga < ex_hi)) best = e, best_i = ga;   // strict <: first minimum wins
+        for (int i = threadIdx.x; i < cnt * D; i += NN_BLOCK) {
+            const int a = i / D, h = dom.order[i - a * D];
+            s_db[i] = normalise(db[(size_t)(base + a) * D + h], h, dom);
         }
+        __syncthreads();
+        scan_rows_dispatch(q, s_db, cnt, D, base, ex_lo, ex_hi, best, best_i);
     }
     if (active) {
         part_dist[qi * n_chunks + blockIdx.y] = best;
@@ -176,7 +215,10 @@ __global__ void __launch_bounds__(128) hb_knownfn_kernel(const __grid_constant__
     double* s_db = reinterpret_cast<double*>(smem_raw);                       // [A][D] normalised
     unsigned char* warp_base = smem_raw + (((size_t)p.A * D * sizeof(double) + 15) & ~(size_t)15);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i < p.A * D; i += blockDim.x) s_db[i] = normalise(p.db[i], i % D, p.dom);
+    for (int i = tid; i < p.A * D; i += blockDim.x) {           // summation order, see scan_rows
+        const int a = i / D, h = p.dom.order[i - a * D];
+        s_db[i] = normalise(p.db[a * D + h], h, p.dom);
+    }
     __syncthreads();
     double* s_ck = reinterpret_cast<double*>(warp_base + (size_t)warp * p.warp_bytes);   // [C][stride]
     Key64* keys = reinterpret_cast<Key64*>(s_ck + (size_t)C * p.stride);
@@ -199,13 +241,13 @@ __global__ void __launch_bounds__(128) hb_knownfn_kernel(const __grid_constant__
                 } else {
                     draw_proposed(p, (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A_arms + arm, vals);
                 }
-                for (int h = 0; h < D; ++h) q[h] = normalise(vals[h], h, p.dom);
+                for (int k = 0; k < D; ++k) {
+                    const int h = p.dom.order[k];
+                    q[k] = normalise(vals[h], h, p.dom);
+                }
                 double best = CUDART_INF;
                 int best_i = 0;
-                for (int a = 0; a < p.A; ++a) {
-                    const double e = sq_error(q, s_db + a * D, p.dom);
-                    if (e < best) best = e, best_i = a;
-                }
+                scan_rows_dispatch(q, s_db, p.A, D, 0, 0, 0, best, best_i);
                 if (p.nn_idx != nullptr) p.nn_idx[rep_g * A_arms + arm] = best_i;
                 for (int c = 0; c < C; ++c) {
                     const double loss = p.curves[(size_t)best_i * p.L + (p.plan.ckpt_time[c] - 1)];
