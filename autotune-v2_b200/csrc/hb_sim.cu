@@ -40,6 +40,7 @@ struct Params {
     int G;            // repetitions per tile
     long long n_tiles;
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
+    int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
     int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
     int n_teams;      // teams per CTA
     int npad;         // power of two >= widest bracket
@@ -104,7 +105,53 @@ __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __
         const int n_items = g_eff * A;
 
         // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
-        for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
+        bool split_done = false;
+        if constexpr (MODE == MODE_PHILOX && HAS_SMOOTH) {
+            if (p.split_cap > 0) {
+                // Families mix raw and Savitzky-Golay-smoothed arms.  A smoothed arm accumulates C dot products along its
+                // trajectory; in a mixed warp pass every lane pays for them.  So this warp first lists its items with the raw
+                // arms in front and the smoothed ones at the back (the family of an arm is one Philox block away), then runs
+                // the passes that hold only raw arms through the lean loop.  The list aliases the halving sort scratch.
+                // Every arm is simulated by the same arithmetic either way: outputs do not change by a bit.
+                unsigned short* order = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride)) +
+                                        (size_t)wteam * p.split_cap;
+                const int cap = p.split_cap;
+                int n_raw = 0, n_sm = 0;
+                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
+                    const int i = base + lane;
+                    const bool act = i < n_items;
+                    const int ii = act ? i : 0;
+                    const int rep_l = ii / A, arm = ii - rep_l * A;
+                    const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
+                    const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
+                    const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (act) order[sm ? cap - 1 - (n_sm + __popc(m_sm & below)) : n_raw + __popc(m_raw & below)] = (unsigned short)i;
+                    n_raw += __popc(m_raw), n_sm += __popc(m_sm);
+                }
+                __syncwarp();
+                for (int k = 0; k < n_raw + n_sm; k += 32) {
+                    const int q = k + lane;
+                    const bool active = q < n_raw + n_sm;
+                    const int ii = active ? (int)order[q < n_raw ? q : cap - 1 - (q - n_raw)] : 0;
+                    const int rep_l = ii / A, arm = ii - rep_l * A;
+                    const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
+                    const ArmDraw d = draw_arm(p.sp, gid, arm);
+                    const Fam<T> fam = p.fam[d.fam];
+                    const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
+                    const float fn = f - (float)fam.s1, f1 = (f + p.sp.noise * d.z) - (float)fam.s0;
+                    if (k + 32 <= n_raw)
+                        philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.ml, (float)fam.up,
+                                                                    fam.pw_off, gid, p.sp.rk, R, s_ck + ii, p.stride, C);
+                    else
+                        philox_trajectory<T, true, CK, false, GTAB>(tb, active, fam.smooth != 0, f1, fn, (float)fam.ml,
+                                                                    (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
+                                                                    p.stride, C);
+                }
+                split_done = true;
+            }
+        }
+        for (int base = wteam * 32; base < n_items && !split_done; base += p.team_warps * 32) {
             const int i = base + lane;
             const bool active = i < n_items;
             const int ii = active ? i : 0;
@@ -352,6 +399,14 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
     p->sort_warps = lc->team_warps < lc->G ? lc->team_warps : lc->G;
+    // raw / smoothed arms in separate warp passes when the families mix both and a warp's order list fits in the team's sort
+    // scratch, which it aliases (see the kernel); AT2_HB_NO_SPLIT=1 disables it (development aid)
+    int n_smooth = 0;
+    for (int f = 0; f < cfg->n_families; ++f) n_smooth += cfg->fam[f].is_smooth ? 1 : 0;
+    const int cap = ((lc->stride / 32 + lc->team_warps - 1) / lc->team_warps) * 32;
+    const size_t scratch = (size_t)p->sort_warps * lc->npad * (sizeof(typename KeyOf<T>::type) + 2 * sizeof(unsigned short));
+    p->split_cap = (n_smooth > 0 && n_smooth < cfg->n_families && (size_t)cap * 2 * lc->team_warps <= scratch &&
+                    lc->stride < 65536 && getenv("AT2_HB_NO_SPLIT") == nullptr) ? cap : 0;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     return AT2_OK;
 }

@@ -159,6 +159,13 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
     return d;
 }
 
+// the family draw_arm would give this arm, without the rest of the draw
+__device__ __noinline__ int arm_family(const ArmSpace& sp, unsigned long long gid, int arm) {
+    if (sp.scheduler != AT2_SCHED_UNIFORM) return arm % sp.F;
+    const At2U4 r = at2_philox10(At2U4{0u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
+    return (int)__umulhi(r.z, (uint32_t)sp.F);
+}
+
 // Shared-memory tables of one CTA as the trajectory loop sees them.
 struct SimTables {
     uint32_t rec_addr;     // shared-space address of rec[0][0]  (GTAB: byte offset of rec in the global table)
