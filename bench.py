@@ -126,14 +126,15 @@ class ClockSampler(threading.Thread):
                 'samples': len(inside)}
 
 
-def measured_traffic():
-    """DRAM bytes per launch of the simulation kernel from the committed ncu --set full capture (profiles/), or None."""
+def measured_traffic(key='dram_bytes_per_launch_avg'):
+    """DRAM bytes (or SASS-counted FP32 flop) per launch of the simulation kernel from the committed ncu captures
+    (profiles/), or None."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'r01_dram_traffic.json')) as f:
             d = json.load(f)
         for k, v in d.items():
             if k.startswith('hb_sim_kernel<float, 0, 0, 1'):
-                return v['dram_bytes_per_launch_avg']
+                return v[key]
     except Exception:  # noqa: BLE001
         pass
     return None
@@ -351,6 +352,7 @@ def main():
                          'peak_source': 'best of 3 FFMA micro-benchmark variants measured in this run '
                                         '(at2_fma_peak_probe); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s',
                          'fma_probe_variants_tflops': fma_variants,
+                         'sass_counted_fp32_flop_per_launch': measured_traffic('sass_fp32_flop_per_launch'),
                          'kernel_ms': sim_ms, 'algorithmic_flop_per_launch': n_local * ARM_EPOCHS * FLOP_PER_ARM_EPOCH,
                          'hbm_peak_gbs': peaks.get('hbm_gbs'), 'hbm_peak_source': peak_src},
         }

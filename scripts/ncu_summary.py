@@ -86,6 +86,22 @@ for rep in (f'{tag}_prof_bench.ncu-rep', f'{tag}_prof_tpe.ncu-rep'):
             return float(x) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(unit, 1)
         traffic[k] = {'dram_bytes_per_launch_avg': sum(tobytes(q[rd], units[rd]) + tobytes(q[wr], units[wr]) for q in rs) / len(rs),
                       'launches_captured': len(rs)}
+# ---- SASS-counted FP32 work of one simulation launch (separate --metrics pass) ----
+scsv = os.path.join(out, f'{tag}_sass_flops.csv')
+if os.path.exists(scsv):
+    vals = {}
+    with open(scsv) as f:
+        for r in csv.reader(f):
+            if len(r) > 14 and r[0].isdigit():
+                vals[r[12]] = float(r[14])
+                kname = short(r[4])
+    fadd, fmul, ffma = (vals.get(f'smsp__sass_thread_inst_executed_op_{k}_pred_on.sum', 0.0) for k in ('fadd', 'fmul', 'ffma'))
+    flop = fadd + fmul + 2 * ffma
+    lines += [f'## SASS-counted FP32 work of one `{kname}` launch', '', '| metric | value |', '|---|---|'] + \
+             [f'| `{k}` | {v:.0f} |' for k, v in vals.items()] + \
+             [f'| FP32 flop (fadd + fmul + 2 ffma) | {flop:.0f} |', '']
+    traffic.setdefault(kname, {})['sass_fp32_flop_per_launch'] = flop
+    traffic[kname]['thread_inst_per_launch'] = vals.get('smsp__thread_inst_executed.sum')
 traffic['_source'] = f'ncu --set full --clock-control none, profiles/{tag}_kernels_ncu_summary.md'
 with open(os.path.join(prof, f'{tag}_kernels_ncu_summary.md'), 'w') as f:
     f.write('\n'.join(lines) + '\n')
