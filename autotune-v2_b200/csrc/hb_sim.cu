@@ -62,8 +62,10 @@ struct Params {
     T* ckpt_loss;
 };
 
+// Shared memory (a 3-repetition tile per warp) holds three 8-warp CTAs per SM at the headline shapes, so the register cap
+// is 80, not 64: measured -4 % on the configurations with smoothed families, no change on the flat one.
 #ifndef AT2_HB_MIN_BLOCKS
-#define AT2_HB_MIN_BLOCKS 4
+#define AT2_HB_MIN_BLOCKS 3
 #endif
 template <typename T, int MODE, bool HAS_SMOOTH, int CK, bool GTAB>
 __global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __grid_constant__ Params<T> p) {
