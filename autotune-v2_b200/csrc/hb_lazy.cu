@@ -230,7 +230,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
     size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     // plans whose tables do not fit beside two warps' state read them from global memory
-    const bool gtab = fixed + 2 * (size_t)p.warp_bytes > (size_t)max_smem;
+    const bool gtab = fixed + 2 * (size_t)p.warp_bytes > (size_t)max_smem || getenv("AT2_FORCE_GTAB") != nullptr;   // env: tests
     if (gtab) fixed = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     int nwarps = 8;
     while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;

@@ -308,7 +308,7 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     size_t team_bytes = (size_t)C * stride * sizeof(T) + (best_tw < best_g ? best_tw : best_g) * sort_per_warp;
     team_bytes = (team_bytes + 15) & ~(size_t)15;
     // plans whose tables do not fit beside one team's state (R ~ 1000 with six families) read them from global memory
-    out->gtab = fixed + team_bytes > (size_t)max_smem ? 1 : 0;
+    out->gtab = (fixed + team_bytes > (size_t)max_smem || getenv("AT2_FORCE_GTAB") != nullptr) ? 1 : 0;   // env: tests
     if (out->gtab) fixed = (AT2_MAX_CKPTS + 4) * sizeof(int);
     int warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", 8);
     if (warps_per_cta < best_tw) warps_per_cta = best_tw;

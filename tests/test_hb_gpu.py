@@ -269,3 +269,38 @@ def test_egg4_extension_flat_family_ofe_is_the_function_value():
     from autotune.b200.engine import run_hybrid_repetitions
     with pytest.raises(Exception, match='2-D'):
         run_hybrid_repetitions(spec, 10, 'none')
+
+
+def test_global_memory_tables_are_bit_identical_to_shared_memory_tables(monkeypatch):
+    """Plans too large for shared memory read their constant tables from global memory (GTAB kernel variants); forced
+    here on ordinary plans, every output must equal the shared-memory variant's bit for bit - full and early-stopping."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    for func, fams, R in (('rastrigin', FAM6, 81), ('branin', FLAT, 81), ('egg', FAM6[:3], 243)):
+        spec = HyperbandSimSpec(func, fams, R, 3, 10)
+        n = 600 if R < 243 else 150
+        monkeypatch.delenv('AT2_FORCE_GTAB', raising=False)
+        a = run_hyperband_repetitions(spec, n, seed=23, details=True)
+        al = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=True)
+        monkeypatch.setenv('AT2_FORCE_GTAB', '1')
+        b = run_hyperband_repetitions(spec, n, seed=23, details=True)
+        bl = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=True)
+        monkeypatch.delenv('AT2_FORCE_GTAB')
+        for k in a:
+            assert torch.equal(a[k], b[k]), (func, k)
+        for k in al:
+            assert torch.equal(al[k], bl[k]) and torch.equal(al[k], a[k]), (func, k)
+
+
+def test_raw_smoothed_split_passes_do_not_change_outputs(monkeypatch):
+    """Mixed families: raw and smoothed arms of a tile run in separate warp passes (hb_sim.cu).  Disabling the split must
+    give the same bits."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    for func, fams, R, sched in (('rastrigin', FAM6, 81, 'uniform'), ('egg', FAM6[:3], 243, 'round-robin'), ('wave', FAM6, 27, 'uniform')):
+        spec = HyperbandSimSpec(func, fams, R, 3, 10, sched)
+        monkeypatch.delenv('AT2_HB_NO_SPLIT', raising=False)
+        a = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True)
+        monkeypatch.setenv('AT2_HB_NO_SPLIT', '1')
+        b = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True)
+        monkeypatch.delenv('AT2_HB_NO_SPLIT')
+        for k in a:
+            assert torch.equal(a[k], b[k]), (func, k)
