@@ -90,9 +90,10 @@ __device__ __forceinline__ void scan_rows(const double* qo, const double* __rest
 }
 __device__ __forceinline__ void scan_rows_dispatch(const double* qo, const double* __restrict__ s, int cnt, int D, int base,
                                                    int ex_lo, int ex_hi, double& best, int& best_i) {
-    switch (D) {   // the reference's recorded-arm shapes: MNIST D = 4, CIFAR D = 9; test functions D = 2
+    switch (D) {   // the reference's recorded-arm shapes: MNIST D = 4, CIFAR D = 9; test functions D = 2; D = 8: bench
         case 2: return scan_rows<2>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
         case 4: return scan_rows<4>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
+        case 8: return scan_rows<8>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
         case 9: return scan_rows<9>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
         default: return scan_rows<0>(qo, s, cnt, D, base, ex_lo, ex_hi, best, best_i);
     }

@@ -166,10 +166,20 @@ def main():
         pool.run(FUNC, FAMILIES, R, ETA, NOISE, 2)
         reps_per_proc = 200
         v, wall, _ = pool.run(FUNC, FAMILIES, R, ETA, NOISE, reps_per_proc)
-        pool.close()
         cpu_baseline = {'value': v, 'unit': UNIT, 'cores': procs, 'kind': 'port',
                         'sample': f'{procs} processes x {reps_per_proc} repetitions of the same workload, '
                                   f'{wall:.1f} s wall', 'arm_epochs_per_s_executed': v * (81 * 160 + 27 * 80 + 9 * 80)}
+        # also quote what batched NumPy reaches on the same cores, so the GPU/CPU ratio is not overstated
+        from oracle import vectorised as ov
+        vec_reps = 3000
+        jobs = [(FUNC, FAMILIES, R, ETA, NOISE, vec_reps, 500, 7000 + w) for w in range(procs)]
+        t0 = time.perf_counter()
+        pool.pool.map(ov._worker, jobs) if pool.pool else [ov._worker(jobs[0])]
+        vwall = time.perf_counter() - t0
+        cpu_baseline['vectorised_numpy'] = {
+            'value': procs * vec_reps / vwall, 'unit': UNIT, 'cores': procs, 'kind': 'port (batched NumPy, not the '
+            "reference's code shape)", 'sample': f'{procs} processes x {vec_reps} repetitions in blocks of 500, {vwall:.1f} s wall'}
+        pool.close()
 
     import torch
     import torch.distributed as dist
@@ -285,6 +295,7 @@ def main():
     extras = {}
     if rank == 0:
         from autotune.b200.engine import run_hybrid_repetitions
+        peaks_hbm = measured_peaks()[0].get('hbm_gbs')
 
         def timed(fn, n_units, steps=8):
             for i in range(3):
@@ -326,7 +337,34 @@ def main():
         except Exception as e:  # noqa: BLE001
             extras['hb_closest_known_fn_mnist_shape_A425_D4_R81_1e4reps'] = {'error': repr(e)}
         big = torch.randn(1000000, device=dev)
-        extras['kde_epanechnikov_1e6_samples_1000_grid'] = timed(lambda sd: density(big, -4.0, 4.0, 0.3, 1000), 1000000)
+        extras['kde_epanechnikov_1e6_samples_1000_grid'] = k = timed(lambda sd: density(big, -4.0, 4.0, 0.3, 1000), 1000000)
+        k['fp32_tflops_6_flop_per_pair'] = 6.0 * 1e6 * 1000 / (k['ms_per_step'] * 1e-3) / 1e12
+        k['frac_of_measured_ffma_peak'] = k['fp32_tflops_6_flop_per_pair'] / fma_peak_tflops
+        k['input_gb_per_s'] = (4e6 + 4e3) / (k['ms_per_step'] * 1e-3) / 1e9
+        try:   # scaled-up nearest-recorded-arm scan: A = 2^20 recorded arms x D = 8, 2^13 queries
+            from autotune.b200 import ops as at2ops
+            from autotune.b200.engine import domain_desc
+            from autotune.core import Domain, Param
+            dom8 = Domain(**{f'h{i}': Param(f'h{i}', 0.0, 1.0, distrib='uniform', scale='linear') for i in range(8)})
+            desc8, names8 = domain_desc(dom8, tuple(dom8.hyperparams_names()))
+            dbytes = at2ops.struct_tensor(desc8)
+            A8, Q8 = 1 << 20, 1 << 13
+            db8 = torch.rand(A8, 8, device=dev, dtype=torch.float64)
+            q8 = torch.rand(Q8, 8, device=dev, dtype=torch.float64)
+            none_c, none_t = db8.new_empty((0, 0)), torch.empty(0, device=dev, dtype=torch.int32)
+            extras['nn_lookup_A2^20_D8_2^13_queries'] = k = timed(
+                lambda sd: torch.ops.at2.nn_lookup(dbytes, db8, q8, none_c, none_t), Q8, steps=3)
+            dp_instr = float(Q8) * A8 * (3 * 8 - 1)
+            k['lookups_per_s'] = k.pop('runs_per_s')
+            k['fp64_instr_per_s'] = dp_instr / (k['ms_per_step'] * 1e-3)
+            k['frac_of_fp64_issue_rate'] = k['fp64_instr_per_s'] / (148 * 64 * 1.965e9)
+            k['db_stream_gb_per_s'] = (Q8 / 128) * A8 * 8 * 8 / (k['ms_per_step'] * 1e-3) / 1e9
+            k['note'] = ('float64, un-fused, first-minimum; every 128-query CTA streams the 64 MB table (L2-resident) once; '
+                         'FP64-pipe bound (3D-1 DP instructions per recorded arm per query), not HBM bound: '
+                         f'hbm copy peak {peaks_hbm} GB/s')
+            del db8, q8
+        except Exception as e:  # noqa: BLE001
+            extras['nn_lookup_A2^20_D8_2^13_queries'] = {'error': repr(e)}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

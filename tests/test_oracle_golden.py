@@ -88,3 +88,18 @@ def test_gamma_parameters():
             a, s = gp.gamma_shape_scale(t, R)
             assert 1 < a <= 3.7321
             assert abs((a - 1) * s - 2) < 1e-12
+
+
+def test_vectorised_numpy_port_matches_reference_ofe_distributions():
+    """oracle/vectorised.py (bench.py's `cpu_baseline.vectorised_numpy`) against the reference's stored OFE vectors."""
+    from scipy.stats import ks_2samp
+
+    from oracle import vectorised as ov
+    fam6 = [(1.5, 10, 15, False, 0, 200), (0.5, 7, 10, False, 0, 200), (0.2, 4, 7, True, 0, 200),
+            (1.5, 10, 15, False, 200, 400), (0.5, 7, 10, False, 200, 400), (0.2, 4, 7, True, 200, 400)]
+    g = np.load(f'{GOLDEN}/epdf_ofes.npz')
+    for key, func, fams, noise in (('simulation-rastrigin-families-2/hist-sim-rastrigin-sim(hb)-7000-1', 'rastrigin', fam6, 10),
+                                   ('simulation-flat-branin/hist-sim(hb)-7000-1', 'branin', [(0, 1, 0, False, 0, 0)], 0),
+                                   ('simulation-flat-drop-wave/hist-sim-wave-sim(hb)-7000-1', 'wave', [(0, 1, 0, False, 0, 0)], 0)):
+        got = ov.run_batch(func, fams, 81, 3, noise, 1500, np.random.default_rng(5))
+        assert ks_2samp(got, g[key]).pvalue > 0.01, key
