@@ -63,14 +63,13 @@ class RecordedDomainProblem(HyperparameterOptimisationProblem):
 
 
 def mnist_domain_problem():
-    return RecordedDomainProblem('mnist', MNIST_DOMAIN)
+    from autotune.benchmarks.mnist_problem import MnistProblem
+    return MnistProblem()
 
 
 def cifar_domain_problem():
-    p = RecordedDomainProblem('cifar', CIFAR_DOMAIN, CIFAR_HYPERPARAMS_TO_OPTIMIZE)
-    # keep the domain order (the reference's set intersection leaves it unspecified; its arms are drawn in domain order)
-    p.hyperparams_to_opt = tuple(n for n in CIFAR_DOMAIN.hyperparams_names() if n in CIFAR_HYPERPARAMS_TO_OPTIMIZE)
-    return p
+    from autotune.benchmarks.cifar_problem import CifarProblem
+    return CifarProblem()
 
 
 def synthetic_database(problem, n_arms, curve_len=300, seed=0):

@@ -16,8 +16,9 @@ from os.path import exists, join as join_path
 
 import numpy as np
 
-from autotune.benchmarks import AVAILABLE_OPT_FUNCTIONS, KnownFnProblem, OptFunctionProblem
-from autotune.benchmarks.mnist_like import cifar_domain_problem, mnist_domain_problem, synthetic_database
+from autotune.benchmarks import (
+    AVAILABLE_OPT_FUNCTIONS, CifarProblem, KnownFnProblem, MnistProblem, MrbiProblem, OptFunctionProblem, SvhnProblem)
+from autotune.benchmarks.mnist_like import synthetic_database
 from autotune.experiments.monte_carlo import run_repetitions
 from autotune.optimisers import HyperbandOptimiser
 
@@ -58,11 +59,13 @@ def get_real_problem(arguments):
     """The problem whose domain normalises the arms (:75-90); real training problems are replaced by their domains."""
     name = arguments.problem.lower()
     if name == "cifar":
-        return cifar_domain_problem()
+        return CifarProblem(arguments.input_dir, arguments.output_dir, dataset_loader=None)
     if name == "mnist":
-        return mnist_domain_problem()
-    if name in ("svhn", "mrbi"):
-        raise NotImplementedError(f'{name}: the reference has no recorded arms for it either (:124-127)')
+        return MnistProblem(arguments.input_dir, arguments.output_dir)
+    if name == "svhn":
+        return SvhnProblem(arguments.input_dir, arguments.output_dir)
+    if name == "mrbi":
+        return MrbiProblem(arguments.input_dir, arguments.output_dir)
     if name in AVAILABLE_OPT_FUNCTIONS:
         return OptFunctionProblem(name)
     raise ValueError(f"Supplied problem {name} does not exist")

@@ -5,10 +5,12 @@ from autotune.optimisers.sequential.hybrid_hyperband_tpe_with_transfer import (
     HybridHyperbandTpeTransferThresholdOptimiser)
 from autotune.optimisers.sequential.hyperband_optimiser import HyperbandOptimiser
 from autotune.optimisers.sequential.random_optimiser import RandomOptimiser
+from autotune.optimisers.sequential.sigopt_optimiser import HybridHyperbandSigoptOptimiser, SigOptimiser
 from autotune.optimisers.sequential.tpe_optimiser import TpeOptimiser
 
 __all__ = [
-    'HybridHyperbandTpeOptimiser', 'HyperbandOptimiser', 'RandomOptimiser', 'TpeOptimiser',
+    'HybridHyperbandTpeOptimiser', 'HybridHyperbandSigoptOptimiser', 'HyperbandOptimiser', 'RandomOptimiser',
+    'SigOptimiser', 'TpeOptimiser',
     'HybridHyperbandTpeTransferAllOptimiser', 'HybridHyperbandTpeTransferLongestOptimiser',
     'HybridHyperbandTpeTransferThresholdOptimiser', 'HybridHyperbandTpeNoTransferOptimiser',
     'HybridHyperbandTpeTransferSameOptimiser']
