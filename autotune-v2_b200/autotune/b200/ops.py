@@ -218,17 +218,20 @@ def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.T
 def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, tpe_bytes: torch.Tensor, n_reps: int,
             rep_offset: int, seed: int, details: bool) -> List[torch.Tensor]:
     """Hyperband-TPE hybrids / stand-alone TPE / random search on the simulation problem (at2_tpe_sim_f32).
-    Returns the at2::hb_sim_f32 outputs followed by arm_xy [n_reps, n_arms, 2] when `details`."""
+    Returns the at2::hb_sim_f32 outputs followed, when `details`, by arm_xy [n_reps, n_arms, 2] and obs_loss [n_reps, n_arms]
+    (the loss the TPE phase observed for an arm; NaN for arms that were not observed)."""
     _require_cuda(tables, 'tables')
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     tpe = _struct(nat.TpeConfig, tpe_bytes)
     with torch.cuda.device(tables.device):
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
         arm_xy = torch.empty(n_reps, plan.n_arms, 2, device=tables.device, dtype=torch.float32) if details else None
+        obs = torch.full((n_reps, plan.n_arms), float('nan'), device=tables.device, dtype=torch.float32) if details else None
         nat.check(nat.lib.at2_tpe_sim_f32(C.byref(plan), C.byref(cfg), C.byref(tpe), tables.data_ptr(), n_reps, rep_offset,
                                           seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs),
-                                          arm_xy.data_ptr() if details else None, _stream_ptr(tables.device)))
-    return tensors + ([arm_xy] if details else [])
+                                          arm_xy.data_ptr() if details else None, obs.data_ptr() if details else None,
+                                          _stream_ptr(tables.device)))
+    return tensors + ([arm_xy, obs] if details else [])
 
 
 @torch.library.custom_op('at2::tpe_score', mutates_args=(), device_types='cuda')

@@ -50,6 +50,7 @@ struct TpeParams {
     int* survivors;
     float* ckpt_loss;
     float* arm_xy;      // optional [n_reps][n_arms][2]
+    float* obs_loss;    // optional [n_reps][n_arms]: the loss TPE observed (only written for observed arms)
 };
 
 // warp-private working set
@@ -427,9 +428,11 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                             xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.rk, r0, lane);
                         if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
                     }
-                    if (step + 1 < n_b)                              // the loss TPE sees for this arm
-                        do_insert = true, ix = xy[0], iy = xy[1],
-                        il = sign * (base_function(p.sp.func, xy[0], xy[1]) + w.ck[arm]);
+                    if (step + 1 < n_b) {                            // the loss TPE sees for this arm
+                        const float loss = base_function(p.sp.func, xy[0], xy[1]) + w.ck[arm];
+                        do_insert = true, ix = xy[0], iy = xy[1], il = sign * loss;
+                        if (lane == 0 && p.obs_loss != nullptr) p.obs_loss[rep * A + arm] = loss;
+                    }
                 }
                 __syncwarp();
                 if (do_insert) tpe_insert(w, ix, iy, il, lane);
@@ -567,7 +570,7 @@ extern "C" int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resou
 
 extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe,
                                const void* d_tables, int64_t n_reps, int64_t rep_offset, uint64_t seed,
-                               const at2_hb_outputs* out, float* d_arm_xy, void* stream) {
+                               const at2_hb_outputs* out, float* d_arm_xy, float* d_obs_loss, void* stream) {
     at2_reset_launch_count();
     AT2_REQUIRE(plan && cfg && d_tables && out, "at2_tpe_sim_f32: NULL plan/config/tables/outputs");
     AT2_REQUIRE(n_reps > 0 && rep_offset >= 0, "at2_tpe_sim_f32: n_reps must be positive and rep_offset >= 0");
@@ -602,7 +605,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     p.n_reps = n_reps, p.rep_offset = rep_offset;
     p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
     p.round_best = (float*)out->d_round_best, p.round_best_arm = out->d_round_best_arm;
-    p.survivors = out->d_survivors, p.ckpt_loss = (float*)out->d_ckpt_loss, p.arm_xy = d_arm_xy;
+    p.survivors = out->d_survivors, p.ckpt_loss = (float*)out->d_ckpt_loss, p.arm_xy = d_arm_xy, p.obs_loss = d_obs_loss;
     p.npad = halving_npad(plan);
     p.cap = (plan->n_arms + 31) & ~31;
     const int C = plan->n_ckpts;

@@ -190,10 +190,12 @@ int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resources, at2_p
 /* Hyperband whose first round of every bracket is a TPE run (+ history transfer), fused with simulation and halving:
  * replaces the repetition loop of experiments/run_simulation.py:147-157 for methods sim(hb+tpe), sim(hb+tpe+transfer+*),
  * sim(tpe), sim(random).  Same tables/outputs as at2_hb_sim_f32; with tpe->enabled == 0 and a Hyperband plan the results
- * are bit-identical to at2_hb_sim_f32.  d_arm_xy (optional): float[n_reps][n_arms][2] hyperparameters of every arm. */
+ * are bit-identical to at2_hb_sim_f32.  d_arm_xy (optional): float[n_reps][n_arms][2] hyperparameters of every arm.
+ * d_obs_loss (optional): float[n_reps][n_arms], the loss the TPE phase observed for an arm (its read-out at the bracket's
+ * first resource level, tpe_optimiser.py:62-89) - written only for arms that were observed, so pre-fill with NaN. */
 int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe, const void* d_tables,
                     int64_t n_reps, int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* d_arm_xy,
-                    void* stream);
+                    float* d_obs_loss, void* stream);
 
 /* Parzen-estimator scoring alone (parity of the estimator arithmetic): for each of n_problems independent 1-D
  * hp.uniform(low, high) problems with n_obs observations (d_obs, d_loss: float[n_problems][n_obs], trial order), build the

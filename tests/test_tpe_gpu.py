@@ -150,3 +150,31 @@ def test_standalone_tpe_and_random_search_vs_oracle():
     assert got_tpe.mean() < got_rnd.mean()
     with pytest.raises(IndexError):
         run_tpe_repetitions(spec, 10, 82, 81)                      # fs[81] on an 81-point curve: python raises IndexError
+
+
+@pytest.mark.parametrize('func,fams,R,noise', [('rastrigin', FAM6, 81, 10), ('egg', FAM6[:3], 243, 10), ('branin', FLAT, 81, 0),
+                                               ('wave', FAM6, 27, 5)])
+def test_tpe_observed_losses_equal_the_trajectory_readouts(func, fams, R, noise):
+    """The TPE phase observes an arm's loss at the bracket's first resource level as f(x, y) + offset, the offset coming
+    from an affine walk of the arm's Gamma stream made before the arm's hyperparameters were suggested
+    (sim_core.cuh philox_affine_offset).  It must be the read-out the full trajectory - simulated afterwards with the
+    suggested hyperparameters, the one successive halving ranks - shows at that checkpoint (FP32 rounding apart)."""
+    from autotune.b200.engine import run_hybrid_repetitions
+    spec = _spec(func, fams, R, noise)
+    out = run_hybrid_repetitions(spec, 300, 'all', seed=31, details=True)
+    obs, ck = out['obs_loss'], out['ckpt_loss']
+    plan, n_checked = spec.plan, 0
+    for b in range(plan.n_brackets):
+        first, n_b = plan.bracket_first_arm[b], plan.bracket_n[b]
+        c0 = plan.round_ckpt[plan.bracket_first_round[b]]
+        o = obs[:, first:first + n_b]
+        seen = ~torch.isnan(o)
+        if n_b > 10:                                         # a TPE bracket: every arm but the last was observed
+            assert seen[:, :-1].all() and not seen[:, -1].any()
+        else:                                                # 9 arms < 10 start-up trials: no TPE phase, nothing observed
+            assert not seen.any()
+        want = ck[:, first:first + n_b, c0]
+        scale = want[seen].abs().max().item() if seen.any() else 1.0
+        assert torch.allclose(o[seen], want[seen], rtol=2e-6, atol=2e-6 * scale + 1e-5)
+        n_checked += int(seen.sum())
+    assert n_checked >= 300 * 26
