@@ -8,8 +8,11 @@
 //     re-drawing whenever any lane rejects; per-epoch constants come from shared-memory tables indexed per lane;
 //   * only the losses at the Hyperband checkpoints are kept (shared memory, C values per arm); smooth families
 //     accumulate the Savitzky-Golay dot products of those C read-outs on the fly, so no trajectory is ever stored;
-//   * successive halving then runs per repetition inside one warp: (loss, position) keys, bitonic network in shared
-//     memory for the wide first round, pure warp-shuffle network once a round fits in 32 lanes.
+//   * when the families mix raw and smoothed arms, a warp first lists its tile's arms raw-first and runs the all-raw
+//     warp passes through the lean trajectory loop (no dot products);
+//   * successive halving then runs per repetition inside one warp, in registers (halving.cuh): rounds of <= 32 arms are
+//     ranked by counting, wider rounds sorted by a bitonic network over 4 or 8 (loss, position) keys per lane with 64-bit
+//     shuffles; the float64 parity path and rounds wider than 256 use a shared-memory bitonic network.
 //
 // Reference behaviour implemented (paths relative to the reference root):
 //   core/simulation_evaluator.py:36-48,84-116   Gamma draw + recurrence
