@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
 // stand-alone scoring entry (tests): build both models from given observations, score given candidates
 __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __restrict__ loss, int n_obs, float lo, float hi,
                                  TpeDev cfg, const float* __restrict__ cand, int n_cand, float* __restrict__ score_out,
-                                 float* __restrict__ model_out, int cap, int n_prob) {
+                                 float* __restrict__ model_out, float* __restrict__ lean_out, int cap, int n_prob) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t warp_bytes = (size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (cap + 4) + 64;
@@ -519,6 +519,22 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
                     0.69314718055994531f * (fast_lg2(lg[q]) - fast_lg2(tpe_mixture(w, na, cand[(size_t)prob * n_cand + j])));
         }
         __syncwarp();
+        if (lean_out != nullptr) {      // the models as a suggestion inside the simulation kernel builds them
+            const int nb2 = tpe_build_model<false>(w, 0, true, lo, hi, cfg, lane, &unused);
+            for (int q = 0; q < 8; ++q) {
+                const int j = q * 32 + lane;
+                lg[q] = j < n_cand ? tpe_mixture(w, nb2, cand[(size_t)prob * n_cand + j]) : 1.0f;
+            }
+            __syncwarp();
+            const int na2 = tpe_build_model<false>(w, 0, false, lo, hi, cfg, lane, &unused);
+            for (int q = 0; q < 8; ++q) {
+                const int j = q * 32 + lane;
+                if (j < n_cand)
+                    lean_out[(size_t)prob * n_cand + j] =
+                        0.69314718055994531f * (fast_lg2(lg[q]) - fast_lg2(tpe_mixture(w, na2, cand[(size_t)prob * n_cand + j])));
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -649,7 +665,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
 
 extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low,
                                  double high, const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates,
-                                 float* d_scores, float* d_models, void* stream) {
+                                 float* d_scores, float* d_models, float* d_lean_scores, void* stream) {
     at2_reset_launch_count();
     TpeDev cfg;
     const int rc = fill_tpe(tpe, &cfg);
@@ -664,8 +680,8 @@ extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_
     AT2_CUDA_CHECK(cudaFuncSetAttribute(tpe_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (n_problems + nwarps - 1) / nwarps;
     tpe_score_kernel<<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(d_obs, d_loss, n_obs, (float)low, (float)high, cfg,
-                                                                         d_candidates, n_candidates, d_scores, d_models, cap,
-                                                                         n_problems);
+                                                                         d_candidates, n_candidates, d_scores, d_models,
+                                                                         d_lean_scores, cap, n_problems);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
     return AT2_OK;

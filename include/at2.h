@@ -201,10 +201,13 @@ int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_t
  * hp.uniform(low, high) problems with n_obs observations (d_obs, d_loss: float[n_problems][n_obs], trial order), build the
  * good/bad adaptive Parzen models and return log l(x) - log g(x) for the given candidates
  * (d_candidates, d_scores: float[n_problems][n_candidates]).  d_models (optional):
- * float[n_problems][2][cap+1][3] = (weight, mu, sigma) of the good then the bad model, cap = n_obs rounded up to 32. */
+ * float[n_problems][2][cap+1][3] = (weight, mu, sigma) of the good then the bad model, cap = n_obs rounded up to 32.
+ * d_lean_scores (optional): float[n_problems][n_candidates], the same candidates scored the way at2_tpe_sim_f32 scores them
+ * inside a suggestion - without the weight normalisation and the truncation mass p_accept, which shift all candidates of a
+ * problem alike: d_lean_scores - d_scores is constant per problem and the arg-max is the same. */
 int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low, double high,
                       const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates, float* d_scores,
-                      float* d_models, void* stream);
+                      float* d_models, float* d_lean_scores, void* stream);
 
 /* ---- (d): closest-known-loss-function approximation ------------------------------------------------------------------ */
 
