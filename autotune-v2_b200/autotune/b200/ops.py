@@ -59,8 +59,9 @@ def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     with torch.cuda.device(tables.device):
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, dims=nat.lib.at2_func_dims(cfg.func))
-        nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
-                                         seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
+        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
+            nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
+                                             seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
     return tensors
 
 
@@ -74,8 +75,9 @@ def hb_sim_early_stop(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes:
     with torch.cuda.device(tables.device):
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=False,
                                  dims=nat.lib.at2_func_dims(cfg.func))
-        nat.check(nat.lib.at2_hb_sim_early_stop_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
-                                                    seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
+        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
+            nat.check(nat.lib.at2_hb_sim_early_stop_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
+                                                        seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
     return tensors
 
 
@@ -207,10 +209,11 @@ def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.T
         ptr = lambda k: o[k].data_ptr() if k in o else None  # noqa: E731
         outs = nat.HbOutputs(ptr('ofe'), ptr('ofe_arm'), None, ptr('round_best'), ptr('round_best_arm'),
                              ptr('survivors'), ptr('ckpt_loss'))
-        nat.check(nat.lib.at2_hb_knownfn_f64(C.byref(plan), C.byref(dom), db.data_ptr(), A, curves.data_ptr(),
-                                             curves.shape[1], int(descending), n_reps, rep_offset,
-                                             seed & 0xFFFFFFFFFFFFFFFF, _opt_ptr(predrawn), C.byref(outs),
-                                             ptr('nn_idx'), ptr('best_arm_vals'), _stream_ptr(dev)))
+        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
+            nat.check(nat.lib.at2_hb_knownfn_f64(C.byref(plan), C.byref(dom), db.data_ptr(), A, curves.data_ptr(),
+                                                 curves.shape[1], int(descending), n_reps, rep_offset,
+                                                 seed & 0xFFFFFFFFFFFFFFFF, _opt_ptr(predrawn), C.byref(outs),
+                                                 ptr('nn_idx'), ptr('best_arm_vals'), _stream_ptr(dev)))
     return [o[k] for k in KF_OUTPUT_NAMES if k in o]
 
 
@@ -227,10 +230,11 @@ def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Ten
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
         arm_xy = torch.empty(n_reps, plan.n_arms, 2, device=tables.device, dtype=torch.float32) if details else None
         obs = torch.full((n_reps, plan.n_arms), float('nan'), device=tables.device, dtype=torch.float32) if details else None
-        nat.check(nat.lib.at2_tpe_sim_f32(C.byref(plan), C.byref(cfg), C.byref(tpe), tables.data_ptr(), n_reps, rep_offset,
-                                          seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs),
-                                          arm_xy.data_ptr() if details else None, obs.data_ptr() if details else None,
-                                          _stream_ptr(tables.device)))
+        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
+            nat.check(nat.lib.at2_tpe_sim_f32(C.byref(plan), C.byref(cfg), C.byref(tpe), tables.data_ptr(), n_reps, rep_offset,
+                                              seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs),
+                                              arm_xy.data_ptr() if details else None, obs.data_ptr() if details else None,
+                                              _stream_ptr(tables.device)))
     return tensors + ([arm_xy, obs] if details else [])
 
 
