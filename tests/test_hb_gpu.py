@@ -304,3 +304,28 @@ def test_raw_smoothed_split_passes_do_not_change_outputs(monkeypatch):
         monkeypatch.delenv('AT2_HB_NO_SPLIT')
         for k in a:
             assert torch.equal(a[k], b[k]), (func, k)
+
+
+@pytest.mark.parametrize('R,eta,mom', [(81, 3, 'min'), (81, 3, 'max'), (243, 3, 'min'), (27, 3, 'max'), (64, 2, 'min')])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_heavily_tied_losses_keep_pythons_stable_order(R, eta, mom, dtype):
+    """Losses drawn from five values only: almost every comparison of a round is a tie, so the survivor lists are decided
+    by python's stable sorted() / first-min rules (hyperband_optimiser.py:46-57,99-100) - in the register rounds (rank by
+    counting + MATCH.ANY, 64-bit bitonic keys) of the float path and the shared-memory network of the float64 path alike."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_predrawn
+    spec = HyperbandSimSpec('branin', FLAT, R, eta, 0, 'uniform', mom)
+    n, A = 64, spec.n_arms
+    g = torch.Generator().manual_seed(R * 7 + eta)
+    level = torch.randint(0, 5, (n, A), generator=g).double() - 2.0          # includes -0.0 + 0.0 cases via 0
+    level[0] = 1.0                                                            # one repetition with every loss equal
+    level[1, ::2] = -0.0                                                      # signed zeros compare equal in python
+    level[1, 1::2] = 0.0
+    gamma = torch.full((n, A, R - 1), 2.5, dtype=torch.float64)
+    out = run_hyperband_predrawn(spec, level, level.clone(), torch.zeros(n, A, dtype=torch.int32), gamma, dtype=dtype)
+    ck = out['ckpt_loss']
+    assert torch.equal(ck, level.to(dtype).cuda().unsqueeze(-1).expand_as(ck))  # flat family: the curve never moves
+    surv, rb, ofe = _torch_halving(spec, ck, descending=(mom == 'max'))
+    assert torch.equal(surv, out['survivors']) and torch.equal(rb, out['round_best']) and torch.equal(ofe, out['ofe'])
+    first_round_keep = spec.plan.round_keep[0]
+    assert out['survivors'][0][:first_round_keep].tolist() == list(range(first_round_keep))   # all equal: first arms win
+    assert out['ofe_arm'][0] == 0 and out['round_best_arm'][0][0] == 0
