@@ -58,6 +58,7 @@ struct TpeWarp {
     float *ck, *ax, *ay, *ox, *oy, *ol;
     float4* comp;                    // mixture components {coef, sqrt(log2(e)/2)/sigma, mu, weight}
     unsigned short *srt0, *srt1, *age;
+    unsigned short* gidx;            // observation indices of the "good" members, best loss first (tpe_split); <= 25
     unsigned char *latest, *below;
     int n_obs;
 };
@@ -110,7 +111,7 @@ __device__ __forceinline__ void tpe_split(TpeWarp& w, int n_below, int lane) {
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ob < best || (ob == best && oi < bi)) best = ob, bi = oi;
         }
-        if (lane == 0 && bi != INT_MAX) w.below[bi] = 1;
+        if (lane == 0 && bi != INT_MAX) w.below[bi] = 1, w.gidx[s] = (unsigned short)bi;
         __syncwarp();
     }
     int cb = 0, ca = 0;
@@ -147,9 +148,11 @@ __device__ __forceinline__ float normal_cdf(float x, float mu, float sigma) {
 //                log(sum_w) and log(p_accept) shift the scores of all candidates of a model alike, so the arg-max over the
 //                candidates (all a suggestion keeps, tpe.broadcast_best) does not depend on them - and the two erf per
 //                component they cost are most of the model build; the sampler scales its uniform by sum_w instead.
+//   n_list > 0: the members are the observations w.gidx[0 .. n_list) (the good set as tpe_split lists it, at most 25): one
+//                lane per member, sorted by counting - instead of scanning all n sorted observations for the few members.
 template <bool FULL>
 __device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_below, float lo, float hi, const TpeDev& cfg, int lane,
-                                               float* sum_w_out) {
+                                               float* sum_w_out, int n_list = 0) {
     const int n = w.n_obs;
     const float* vals = d ? w.oy : w.ox;
     const unsigned short* srt = d ? w.srt1 : w.srt0;
@@ -157,18 +160,37 @@ __device__ __forceinline__ int tpe_build_model(TpeWarp& w, int d, bool want_belo
     // pass 1: members in sorted order straight into comp[].z (centre) / comp[].w (age rank inside the set); the prior goes
     // to position pp = np.searchsorted(sorted members, prior_mu) = #members < prior_mu, members >= prior_mu shift by one
     int m = 0, ge = 0;
-    for (int base = 0; base < n; base += 32) {
-        const int j = base + lane;
-        const int idx = j < n ? srt[j] : 0;
-        const float v = vals[idx];
-        const bool f = j < n && (w.below[idx] != 0) == want_below;
-        const bool g = f && !(v < prior_mu);
-        const unsigned mask = __ballot_sync(0xffffffffu, f), gmask = __ballot_sync(0xffffffffu, g);
-        if (f) {
-            float4* c = w.comp + (m + __popc(mask & lanemask_lt(lane)) + (g ? 1 : 0));
-            c->z = v, c->w = (float)w.age[idx];
+    if (n_list > 0) {
+        // rank among the listed members by (value, observation index): the order of the sorted lists, which keep equal
+        // values in insertion order (tpe_insert); ages are not needed (linear forgetting starts beyond 25 members)
+        const int id = lane < n_list ? (int)w.gidx[lane] : INT_MAX;
+        const float v = lane < n_list ? vals[id] : 0.0f;
+        int rank = 0;
+        for (int q = 0; q < n_list; ++q) {
+            const float vq = __shfl_sync(0xffffffffu, v, q);
+            const int iq = __shfl_sync(0xffffffffu, id, q);
+            rank += (vq < v || (vq == v && iq < id)) ? 1 : 0;
         }
-        m += __popc(mask), ge += __popc(gmask);
+        const bool g = lane < n_list && !(v < prior_mu);
+        if (lane < n_list) {
+            float4* c = w.comp + (rank + (g ? 1 : 0));
+            c->z = v, c->w = 0.0f;
+        }
+        m = n_list, ge = __popc(__ballot_sync(0xffffffffu, g));
+    } else {
+        for (int base = 0; base < n; base += 32) {
+            const int j = base + lane;
+            const int idx = j < n ? srt[j] : 0;
+            const float v = vals[idx];
+            const bool f = j < n && (w.below[idx] != 0) == want_below;
+            const bool g = f && !(v < prior_mu);
+            const unsigned mask = __ballot_sync(0xffffffffu, f), gmask = __ballot_sync(0xffffffffu, g);
+            if (f) {
+                float4* c = w.comp + (m + __popc(mask & lanemask_lt(lane)) + (g ? 1 : 0));
+                c->z = v, c->w = (float)w.age[idx];
+            }
+            m += __popc(mask), ge += __popc(gmask);
+        }
     }
     const int pp = m - ge, nc = m + 1;
     if (lane == 0) w.comp[pp].z = prior_mu;
@@ -241,39 +263,48 @@ __device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) 
 
 // One hyperparameter of one suggestion: candidates from the good model, argmax of log l - log g
 // (tpe.build_posterior, ap_uniform_sampler, GMM1, GMM1_lpdf, broadcast_best).
-// r0: the lane's Philox block of this suggestion; words (2 d, 2 d + 1) serve the first draw of dimension d, re-draws after
-// a rejection take a block of their own.
-__device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, unsigned long long gid,
-                                 const uint32_t* __restrict__ rk, const At2U4& r0, int lane) {
+// Candidates: tpe.GMM1 draws (component, normal) pairs until the value falls in [lo, hi).  The accepted pair has component i
+// with probability proportional to w_i a_i (a_i: mass of component i inside the bounds) and then a normal truncated to the
+// bounds - which is sampled here directly (one lane per component computes a_i, every candidate lane inverts the
+// truncated CDF), instead of looping: the wide prior component alone rejects 62 % of its draws, so with 24 lanes the
+// rejection loop ran three to four Philox blocks deep on almost every suggestion.
+// r0: the lane's Philox block of this suggestion; words (2 d, 2 d + 1) serve dimension d.
+__device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, int n_good,
+                                                 const At2U4& r0, int lane) {
     float cand = 0.5f * (lo + hi);
     float lik[2] = {1.0f, 1.0f};
 #pragma unroll 1
     for (int which = 0; which < 2; ++which) {                   // 0: good model (sample from it), 1: bad model
         float sum_w;
-        const int nc = tpe_build_model<false>(w, d, which == 0, lo, hi, cfg, lane, &sum_w);
-        if (which == 0 && lane < cfg.n_cand) {
-            // lane j draws candidate j from the good mixture truncated to [lo, hi) by rejection.  One draw takes two
-            // words: 24 + 24 bits for the Box-Muller pair, the two low bytes for the component pick.
-            uint32_t wa = d ? r0.z : r0.x, wb = d ? r0.w : r0.y;
-            for (int attempt = 0; attempt < 64; ++attempt) {
-                if (attempt > 0) {
-                    const At2U4 r = at2_philox10_rk(At2U4{(uint32_t)((d << 20) | (attempt << 5) | lane), (uint32_t)gid,
-                                                          (uint32_t)(gid >> 32), AT2_STREAM_TPE}, rk);
-                    wa = r.x, wb = r.y;
-                }
-                const float u = (float)(((wa & 0xffu) << 8) | (wb & 0xffu)) * 1.52587890625e-5f * sum_w;
+        const int nc = tpe_build_model<false>(w, d, which == 0, lo, hi, cfg, lane, &sum_w, which == 0 ? n_good : 0);
+        if (which == 0) {
+            // lanes = components (nc <= 26): truncation masses, effective weights, their running sum
+            float sigma = 1.0f, f_lo = 0.0f, mass = 0.0f, eff = 0.0f;
+            if (lane < nc) {
+                const float4 c = w.comp[lane];
+                sigma = 0.84932180028801904f * fast_rcp(c.y);
+                f_lo = normcdff((lo - c.z) * fast_rcp(sigma));
+                mass = normcdff((hi - c.z) * fast_rcp(sigma)) - f_lo;
+                eff = c.w * mass;
+            }
+            float cum = eff;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_up_sync(0xffffffffu, cum, o);
+                if (lane >= o) cum += t;
+            }
+            const float total = __shfl_sync(0xffffffffu, cum, nc - 1);
+            if (lane < nc) w.comp[nc + lane] = make_float4(cum, f_lo, mass, sigma);   // beyond the model: free space
+            __syncwarp();
+            if (lane < cfg.n_cand) {
+                const uint32_t wa = d ? r0.z : r0.x, wb = d ? r0.w : r0.y;
+                const float u = (float)(wa >> 8) * 5.9604644775390625e-8f * total;                      // [0, total)
+                const float t = fmaf((float)(wb >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);  // (0, 1)
                 int pick = 0;
-                float cum = w.comp[0].w;
-                while (pick < nc - 1 && u >= cum) cum += w.comp[++pick].w;
-                const float u1 = fmaf((float)(wa >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-                const float z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) *
-                                fast_cos((float)(int32_t)(wb & 0xffffff00u) * 1.4629180792671596e-9f);   // sqrt(-2 ln u1) cos([-pi, pi))
-                const float4 c = w.comp[pick];
-                const float v = fmaf(0.84932180028801904f * fast_rcp(c.y), z, c.z);
-                if (v >= lo && v < hi) {
-                    cand = v;
-                    break;
-                }
+                while (pick < nc - 1 && u >= w.comp[nc + pick].x) ++pick;
+                const float4 g = w.comp[nc + pick];
+                const float v = fmaf(g.w, normcdfinvf(fmaf(t, g.z, g.y)), w.comp[pick].z);
+                cand = fminf(fmaxf(v, lo), nextafterf(hi, lo));                                          // [lo, hi)
             }
         }
         __syncwarp();
@@ -356,6 +387,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
     w.srt0 = up, up += cap;
     w.srt1 = up, up += cap;
     w.age = up, up += cap;
+    w.gidx = up, up += 32;
     unsigned char* bp = reinterpret_cast<unsigned char*>(up);
     w.latest = bp, bp += cap;
     w.below = bp, bp += cap;
@@ -418,14 +450,14 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                     const int arm = first + step;
                     float xy[2] = {w.ax[arm], w.ay[arm]};
                     if (w.n_obs >= n_startup) {
-                        const float g = fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
-                        tpe_split(w, (int)g, lane);
+                        const int n_good = (int)fminf(ceilf(p.tpe.gamma * sqrtf((float)w.n_obs)), 25.0f);
+                        tpe_split(w, n_good, lane);
                         const unsigned long long gid = gid0 + arm;
                         const At2U4 r0 = at2_philox10_rk(At2U4{(uint32_t)lane, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_TPE},
                                                          p.sp.rk);
 #pragma unroll 1
                         for (int dd = 0; dd < 2; ++dd)
-                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, gid, p.sp.rk, r0, lane);
+                            xy[dd] = tpe_suggest_dim(w, dd, dd ? y_lo : x_lo, dd ? y_hi : x_hi, p.tpe, n_good, r0, lane);
                         if (lane == 0) w.ax[arm] = xy[0], w.ay[arm] = xy[1];
                     }
                     if (step + 1 < n_b) {                            // the loss TPE sees for this arm
@@ -471,7 +503,7 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
                                  float* __restrict__ model_out, float* __restrict__ lean_out, int cap, int n_prob) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const size_t warp_bytes = (size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (cap + 4) + 64;
+    const size_t warp_bytes = (size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (cap + 4) + 128;
     unsigned char* mine = smem_raw + (size_t)warp * ((warp_bytes + 15) & ~(size_t)15);
     TpeWarp w = {};
     float* fp = reinterpret_cast<float*>(mine);
@@ -483,12 +515,14 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
     w.srt0 = up, up += cap;
     w.srt1 = up, up += cap;
     w.age = up, up += cap;
+    w.gidx = up, up += 32;
     w.below = reinterpret_cast<unsigned char*>(up);
     for (int prob = blockIdx.x * nwarps + warp; prob < n_prob; prob += gridDim.x * nwarps) {
         w.n_obs = 0;
         for (int j = 0; j < n_obs; ++j)
             tpe_insert(w, obs[(size_t)prob * n_obs + j], 0.0f, loss[(size_t)prob * n_obs + j], lane);
-        tpe_split(w, (int)fminf(ceilf(cfg.gamma * sqrtf((float)n_obs)), 25.0f), lane);
+        const int n_good = (int)fminf(ceilf(cfg.gamma * sqrtf((float)n_obs)), 25.0f);
+        tpe_split(w, n_good, lane);
         float unused;
         const int nb = tpe_build_model<true>(w, 0, true, lo, hi, cfg, lane, &unused);
         if (model_out != nullptr)
@@ -520,7 +554,7 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
         }
         __syncwarp();
         if (lean_out != nullptr) {      // the models as a suggestion inside the simulation kernel builds them
-            const int nb2 = tpe_build_model<false>(w, 0, true, lo, hi, cfg, lane, &unused);
+            const int nb2 = tpe_build_model<false>(w, 0, true, lo, hi, cfg, lane, &unused, n_good);   // the list path
             for (int q = 0; q < 8; ++q) {
                 const int j = q * 32 + lane;
                 lg[q] = j < n_cand ? tpe_mixture(w, nb2, cand[(size_t)prob * n_cand + j]) : 1.0f;
@@ -630,7 +664,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     if (scratch < (size_t)p.npad * (8 + 4)) scratch = (size_t)p.npad * (8 + 4);
     scratch = (scratch + 15) & ~(size_t)15;
     p.scratch_floats = (int)(scratch / 4);
-    size_t wb = (size_t)p.cap * ((C + 5) * 4 + 3 * 2 + 2) + scratch;
+    size_t wb = (size_t)p.cap * ((C + 5) * 4 + 3 * 2 + 2) + 32 * 2 + scratch;
     p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
     const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
@@ -674,7 +708,7 @@ extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_
     AT2_REQUIRE(n_obs >= 1 && n_obs <= 4096 && n_problems >= 1 && n_candidates >= 1 && n_candidates <= 256 && high > low,
                 "at2_tpe_score_f32: bad sizes (1 <= n_obs <= 4096, 1 <= n_candidates <= 256, low < high)");
     const int cap = (n_obs + 31) & ~31;
-    const size_t warp_bytes = (((size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (size_t)(cap + 4) + 64) + 15) & ~(size_t)15;
+    const size_t warp_bytes = (((size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (size_t)(cap + 4) + 128) + 15) & ~(size_t)15;
     const int nwarps = 4;
     const size_t smem = warp_bytes * nwarps;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(tpe_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
