@@ -283,8 +283,9 @@ __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, fl
             if (lane < nc) {
                 const float4 c = w.comp[lane];
                 sigma = 0.84932180028801904f * fast_rcp(c.y);
-                f_lo = normcdff((lo - c.z) * fast_rcp(sigma));
-                mass = normcdff((hi - c.z) * fast_rcp(sigma)) - f_lo;
+                const float zs = 0.70710678118654752f * fast_rcp(sigma);              // Phi(z) = (1 + erf(z / sqrt 2)) / 2
+                f_lo = fmaf(0.5f, erff((lo - c.z) * zs), 0.5f);
+                mass = fmaf(0.5f, erff((hi - c.z) * zs), 0.5f) - f_lo;
                 eff = c.w * mass;
             }
             float cum = eff;
