@@ -380,6 +380,11 @@ extern "C" int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain
     const int nwarps = 4;
     p.npad = halving_npad(plan);
     p.G = 1;
+    {
+        const char* env_g = getenv("AT2_KF_REPS_PER_TILE");      // development aid
+        if (env_g != nullptr && atoi(env_g) > 0) p.G = atoi(env_g);
+        if ((long long)p.G > n_reps) p.G = (int)n_reps;
+    }
     p.stride = (p.G * plan->n_arms + 31) & ~31;
     p.warp_bytes = (int)(((size_t)plan->n_ckpts * p.stride * sizeof(double) + halving_scratch_bytes<double>(p.npad) + 15) & ~(size_t)15);
     p.n_tiles = (n_reps + p.G - 1) / p.G;
