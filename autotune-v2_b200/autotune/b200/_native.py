@@ -97,7 +97,7 @@ def _load():
         'at2_tpe_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), C.POINTER(TpeConfig), vp, i64, i64, u64,
                                       C.POINTER(HbOutputs), vp, vp, vp]),
         'at2_tpe_score_f32': (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_double, C.POINTER(TpeConfig), vp, i32, vp, vp, vp,
-                                        vp]),
+                                        vp, vp]),
         'at2_nn_workspace_bytes': (i64, [i64, i32, i32]),
         'at2_nn_lookup_f64': (C.c_int, [C.POINTER(DomainDesc), vp, i32, vp, i64, vp, vp, vp, i32, vp, vp, vp, i64, vp]),
         'at2_hb_knownfn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(DomainDesc), vp, i32, vp, i32, i32, i64, i64, u64,

@@ -242,8 +242,9 @@ def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Ten
 def tpe_score(obs: torch.Tensor, loss: torch.Tensor, low: float, high: float, tpe_bytes: torch.Tensor,
               candidates: torch.Tensor) -> List[torch.Tensor]:
     """log l(x) - log g(x) of the adaptive Parzen models built from (obs, loss) [n_problems, n_obs] for the given
-    candidates [n_problems, n_cand] (at2_tpe_score_f32).  Returns [scores, models[n_problems, 2, cap+1, 3], lean_scores]
-    (lean_scores: the candidates scored as a suggestion inside at2::tpe_sim scores them, see include/at2.h)."""
+    candidates [n_problems, n_cand] (at2_tpe_score_f32).  Returns [scores, models[n_problems, 2, cap+1, 3], lean_scores,
+    samples[n_problems, 32]] (lean_scores: the candidates scored as a suggestion inside at2::tpe_sim scores them; samples:
+    draws from the truncated good model as a suggestion draws its candidates - see include/at2.h)."""
     for name, t in (('obs', obs), ('loss', loss), ('candidates', candidates)):
         _require_cuda(t, name)
         if t.dtype != torch.float32 or t.dim() != 2 or not t.is_contiguous():
@@ -255,10 +256,11 @@ def tpe_score(obs: torch.Tensor, loss: torch.Tensor, low: float, high: float, tp
         scores = torch.empty_like(candidates)
         models = torch.zeros(n_prob, 2, cap + 1, 3, device=obs.device, dtype=torch.float32)
         lean = torch.empty_like(candidates)
+        samples = torch.empty(n_prob, 32, device=obs.device, dtype=torch.float32)
         nat.check(nat.lib.at2_tpe_score_f32(obs.data_ptr(), loss.data_ptr(), n_obs, n_prob, low, high, C.byref(tpe),
                                             candidates.data_ptr(), candidates.shape[1], scores.data_ptr(),
-                                            models.data_ptr(), lean.data_ptr(), _stream_ptr(obs.device)))
-    return [scores, models, lean]
+                                            models.data_ptr(), lean.data_ptr(), samples.data_ptr(), _stream_ptr(obs.device)))
+    return [scores, models, lean, samples]
 
 
 @torch.library.custom_op('at2::sim_trajectories', mutates_args=(), device_types='cuda')

@@ -261,13 +261,49 @@ __device__ __forceinline__ float tpe_mixture(const TpeWarp& w, int nc, float x) 
     return s;
 }
 
+// Candidates from the mixture in comp[0 .. nc) (layout of tpe_build_model<false>) truncated to [lo, hi): lane j < n_cand
+// returns candidate j, drawn from the two random words (wa, wb) it is given; the other lanes return the centre.
+// tpe.GMM1 draws (component, normal) pairs until the value falls inside the bounds.  The accepted pair has component i with
+// probability proportional to w_i a_i (a_i: mass of component i inside the bounds) and then a normal truncated to the
+// bounds - which is sampled here directly: one lane per component computes a_i, every candidate lane picks a component
+// and inverts the truncated CDF.  All 32 lanes must call it; nc <= 32; uses comp[nc .. 2 nc) as scratch.
+__device__ __forceinline__ float tpe_sample_truncated(TpeWarp& w, int nc, float lo, float hi, int n_cand, uint32_t wa, uint32_t wb,
+                                                      int lane) {
+    float sigma = 1.0f, f_lo = 0.0f, mass = 0.0f, eff = 0.0f;
+    if (lane < nc) {
+        const float4 c = w.comp[lane];
+        sigma = 0.84932180028801904f * fast_rcp(c.y);
+        const float zs = 0.70710678118654752f * fast_rcp(sigma);              // Phi(z) = (1 + erf(z / sqrt 2)) / 2
+        f_lo = fmaf(0.5f, erff((lo - c.z) * zs), 0.5f);
+        mass = fmaf(0.5f, erff((hi - c.z) * zs), 0.5f) - f_lo;
+        eff = c.w * mass;
+    }
+    float cum = eff;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, cum, o);
+        if (lane >= o) cum += t;
+    }
+    const float total = __shfl_sync(0xffffffffu, cum, nc - 1);
+    if (lane < nc) w.comp[nc + lane] = make_float4(cum, f_lo, mass, sigma);   // beyond the model: free space
+    __syncwarp();
+    float cand = 0.5f * (lo + hi);
+    if (lane < n_cand) {
+        const float u = (float)(wa >> 8) * 5.9604644775390625e-8f * total;                      // [0, total)
+        const float t = fmaf((float)(wb >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);  // (0, 1)
+        int pick = 0;
+        while (pick < nc - 1 && u >= w.comp[nc + pick].x) ++pick;
+        const float4 g = w.comp[nc + pick];
+        const float v = fmaf(g.w, normcdfinvf(fmaf(t, g.z, g.y)), w.comp[pick].z);
+        cand = fminf(fmaxf(v, lo), nextafterf(hi, lo));                                          // [lo, hi)
+    }
+    return cand;
+}
+
 // One hyperparameter of one suggestion: candidates from the good model, argmax of log l - log g
 // (tpe.build_posterior, ap_uniform_sampler, GMM1, GMM1_lpdf, broadcast_best).
-// Candidates: tpe.GMM1 draws (component, normal) pairs until the value falls in [lo, hi).  The accepted pair has component i
-// with probability proportional to w_i a_i (a_i: mass of component i inside the bounds) and then a normal truncated to the
-// bounds - which is sampled here directly (one lane per component computes a_i, every candidate lane inverts the
-// truncated CDF), instead of looping: the wide prior component alone rejects 62 % of its draws, so with 24 lanes the
-// rejection loop ran three to four Philox blocks deep on almost every suggestion.
+// Candidates come from tpe_sample_truncated instead of a rejection loop: the wide prior component alone rejects 62 % of
+// its draws, so with 24 lanes the loop ran three to four Philox blocks deep on almost every suggestion.
 // r0: the lane's Philox block of this suggestion; words (2 d, 2 d + 1) serve dimension d.
 __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, float hi, const TpeDev& cfg, int n_good,
                                                  const At2U4& r0, int lane) {
@@ -277,37 +313,7 @@ __device__ __forceinline__ float tpe_suggest_dim(TpeWarp& w, int d, float lo, fl
     for (int which = 0; which < 2; ++which) {                   // 0: good model (sample from it), 1: bad model
         float sum_w;
         const int nc = tpe_build_model<false>(w, d, which == 0, lo, hi, cfg, lane, &sum_w, which == 0 ? n_good : 0);
-        if (which == 0) {
-            // lanes = components (nc <= 26): truncation masses, effective weights, their running sum
-            float sigma = 1.0f, f_lo = 0.0f, mass = 0.0f, eff = 0.0f;
-            if (lane < nc) {
-                const float4 c = w.comp[lane];
-                sigma = 0.84932180028801904f * fast_rcp(c.y);
-                const float zs = 0.70710678118654752f * fast_rcp(sigma);              // Phi(z) = (1 + erf(z / sqrt 2)) / 2
-                f_lo = fmaf(0.5f, erff((lo - c.z) * zs), 0.5f);
-                mass = fmaf(0.5f, erff((hi - c.z) * zs), 0.5f) - f_lo;
-                eff = c.w * mass;
-            }
-            float cum = eff;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, cum, o);
-                if (lane >= o) cum += t;
-            }
-            const float total = __shfl_sync(0xffffffffu, cum, nc - 1);
-            if (lane < nc) w.comp[nc + lane] = make_float4(cum, f_lo, mass, sigma);   // beyond the model: free space
-            __syncwarp();
-            if (lane < cfg.n_cand) {
-                const uint32_t wa = d ? r0.z : r0.x, wb = d ? r0.w : r0.y;
-                const float u = (float)(wa >> 8) * 5.9604644775390625e-8f * total;                      // [0, total)
-                const float t = fmaf((float)(wb >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);  // (0, 1)
-                int pick = 0;
-                while (pick < nc - 1 && u >= w.comp[nc + pick].x) ++pick;
-                const float4 g = w.comp[nc + pick];
-                const float v = fmaf(g.w, normcdfinvf(fmaf(t, g.z, g.y)), w.comp[pick].z);
-                cand = fminf(fmaxf(v, lo), nextafterf(hi, lo));                                          // [lo, hi)
-            }
-        }
+        if (which == 0) cand = tpe_sample_truncated(w, nc, lo, hi, cfg.n_cand, d ? r0.z : r0.x, d ? r0.w : r0.y, lane);
         __syncwarp();
         lik[which] = tpe_mixture(w, nc, cand);
         __syncwarp();
@@ -501,7 +507,8 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
 // stand-alone scoring entry (tests): build both models from given observations, score given candidates
 __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __restrict__ loss, int n_obs, float lo, float hi,
                                  TpeDev cfg, const float* __restrict__ cand, int n_cand, float* __restrict__ score_out,
-                                 float* __restrict__ model_out, float* __restrict__ lean_out, int cap, int n_prob) {
+                                 float* __restrict__ model_out, float* __restrict__ lean_out, float* __restrict__ sample_out,
+                                 int cap, int n_prob) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const size_t warp_bytes = (size_t)cap * (3 * 4 + 3 * 2 + 1) + 16 * (cap + 4) + 128;
@@ -556,6 +563,11 @@ __global__ void tpe_score_kernel(const float* __restrict__ obs, const float* __r
         __syncwarp();
         if (lean_out != nullptr) {      // the models as a suggestion inside the simulation kernel builds them
             const int nb2 = tpe_build_model<false>(w, 0, true, lo, hi, cfg, lane, &unused, n_good);   // the list path
+            if (sample_out != nullptr) {   // 32 draws from the good model, the way a suggestion draws its candidates
+                const At2U4 r = at2_philox10(At2U4{(uint32_t)lane, (uint32_t)prob, 0u, AT2_STREAM_TPE}, 0xC0FFEEu, 0x5EEDu);
+                sample_out[(size_t)prob * 32 + lane] = tpe_sample_truncated(w, nb2, lo, hi, 32, r.x, r.y, lane);
+                __syncwarp();
+            }
             for (int q = 0; q < 8; ++q) {
                 const int j = q * 32 + lane;
                 lg[q] = j < n_cand ? tpe_mixture(w, nb2, cand[(size_t)prob * n_cand + j]) : 1.0f;
@@ -700,7 +712,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
 
 extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low,
                                  double high, const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates,
-                                 float* d_scores, float* d_models, float* d_lean_scores, void* stream) {
+                                 float* d_scores, float* d_models, float* d_lean_scores, float* d_samples, void* stream) {
     at2_reset_launch_count();
     TpeDev cfg;
     const int rc = fill_tpe(tpe, &cfg);
@@ -716,7 +728,7 @@ extern "C" int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_
     const int grid = (n_problems + nwarps - 1) / nwarps;
     tpe_score_kernel<<<grid, nwarps * 32, smem, (cudaStream_t)stream>>>(d_obs, d_loss, n_obs, (float)low, (float)high, cfg,
                                                                          d_candidates, n_candidates, d_scores, d_models,
-                                                                         d_lean_scores, cap, n_problems);
+                                                                         d_lean_scores, d_samples, cap, n_problems);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
     return AT2_OK;

@@ -204,10 +204,12 @@ int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_t
  * float[n_problems][2][cap+1][3] = (weight, mu, sigma) of the good then the bad model, cap = n_obs rounded up to 32.
  * d_lean_scores (optional): float[n_problems][n_candidates], the same candidates scored the way at2_tpe_sim_f32 scores them
  * inside a suggestion - without the weight normalisation and the truncation mass p_accept, which shift all candidates of a
- * problem alike: d_lean_scores - d_scores is constant per problem and the arg-max is the same. */
+ * problem alike: d_lean_scores - d_scores is constant per problem and the arg-max is the same.
+ * d_samples (optional, needs d_lean_scores): float[n_problems][32], 32 draws per problem from the good model truncated to
+ * [low, high), made the way a suggestion draws its candidates (tpe.GMM1's distribution, sampled without its rejection loop). */
 int at2_tpe_score_f32(const float* d_obs, const float* d_loss, int32_t n_obs, int32_t n_problems, double low, double high,
                       const at2_tpe_config* tpe, const float* d_candidates, int32_t n_candidates, float* d_scores,
-                      float* d_models, float* d_lean_scores, void* stream);
+                      float* d_models, float* d_lean_scores, float* d_samples, void* stream);
 
 /* ---- (d): closest-known-loss-function approximation ------------------------------------------------------------------ */
 

@@ -34,8 +34,8 @@ def test_parzen_models_and_scores_match_oracle(n_obs):
     loss = rng.normal(size=(n_prob, n_obs)).astype(np.float32)
     loss[4, :] = 1.0                                    # all losses tie: the oldest trials are "good"
     cand = rng.uniform(lo, hi, (n_prob, n_cand)).astype(np.float32)
-    scores, models, lean = torch.ops.at2.tpe_score(torch.from_numpy(obs).cuda(), torch.from_numpy(loss).cuda(), lo, hi,
-                                                   _tpe_bytes(), torch.from_numpy(cand).cuda())
+    scores, models, lean, _ = torch.ops.at2.tpe_score(torch.from_numpy(obs).cuda(), torch.from_numpy(loss).cuda(), lo, hi,
+                                                      _tpe_bytes(), torch.from_numpy(cand).cuda())
     scores, models, lean = scores.cpu().numpy(), models.cpu().numpy(), lean.cpu().numpy()
     # inside a suggestion the simulation kernel skips the weight normalisation and the truncation mass: a per-problem
     # constant shift of the scores, the same arg-max
@@ -185,3 +185,32 @@ def test_tpe_observed_losses_equal_the_trajectory_readouts(func, fams, R, noise)
         assert torch.allclose(o[seen], want[seen], rtol=2e-6, atol=2e-6 * scale + 1e-5)
         n_checked += int(seen.sum())
     assert n_checked >= 300 * 26
+
+
+@pytest.mark.parametrize('case', ['interior', 'edges', 'few'])
+def test_truncated_mixture_sampler_matches_hyperopts_rejection_sampler(case):
+    """A suggestion's candidates: tpe.GMM1 draws (component, normal) pairs until the value is inside [low, high); the device
+    samples the same distribution directly (component with probability ~ weight x mass inside the bounds, then the inverse
+    CDF of the truncated normal).  Two-sample KS of 32 x 2000 device draws against the oracle's rejection sampler, on good
+    models whose components sit in the interior, on the bounds, and on a single observation."""
+    from scipy.stats import ks_2samp
+    lo, hi = -5.12, 5.12
+    n_obs = {'interior': 40, 'edges': 40, 'few': 10}[case]
+    rng = np.random.default_rng(7)
+    obs1 = rng.uniform(lo, hi, n_obs).astype(np.float32)
+    loss1 = rng.normal(size=n_obs).astype(np.float32)
+    order = np.argsort(loss1, kind='stable')
+    if case == 'edges':                                  # the good members hug the bounds: half of their mass is outside
+        obs1[order[0]], obs1[order[1]] = np.float32(lo + 1e-3), np.float32(hi - 1e-3)
+    n_prob = 2000
+    obs = np.tile(obs1, (n_prob, 1))
+    loss = np.tile(loss1, (n_prob, 1))
+    cand = np.zeros((n_prob, 8), np.float32)
+    samples = torch.ops.at2.tpe_score(torch.from_numpy(obs).cuda(), torch.from_numpy(loss).cuda(), lo, hi, _tpe_bytes(),
+                                      torch.from_numpy(cand).cuda())[3].cpu().numpy().astype(np.float64).ravel()
+    assert samples.min() >= lo and samples.max() < hi and len(np.unique(samples)) > 0.99 * samples.size
+    below, _ = otpe.split_trials(obs1.astype(np.float64), loss1.astype(np.float64))
+    w, mu, sg = otpe.adaptive_parzen_normal(below, 1.0, 0.5 * (hi + lo), hi - lo)
+    want = otpe.gmm1_sample(w, mu, sg, lo, hi, 20000, np.random.RandomState(11))
+    res = ks_2samp(samples, want)
+    assert res.pvalue > 0.01, (case, res)
