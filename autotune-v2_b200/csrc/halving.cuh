@@ -106,7 +106,7 @@ __device__ __forceinline__ K warp_bitonic_shfl(K mine, int lane, int n) {
 // by position, python's stable sorted(): MATCH.ANY finds the lanes holding the same key, the ones below add to the rank.
 __device__ __forceinline__ int warp_rank_by_counting(uint32_t ord, int lane, int n) {
     int rank = 0;
-#pragma unroll 1
+#pragma unroll 4
     for (int j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, ord, j) < ord ? 1 : 0;
     return rank + __popc(__match_any_sync(0xffffffffu, ord) & ((1u << lane) - 1u));
 }

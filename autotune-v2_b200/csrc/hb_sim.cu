@@ -65,13 +65,14 @@ struct Params {
     T* ckpt_loss;
 };
 
-// Shared memory (a 3-repetition tile per warp) holds three 8-warp CTAs per SM at the headline shapes, so the register cap
-// is 80, not 64: measured -4 % on the configurations with smoothed families, no change on the flat one.
-#ifndef AT2_HB_MIN_BLOCKS
-#define AT2_HB_MIN_BLOCKS 3
+// Register cap 80 (65536 / 768): shared memory (a 3-repetition tile per warp) holds about 24 warps per SM anyway - three
+// 8-warp CTAs when the constant tables are small, ONE 24-warp CTA when they are large (six families: 18 KB per CTA), see
+// choose_launch.  Measured -4 % against a 64-register cap on the configurations with smoothed families.
+#ifndef AT2_HB_MAX_WARPS
+#define AT2_HB_MAX_WARPS 24
 #endif
 template <typename T, int MODE, bool HAS_SMOOTH, int CK, bool GTAB>
-__global__ void __launch_bounds__(256, AT2_HB_MIN_BLOCKS) hb_sim_kernel(const __grid_constant__ Params<T> p) {
+__global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const __grid_constant__ Params<T> p) {
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F;
@@ -313,11 +314,25 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     // plans whose tables do not fit beside one team's state (R ~ 1000 with six families) read them from global memory
     out->gtab = (fixed + team_bytes > (size_t)max_smem || getenv("AT2_FORCE_GTAB") != nullptr) ? 1 : 0;   // env: tests
     if (out->gtab) fixed = (AT2_MAX_CKPTS + 4) * sizeof(int);
-    int warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", 8);
-    if (warps_per_cta < best_tw) warps_per_cta = best_tw;
-    if (warps_per_cta > 8) warps_per_cta = 8;
-    int n_teams = warps_per_cta / best_tw;
+    // Warps per CTA: every CTA carries its own copy of the constant tables (`fixed`), so with large tables fewer, bigger
+    // CTAs keep more warps resident.  Take the size with the most resident warps per SM (shared memory, 80 registers per
+    // thread, 2048 threads), the smaller one on ties (more CTAs balance the tail better).
     const long long n_tiles = (n_reps + best_g - 1) / best_g;
+    int warps_per_cta = 8 < best_tw ? best_tw : 8, best_resident = -1;
+    for (int wpc = warps_per_cta; wpc <= AT2_HB_MAX_WARPS; wpc += 4) {
+        if (wpc % best_tw != 0 || (best_tw > 1 && wpc / best_tw > 15)) continue;     // named barriers 1..15 for the teams
+        const size_t need = fixed + (size_t)(wpc / best_tw) * team_bytes;
+        if (need > (size_t)max_smem) break;
+        int ctas = (int)((size_t)(227 * 1024) / (need + 1024));
+        const int by_regs = 65536 / (80 * 32 * wpc), by_threads = 2048 / (wpc * 32);
+        ctas = ctas < by_regs ? ctas : by_regs;
+        ctas = ctas < by_threads ? ctas : by_threads;
+        if (ctas * wpc > best_resident) best_resident = ctas * wpc, warps_per_cta = wpc;
+    }
+    warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", warps_per_cta);
+    if (warps_per_cta < best_tw) warps_per_cta = best_tw;
+    if (warps_per_cta > AT2_HB_MAX_WARPS) warps_per_cta = AT2_HB_MAX_WARPS;
+    int n_teams = warps_per_cta / best_tw;
     while (n_teams > 1 && (fixed + n_teams * team_bytes > (size_t)max_smem || (long long)(n_teams - 1) * sms >= n_tiles)) --n_teams;
     const size_t smem = fixed + n_teams * team_bytes;
     if (smem > (size_t)max_smem) {
