@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(PKG_ROOT, 'lib', 'libat2_b200.so')
 
 MAX_BRACKETS, MAX_ROUNDS, MAX_CKPTS, MAX_FAMILIES = 16, 64, 16, 8
 MAX_PARAMS = 16
+MAX_PEERS = 16
 FUNC_IDS = {'egg': 0, 'branin': 1, 'camel': 2, 'wave': 3, 'rastrigin': 4,
             'egg4': 5}   # egg4: 4-D extension (include/at2.h AT2_FUNC_EGG4), Hyperband entry points only
 SCHED_UNIFORM, SCHED_ROUND_ROBIN = 0, 1
@@ -84,6 +85,8 @@ def _load():
         'at2_hb_tables_build': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), i32, vp]),
         'at2_hb_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
                                      C.POINTER(HbOutputs), vp]),
+        'at2_hb_sim_gather_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64, C.POINTER(HbOutputs),
+                                            C.POINTER(C.c_void_p), i32, i64, vp]),
         'at2_hb_sim_early_stop_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
                                                 C.POINTER(HbOutputs), vp]),
         'at2_hb_sim_predrawn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, vp,

@@ -43,6 +43,57 @@ def gather_slices(local, n_total, group=None):
     return torch.cat(parts)
 
 
+class FusedGather:
+    """The all-gather of the OFE vector fused into the simulation kernel (at2_hb_sim_gather_f32): every rank's kernel stores
+    its OFEs straight into all ranks' buffers over NVLink / NVSwitch while it is still simulating - one store per repetition
+    to the NVSwitch multicast address when the fabric offers one, else one store per peer - and a barrier across the ranks
+    replaces the NCCL collective.  Buffers are torch symmetric memory; two of them alternate so that one barrier per job is
+    enough (a rank can run at most one job ahead of the slowest reader).
+
+    Collective constructor: every rank of `group` must call it.  `FusedGather.create` returns None (on every rank alike)
+    when symmetric memory cannot be set up, and callers fall back to `gather_slices` (NCCL)."""
+
+    def __init__(self, n_total, device, group=None, use_multicast=True):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.n_total, self.device = int(n_total), torch.device(device)
+        self.bufs, self.handles, self.targets = [], [], []
+        for _ in range(2):
+            buf = symm_mem.empty(self.n_total, dtype=torch.float32, device=self.device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if use_multicast else 0
+            self.bufs.append(buf)
+            self.handles.append(hdl)
+            self.targets.append([mc] if mc else [int(p) for p in hdl.buffer_ptrs])
+        self.multicast = len(self.targets[0]) == 1 and self.world > 1
+        self.turn = 0
+
+    @classmethod
+    def create(cls, n_total, device, group=None, use_multicast=True):
+        """None unless every rank of the group managed to set the buffers up."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
+            return None
+        try:
+            fg, ok = cls(n_total, device, group, use_multicast), 1
+        except Exception:  # noqa: BLE001  (driver / fabric without peer mapping: use NCCL)
+            fg, ok = None, 0
+        flag = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return fg if int(flag.item()) == 1 else None
+
+    def run(self, spec, seed):
+        """This rank's share of the job's repetitions; returns the gathered [n_total] OFE vector (a view of a symmetric
+        buffer that stays valid until the job after the next one)."""
+        lo, hi = shard_range(self.n_total, self.rank, self.world)
+        buf, hdl, targets = self.bufs[self.turn], self.handles[self.turn], self.targets[self.turn]
+        self.turn ^= 1
+        torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo, lo,
+                                    int(seed), buf, targets, lo)
+        hdl.barrier(channel=0)          # on the current stream: every rank's stores are in every buffer after it
+        return buf
+
+
 def density(ofes, start, end, bandwidth, grid_points=1000, kernel='epanechnikov'):
     """EPDF of a float32 CUDA vector on linspace(start, end, grid_points)."""
     return torch.ops.at2.kde(ofes.contiguous(), float(start), float(end), int(grid_points), float(bandwidth),
@@ -60,16 +111,24 @@ def summary_stats(ofes):
 
 
 def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=1000, kernel='epanechnikov',
-                 group=None, device=None, runner=None):
+                 group=None, device=None, runner=None, fused=None):
     """The whole job: this rank's share of `n_reps` Hyperband repetitions -> all-gather -> KDE.
 
     Returns {'ofes': [n_reps] float32 (all ranks' OFEs, in repetition order), 'density': [grid_points], 'grid': ...}.
     `runner(spec, n, seed, rep_offset, device)` defaults to the fused Hyperband kernel; other optimisers plug in here.
+    `fused`: a FusedGather for (n_reps, device, group) - the kernel then scatters its OFEs into every rank's buffer itself
+    and no NCCL collective runs (plain Hyperband only); the gathered vector is bit-identical either way.
     """
     from .engine import _cuda_device, run_hyperband_repetitions
     device = _cuda_device(device)
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    if fused is not None and runner is None:
+        if fused.n_total != int(n_reps):
+            raise ValueError(f'FusedGather was built for {fused.n_total} repetitions, not {n_reps}')
+        ofes = fused.run(spec, seed)
+        return {'ofes': ofes, 'density': density(ofes, start, end, bandwidth, grid_points, kernel),
+                'grid': np.linspace(start, end, grid_points)}
     lo, hi = shard_range(n_reps, rank, world)
     if runner is None:
         def runner(spec_, n, seed_, off, dev):

@@ -341,11 +341,12 @@ __device__ __forceinline__ void halving_finish(const HalvingOut<T>& out, const H
 template <typename T>
 __device__ int warp_halving(const at2_plan& plan, const T* ck, int stride, typename KeyOf<T>::type* keys,
                             unsigned short* ids_a, unsigned short* ids_b, bool desc, int lane, long long rep_g,
-                            const HalvingOut<T>& out) {
+                            const HalvingOut<T>& out, T* ofe_value = nullptr) {
     HalvingState<T> st{(T)0, -1, 0};
     for (int b = 0; b < plan.n_brackets; ++b)
         warp_halving_bracket<T>(plan, b, ck, stride, keys, ids_a, ids_b, desc, lane, rep_g, out, st);
     halving_finish<T>(out, st, lane, rep_g);
+    if (ofe_value != nullptr) *ofe_value = st.best;
     return st.best_arm;
 }
 

@@ -55,6 +55,11 @@ struct Params {
     const int* family;
     const T* gamma;
     const T* xy;
+    // fused all-gather of the OFEs: repetition i of this call also lands in element gather_base + i of every gather[r]
+    // (the peers' symmetric buffers, written over NVLink), or of the one NVSwitch multicast address that fans out to all
+    T* gather[AT2_MAX_PEERS];
+    int n_gather;
+    long long gather_base;
     // outputs
     T* ofe;
     int* ofe_arm;
@@ -233,8 +238,10 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
         for (int rep_l = wteam; rep_l < g_eff; rep_l += p.team_warps) {
             const long long rep_g = rep0 + rep_l;
             HalvingOut<T> ho{p.ofe, p.ofe_arm, p.round_best, p.round_best_arm, p.survivors};
+            T ofe_value;
             const int best_arm = warp_halving<T>(p.plan, s_ck + rep_l * A, p.stride, keys, ids_a, ids_b, desc, lane,
-                                                 rep_g, ho);
+                                                 rep_g, ho, &ofe_value);
+            if (lane < p.n_gather) p.gather[lane][p.gather_base + rep_g] = ofe_value;   // one peer (or the multicast) per lane
             if (lane == 0 && p.best_xy != nullptr) {
                 if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm;
@@ -441,6 +448,28 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
     const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
+    p.rep_offset = rep_offset;
+    p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
+    at2_round_keys(seed, p.sp.rk);
+    return launch_dispatch<float, MODE_PHILOX>(p, lc, at2_cfg_has_smooth(cfg), (cudaStream_t)stream);
+}
+
+extern "C" int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                                     int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* const* d_gather,
+                                     int32_t n_gather, int64_t gather_base, void* stream) {
+    at2_reset_launch_count();
+    Params<float> p = {};
+    LaunchCfg<float> lc;
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
+    if (rc != AT2_OK) return rc;
+    AT2_REQUIRE(rep_offset >= 0 && gather_base >= 0, "at2_hb_sim_gather_f32: rep_offset and gather_base must be >= 0");
+    AT2_REQUIRE(d_gather != nullptr && n_gather >= 1 && n_gather <= AT2_MAX_PEERS,
+                "at2_hb_sim_gather_f32: need 1..%d gather buffers", AT2_MAX_PEERS);
+    for (int r = 0; r < n_gather; ++r) {
+        AT2_REQUIRE(d_gather[r] != nullptr, "at2_hb_sim_gather_f32: gather buffer %d is NULL", r);
+        p.gather[r] = d_gather[r];
+    }
+    p.n_gather = n_gather, p.gather_base = gather_base;
     p.rep_offset = rep_offset;
     p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
     at2_round_keys(seed, p.sp.rk);

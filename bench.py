@@ -39,6 +39,7 @@ def parse_args():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--reps-per-gpu', type=int, default=REPS_PER_GPU)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--nccl-gather', action='store_true', help='N > 1: NCCL all-gather instead of the fused gather')
     return ap.parse_args()
 
 
@@ -185,7 +186,7 @@ def main():
     import torch.distributed as dist
     from autotune.b200 import _native as nat
     from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
-    from autotune.b200.epdf import density, gather_slices, run_epdf_ofe
+    from autotune.b200.epdf import FusedGather, density, gather_slices, run_epdf_ofe
 
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
@@ -220,13 +221,26 @@ def main():
     fma_peak_tflops = 2.0 * 16 * iters * blocks * threads / (best_ms * 1e-3) / 1e12
     fma_variants = {str(k): 2.0 * 16 * iters * blocks * threads / (v * 1e-3) / 1e12 for k, v in by_variant.items()}
 
+    # N > 1: the all-gather of the OFEs is fused into the simulation kernel (peer / NVSwitch-multicast stores + one barrier);
+    # NCCL all-gather if symmetric memory cannot be set up (decided collectively) or with --nccl-gather
+    fused = None if (world == 1 or args.nccl_gather) else FusedGather.create(n_total, dev)
+    gather_kind = 'none (one GPU)' if world == 1 else (
+        'NCCL all-gather' if fused is None else
+        'fused into the simulation kernel (' + ('NVSwitch multicast stores' if fused.multicast else 'peer stores over NVLink')
+        + ' + one barrier, torch symmetric memory)')
+
     def step(seed, sim_events=None):
         if sim_events is not None:
             sim_events[0].record(stream)
-        ofe = run_hyperband_repetitions(spec, n_local, seed=seed, rep_offset=rank * n_local, device=dev)['ofe']
-        if sim_events is not None:
-            sim_events[1].record(stream)
-        full = gather_slices(ofe, n_total) if world > 1 else ofe
+        if fused is not None:
+            full = fused.run(spec, seed)         # this rank's 1e5 repetitions, every rank's OFEs
+            if sim_events is not None:
+                sim_events[1].record(stream)     # (includes the barrier across the ranks)
+        else:
+            ofe = run_hyperband_repetitions(spec, n_local, seed=seed, rep_offset=rank * n_local, device=dev)['ofe']
+            if sim_events is not None:
+                sim_events[1].record(stream)
+            full = gather_slices(ofe, n_total) if world > 1 else ofe
         return full, density(full, KDE_START, KDE_END, KDE_H, KDE_G)
 
     # bring the SM clock up before the W warm-up steps: a cold B200 needs a few hundred ms of load to leave its idle
@@ -270,7 +284,7 @@ def main():
         nat.check(nat.lib.at2_hb_tables_build(C.byref(spec.plan), C.byref(spec.cfg), 0, host_tab.data_ptr()))
         spec._tables[(str(dev), torch.float32)] = host_tab.to(dev, non_blocking=True)
         res = run_epdf_ofe(spec, n_total, seed, start=KDE_START, end=KDE_END, bandwidth=KDE_H, grid_points=KDE_G,
-                           device=dev)
+                           device=dev, fused=fused)
         host_ofe.copy_(res['ofes'], non_blocking=True)
         host_den.copy_(res['density'], non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -375,7 +389,7 @@ def main():
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'reps_per_gpu_per_step': n_local, 'arms_per_rep': ARMS,
                        'arm_epochs_per_rep': ARM_EPOCHS, 'kde': 'epanechnikov h=0.1 on linspace(0.37,1.5,1000)',
-                       'parallelism': f'repetition-sharded x{world}, one all-gather of OFEs',
+                       'parallelism': f'repetition-sharded x{world}; OFE all-gather: {gather_kind}',
                        'l2': 'no HBM inputs (Philox RNG in-kernel); per-step outputs 1.2 MB; seed changes every step'},
             'arm_epochs_per_s': value * ARM_EPOCHS,
             'clocks': sampler.summary(t0, t1),

@@ -36,6 +36,7 @@ extern "C" {
 #define AT2_MAX_ROUNDS 64
 #define AT2_MAX_CKPTS 16
 #define AT2_MAX_FAMILIES 8
+#define AT2_MAX_PEERS 16     /* gather buffers of at2_hb_sim_gather_f32 */
 
 /* test functions, reference autotune/benchmarks/opt_function_problem.py:141-147 */
 #define AT2_FUNC_EGG 0
@@ -140,6 +141,17 @@ typedef struct at2_hb_outputs {
  * Repetition ids rep_offset .. rep_offset+n_reps-1 key the RNG. */
 int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                    int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
+
+/* at2_hb_sim_f32 fused with the all-gather of the OFE vector (the one collective of the path: the OFEs of all ranks feed
+ * the KDE, experiments/run_simulation.py:156-157 + simulation_evaluation/plot_results.py:11-17).  The OFE of repetition i of
+ * this call is additionally stored to element gather_base + i of each of the n_gather device buffers in d_gather (a HOST
+ * array of device pointers): the peers' symmetric-memory buffers mapped into this process (stores travel over
+ * NVLink / NVSwitch while the kernel is still simulating), or a single NVSwitch multicast address that fans one store out
+ * to every GPU.  The caller orders the stores against the readers (a barrier across the ranks after the launch).  Every
+ * other argument and output as in at2_hb_sim_f32; out->d_ofe may be NULL. */
+int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                          int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* const* d_gather,
+                          int32_t n_gather, int64_t gather_base, void* stream);
 
 /* Same repetitions with early stopping: an arm is only simulated as far as the round that reads it needs (the reference
  * simulates every arm to R on its first evaluate() but only ever reads the checkpoints - SURVEY D5).  Streams and

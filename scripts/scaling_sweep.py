@@ -20,7 +20,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from autotune.b200.engine import HyperbandSimSpec  # noqa: E402
-from autotune.b200.epdf import run_epdf_ofe  # noqa: E402
+from autotune.b200.epdf import FusedGather, run_epdf_ofe  # noqa: E402
 
 EGG_FAMILIES = [(1.5, 10, 15, False, 0, 1000), (0.5, 7, 10, False, 0, 1000), (0.2, 4, 7, True, 0, 1000)]
 
@@ -48,8 +48,11 @@ def main():
     # KDE window of the egg families: the curves end near f - 1000
     lo, hi, h = (-2100.0, -1500.0, 15.0) if args.func == 'egg' else (-4200.0, -2500.0, 30.0)
     for n in (int(x) for x in args.sizes.split(',')):
+        # N > 1, plain Hyperband: the OFE all-gather is fused into the simulation kernel (None -> NCCL all-gather)
+        fused = FusedGather.create(n, dev) if (world > 1 and runner is None) else None
+
         def job(seed):
-            return run_epdf_ofe(spec, n, seed, start=lo, end=hi, bandwidth=h, device=dev, runner=runner)
+            return run_epdf_ofe(spec, n, seed, start=lo, end=hi, bandwidth=h, device=dev, runner=runner, fused=fused)
         for i in range(3):
             job(100 + i)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -69,6 +72,7 @@ def main():
             print(json.dumps({'workload': f'Hyperband(R={args.max_iter},eta=3) EPDF-OFE on the {args.func} simulation, '
                                           f'3 families, {n} repetitions' + (', early stop' if args.early_stop else ''),
                               'n_gpus': world, 'scaling': 'strong', 'repetitions': n, 'ms_per_job': ms,
+                              'gather': 'fused' if fused is not None else ('nccl' if world > 1 else 'none'),
                               'runs_per_s': n / ms * 1e3,
                               'arm_epochs_per_s': n * spec.arm_epochs_per_repetition / ms * 1e3,
                               'ofe_mean': res['ofes'].double().mean().item(),

@@ -329,3 +329,27 @@ def test_heavily_tied_losses_keep_pythons_stable_order(R, eta, mom, dtype):
     first_round_keep = spec.plan.round_keep[0]
     assert out['survivors'][0][:first_round_keep].tolist() == list(range(first_round_keep))   # all equal: first arms win
     assert out['ofe_arm'][0] == 0 and out['round_best_arm'][0][0] == 0
+
+
+def test_fused_gather_entry_point_on_one_gpu():
+    """at2_hb_sim_gather_f32 with plain local buffers as gather targets (the multi-GPU run maps the peers' symmetric buffers
+    or the NVSwitch multicast address there - scripts/check_fused_gather.py verifies that at 2 and 8 GPUs): every target
+    receives the OFEs at gather_base + i, nothing else is touched, outputs equal at2_hb_sim_f32's."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    spec = HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10)
+    dev = torch.device('cuda')
+    n, base, total = 777, 1000, 2500
+    want = run_hyperband_repetitions(spec, n, seed=8, rep_offset=base)
+    a = torch.full((total,), -7.0, device=dev)
+    b = torch.full((total,), -7.0, device=dev)
+    outs = torch.ops.at2.hb_sim_gather(spec.tables(dev, torch.float32), spec.plan_bytes, spec.cfg_bytes, n, base, 8, a,
+                                       [a.data_ptr(), b.data_ptr()], base)
+    assert torch.equal(outs[0], want['ofe']) and torch.equal(outs[1], want['ofe_arm']) and torch.equal(outs[2], want['best_xy'])
+    for buf in (a, b):
+        assert torch.equal(buf[base:base + n], want['ofe'])
+        assert (buf[:base] == -7.0).all() and (buf[base + n:] == -7.0).all()
+    with pytest.raises(RuntimeError):
+        torch.ops.at2.hb_sim_gather(spec.tables(dev, torch.float32), spec.plan_bytes, spec.cfg_bytes, n, base, 8, a,
+                                    [a.data_ptr()], total - 5)            # would write past the buffer
+    with pytest.raises(RuntimeError):
+        torch.ops.at2.hb_sim_gather(spec.tables(dev, torch.float32), spec.plan_bytes, spec.cfg_bytes, n, base, 8, a, [], base)
