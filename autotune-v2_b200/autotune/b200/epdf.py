@@ -50,37 +50,49 @@ class FusedGather:
     replaces the NCCL collective.  Buffers are torch symmetric memory; two of them alternate so that one barrier per job is
     enough (a rank can run at most one job ahead of the slowest reader).
 
-    Collective constructor: every rank of `group` must call it.  `FusedGather.create` returns None (on every rank alike)
-    when symmetric memory cannot be set up, and callers fall back to `gather_slices` (NCCL)."""
+    Built by the collective `FusedGather.create`, which returns None (on every rank alike) when symmetric memory cannot be
+    set up; callers then fall back to `gather_slices` (NCCL)."""
 
-    def __init__(self, n_total, device, group=None, use_multicast=True):
-        import torch.distributed._symmetric_memory as symm_mem
-        self.group = group if group is not None else dist.group.WORLD
-        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+    def __init__(self, n_total, device, group, bufs, handles, use_multicast):
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_total, self.device = int(n_total), torch.device(device)
-        self.bufs, self.handles, self.targets = [], [], []
-        for _ in range(2):
-            buf = symm_mem.empty(self.n_total, dtype=torch.float32, device=self.device)
-            hdl = symm_mem.rendezvous(buf, self.group)
+        self.bufs, self.handles, self.targets = bufs, handles, []
+        for hdl in handles:
             mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if use_multicast else 0
-            self.bufs.append(buf)
-            self.handles.append(hdl)
             self.targets.append([mc] if mc else [int(p) for p in hdl.buffer_ptrs])
         self.multicast = len(self.targets[0]) == 1 and self.world > 1
         self.turn = 0
 
     @classmethod
     def create(cls, n_total, device, group=None, use_multicast=True):
-        """None unless every rank of the group managed to set the buffers up."""
+        """A FusedGather, or None - on every rank alike - when symmetric memory cannot be set up (callers then use NCCL).
+        Collective: every rank of the group must call it.  The local allocation and the collective rendezvous are agreed on
+        separately, so that a rank whose allocation failed never leaves the others waiting inside the rendezvous."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
             return None
+        group = group if group is not None else dist.group.WORLD
+
+        def all_ok(ok):
+            flag = torch.tensor([1 if ok else 0], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            return int(flag.item()) == 1
+        bufs = handles = None
         try:
-            fg, ok = cls(n_total, device, group, use_multicast), 1
-        except Exception:  # noqa: BLE001  (driver / fabric without peer mapping: use NCCL)
-            fg, ok = None, 0
-        flag = torch.tensor([ok], device=device, dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        return fg if int(flag.item()) == 1 else None
+            import torch.distributed._symmetric_memory as symm_mem
+            bufs = [symm_mem.empty(int(n_total), dtype=torch.float32, device=torch.device(device)) for _ in range(2)]
+        except Exception:  # noqa: BLE001
+            bufs = None
+        if not all_ok(bufs is not None):
+            return None
+        try:
+            handles = [symm_mem.rendezvous(b, group) for b in bufs]
+            ok = all(len(h.buffer_ptrs) == dist.get_world_size(group) for h in handles)
+        except Exception:  # noqa: BLE001
+            ok = False
+        if not all_ok(ok):
+            return None
+        return cls(n_total, device, group, bufs, handles, use_multicast)
 
     def run(self, spec, seed):
         """This rank's share of the job's repetitions; returns the gathered [n_total] OFE vector (a view of a symmetric
