@@ -1,0 +1,24 @@
+"""Fused simulate + all-gather against the NCCL all-gather on two GPUs (skipped on a single-GPU box; the 8-GPU run of the
+same script is recorded in DESIGN.md 7)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_fused_gather_is_bit_identical_to_nccl_on_two_gpus():
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29631', os.path.join(ROOT, 'scripts', 'check_fused_gather.py')]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]      # the script asserts bit-identity on every rank
+    report = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith('{')][-1])
+    assert report['world'] == 2
+    for case in ('flat-branin', 'rastrigin-6fam'):
+        assert isinstance(report[case]['peer-stores'], dict), report[case]    # symmetric memory was available and verified
