@@ -42,6 +42,7 @@ struct Params {
     long long n_reps, rep_offset;
     int G;            // repetitions per tile
     long long n_tiles;
+    long long n_tiles_full;   // tiles [0, n_tiles_full) hold G repetitions; the rest of the job is cut into 1-repetition tiles
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
     int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
     int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
@@ -111,8 +112,11 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
     const long long team_global = (long long)blockIdx.x * p.n_teams + team;
     const long long team_stride = (long long)gridDim.x * p.n_teams;
     for (long long tile = team_global; tile < p.n_tiles; tile += team_stride) {
-        const long long rep0 = tile * p.G;
-        const int g_eff = (int)min((long long)p.G, p.n_reps - rep0);
+        // whole rounds of G-repetition tiles, then the remainder of the job as single repetitions: the teams' shares then
+        // differ by one repetition at most, not by one tile (see launch_one)
+        const bool full = tile < p.n_tiles_full;
+        const long long rep0 = full ? tile * p.G : p.n_tiles_full * p.G + (tile - p.n_tiles_full);
+        const int g_eff = full ? p.G : 1;
         const int n_items = g_eff * A;
 
         // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
@@ -371,7 +375,14 @@ int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
     if (at2_resident_by_regs(kern, lc.block, &by_regs) != AT2_OK) return AT2_ECUDA;
     int grid = lc.grid;
     if ((long long)by_regs * lc.sms < grid) grid = by_regs * lc.sms;
-    kern<<<grid, lc.block, lc.smem, st>>>(p);
+    // Tile schedule.  A static round-robin over equal tiles leaves some teams one whole tile (G repetitions, ~1/9 of their
+    // work at 10^5 repetitions) more than others.  So only whole rounds are dealt out as G-repetition tiles; what is left
+    // (< teams * G + G repetitions) goes out as single repetitions.  Repetition ids do not change, results neither.
+    Params<T> q = p;
+    const long long teams = (long long)grid * q.n_teams, full_tiles = q.n_reps / q.G;
+    q.n_tiles_full = getenv("AT2_HB_EQUAL_TILES") != nullptr ? full_tiles : (full_tiles / teams) * teams;
+    q.n_tiles = q.n_tiles_full + (q.n_reps - q.n_tiles_full * q.G);
+    kern<<<grid, lc.block, lc.smem, st>>>(q);
     AT2_CUDA_CHECK(cudaGetLastError());
     at2_count_launch(1);
     return AT2_OK;
