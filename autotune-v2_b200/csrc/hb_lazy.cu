@@ -223,6 +223,18 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
         return (size_t)g * widest * 4 + (size_t)g * 12 + (size_t)p.npad * 8 + (size_t)g * 2 * keep_max * 2;
     };
     while (G > 1 && warp_bytes_of(G) > 40 * 1024) G = (G + 1) / 2;
+    if (env_g == nullptr && G >= 8) {
+        // the warps deal the tiles out round-robin: pick the tile size in [G/2, G] whose busiest warp gets the fewest
+        // repetitions (10^5 repetitions over 3552 warps: 2 x 15 instead of 2 x 16)
+        const long long warps = (long long)sms * 24;
+        long long best = -1;
+        int best_g = G;
+        for (int g = G; g >= G / 2; --g) {
+            const long long tiles = (n_reps + g - 1) / g, rounds = (tiles + warps - 1) / warps;
+            if (best < 0 || rounds * g < best) best = rounds * g, best_g = g;
+        }
+        G = best_g;
+    }
     p.G = G;
     p.warp_bytes = (int)((warp_bytes_of(G) + 15) & ~(size_t)15);
     p.n_tiles = (n_reps + G - 1) / G;
