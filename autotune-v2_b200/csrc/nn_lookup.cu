@@ -210,7 +210,7 @@ __device__ void draw_proposed(const KfParams& p, unsigned long long gid, double*
     }
 }
 
-__global__ void __launch_bounds__(128) hb_knownfn_kernel(const __grid_constant__ KfParams p) {
+__global__ void __launch_bounds__(256) hb_knownfn_kernel(const __grid_constant__ KfParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int A_arms = p.plan.n_arms, C = p.plan.n_ckpts, D = p.dom.D;
     double* s_db = reinterpret_cast<double*>(smem_raw);                       // [A][D] normalised
@@ -377,7 +377,11 @@ extern "C" int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int nwarps = 4;
+    int nwarps = 4;
+    {
+        const char* env_w = getenv("AT2_KF_WARPS_PER_CTA");      // development aid
+        if (env_w != nullptr && atoi(env_w) > 0 && atoi(env_w) <= 8) nwarps = atoi(env_w);
+    }
     p.npad = halving_npad(plan);
     p.G = 1;
     {
