@@ -107,11 +107,6 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ float2 lds64(uint32_t addr) {
-    float2 v;
-    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
-    return v;
-}
 // Table fetch of the trajectory loop.  GTAB = false: the tables were staged into shared memory and `addr` is a shared-space
 // address.  GTAB = true (plans whose tables do not fit beside the per-warp state: R ~ 1000 with six families): `addr` is a
 // byte offset into the table in global memory, read through the read-only path (L1/L2 resident: <= 300 KB per launch).
