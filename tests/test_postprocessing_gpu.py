@@ -74,3 +74,43 @@ def test_ks_on_reference_vectors():
     hb, all_, same = (g[f'{pre}({m})-7000-1'] for m in ('hb', 'hb+tpe+transfer+all', 'hb+tpe+transfer+same'))
     assert abs(ks_2samp(hb, all_).statistic - 0.068) < 2e-3
     assert abs(ks_2samp(all_, same).statistic - 0.020) < 2e-3
+
+
+def test_results_comparison_driver_on_the_references_stored_vectors(tmp_path):
+    """experiments/simulation_evaluation/plot_run_simulations_results.py on the reference's own OFE vectors (tests/golden/
+    epdf_ofes.npz): device histograms == numpy's, KS statistics == scipy's, EPDF == the closed form; the reference's
+    finding 'hybrids differ from Hyperband, hybrids resemble each other'  comes out."""
+    import pickle
+
+    from scipy.stats import ks_2samp as scipy_ks
+
+    from autotune.experiments.simulation_evaluation import plot_run_simulations_results as drv
+    from autotune.experiments.simulation_evaluation.plot_results import histograms
+    from oracle import kde as okde
+    g = np.load(f'{GOLDEN}/epdf_ofes.npz')
+    prefix = 'simulation-rastrigin-families-2/hist-sim-rastrigin-'
+    stored = {m: g[f'{prefix}{m}-7000-1'] for _, m in drv.METHODS if f'{prefix}{m}-7000-1' in g.files}
+    assert 'sim(hb)' in stored and 'sim(hb+tpe+transfer+all)' in stored
+    for method, vals in stored.items():                                     # the reference's file naming, -til suffix
+        with open(tmp_path / f'hist-sim-rastrigin-{method}-7000-1.pkl', 'wb') as f:
+            pickle.dump({'method': method, 'n_simulations': 7000, 'all_optimums': list(vals)}, f)
+    out = drv.main(['--simulation', 'rastrigin-families-2', '--dir', str(tmp_path), '-n', '7000'])
+    label_of = {m: lab for lab, m in drv.METHODS}
+    assert set(out['labels']) == {label_of[m] for m in stored}
+    bins = np.asarray(out['bins'])
+    assert bins[0] == -400 and len(bins) == 31
+    for lab, dens in zip(out['labels'], out['histograms']):
+        vals = stored[{v: k for k, v in label_of.items()}[lab]]
+        want, _ = np.histogram(vals, bins=bins, density=True)
+        np.testing.assert_allclose(dens, want, rtol=1e-12)
+    counts = histograms([stored['sim(hb)']], bins)[0]
+    assert np.array_equal(counts, np.histogram(stored['sim(hb)'], bins=bins)[0])
+    for (a, b), (stat, p) in out['ks'].items():
+        ma, mb = ({v: k for k, v in label_of.items()}[x] for x in (a, b))
+        ref = scipy_ks(stored[ma], stored[mb])
+        assert stat == pytest.approx(ref.statistic, abs=1e-6) and p == pytest.approx(ref.pvalue, rel=0.05, abs=1e-12)
+    assert out['ks'][('Hyperband', 'ALL')][1] < 1e-6                          # HB vs hybrids: distinguishable
+    if ('ALL', 'SAME') in out['ks']:
+        assert out['ks'][('ALL', 'SAME')][1] > 0.01                           # hybrids vs hybrids: not
+    want = okde.epdf(stored['sim(hb)'], -400, -370, 3.0)
+    np.testing.assert_allclose(out['epdf'][out['labels'].index('Hyperband')], want, rtol=2e-4, atol=1e-6)
