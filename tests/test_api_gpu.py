@@ -243,6 +243,10 @@ def test_closest_known_function_driver_cli_and_pickle(tmp_path):
         np.random.seed(11)
         want = [okf.run_hyperband(arms, curves, odom, 81, 3)['ofe'] for _ in range(60)]
         assert ks_2samp(np.asarray(saved['all_norm_optimums']), np.asarray(want)).pvalue > 0.01
+    # the result pickles feed the comparison script of the reference (plot_run_known_functions_results.py)
+    from autotune.experiments.simulation_evaluation import plot_run_known_functions_results as cmp_drv
+    cmp_out = _quiet(cmp_drv.main, ['--dir', str(tmp_path), '-n', '3000'])
+    assert cmp_out['labels'] == ['Hyperband'] and len(cmp_out['epdf']) == 3 and len(cmp_out['histograms'][0]) == 19
     with pytest.raises(NotImplementedError):
         _quiet(drv.main, ['-p', 'mnist', '-m', 'sim(hb+tpe+transfer+none)', '-n', '10', '-o', str(tmp_path)])
     with pytest.raises(ValueError):
