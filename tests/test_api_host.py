@@ -45,3 +45,19 @@ def test_reference_import_lines_resolve():
         mnist.get_evaluator()
     with pytest.raises(NotImplementedError):
         o.SigOptimiser(n_resources=3, max_iter=9)
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may use it."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'autotune-v2_b200')
+    pat = re.compile(r'^\s*(from\s+oracle\b|import\s+oracle\b)', re.M)
+    offenders = []
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                path = os.path.join(dirpath, f)
+                if pat.search(open(path, encoding='utf-8', errors='ignore').read()):
+                    offenders.append(path)
+    assert offenders == []
