@@ -181,6 +181,17 @@ def main():
             'value': procs * vec_reps / vwall, 'unit': UNIT, 'cores': procs, 'kind': 'port (batched NumPy, not the '
             "reference's code shape)", 'sample': f'{procs} processes x {vec_reps} repetitions in blocks of 500, {vwall:.1f} s wall'}
         pool.close()
+        try:   # the reference's own KDE call (plot_results.py:13-15: sklearn KernelDensity, epanechnikov, 1000-point grid)
+            import numpy as np
+            from sklearn.neighbors import KernelDensity
+            xs = np.random.default_rng(0).normal(0.81, 0.4, REPS_PER_GPU)[:, np.newaxis]
+            t0 = time.perf_counter()
+            kde = KernelDensity(kernel='epanechnikov', bandwidth=KDE_H).fit(xs)
+            np.exp(kde.score_samples(np.linspace(KDE_START, KDE_END, KDE_G)[:, np.newaxis]))
+            cpu_baseline['kde_sklearn'] = {'seconds': time.perf_counter() - t0, 'samples': REPS_PER_GPU, 'grid': KDE_G,
+                                           'cores': 1, 'kind': 'reference call (sklearn.neighbors.KernelDensity)'}
+        except Exception as e:  # noqa: BLE001
+            cpu_baseline['kde_sklearn'] = {'unavailable': repr(e)}
 
     import torch
     import torch.distributed as dist
