@@ -29,6 +29,18 @@ FLOP_PER_ARM_EPOCH = 32                                   # algorithmic FP32 flo
 WORKLOAD = ('Hyperband(R=81,eta=3) EPDF-OFE, flat Branin Gamma-simulation, 1e5 repetitions per GPU per step '
             '(BASELINE.json configs[1])')
 METRIC, UNIT = 'simulated optimiser runs/sec', 'runs/s'
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of this process, on the real stdout."""
+    data = (json.dumps(line) + '\n').encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def parse_args():
@@ -64,14 +76,14 @@ def run_reference_arm(args, rank):
     pool.close()
     value = n / wall
     sample = f'{procs} processes x {reps_per_proc} repetitions per step ({procs * reps_per_proc} runs/step)'
-    print(json.dumps({
+    emit({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': wall / max(args.steps, 1) * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'sample': sample},
         'arm_epochs_per_s': value * ARM_EPOCHS,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': procs, 'kind': 'port', 'sample': sample},
-        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}), flush=True)
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -150,6 +162,13 @@ def measured_peaks():
 
 
 def main():
+    # stdout carries exactly ONE JSON line.  Libraries write banners to file descriptor 1 behind python's back (NCCL prints
+    # its version there when the first communicator comes up), so fd 1 is pointed at stderr for the whole run and the JSON
+    # line is written to the saved descriptor at the end.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -422,7 +441,7 @@ def main():
         line['extras'] = extras
         if cpu_baseline is not None:
             line['cpu_baseline'] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
