@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                         f = (T)step_exact((double)f, (double)g, tt, R, (double)fn, (double)fam.ml, (double)fam.up,
                                           (double)P, (double)P11);
                     else
-                        f = (T)step_fast((float)f, (float)g, (float)fn, (float)fam.ml, (float)fam.up, (float)P,
-                                         (float)P11, (float)s_rec[AT2_REC * (fam.pw_off + tt) + 6]);
+                        f = (T)step_fast((float)f, (float)g, (float)fn, (float)fam.ml, -2.0f * (float)fam.ml, (float)fam.up,
+                                         (float)P, (float)P11, (float)s_rec[AT2_REC * (fam.pw_off + tt) + 6]);
                     if (HAS_SMOOTH && smooth) {
 #pragma unroll
                         for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[tt * L.sg_stride + c], f, acc[c]);

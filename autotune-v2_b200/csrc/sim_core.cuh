@@ -60,12 +60,13 @@ __device__ __forceinline__ float fast_cos(float x) {
     return r;
 }
 
-__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float upc, float P, float P11, float Q) {
+__device__ __forceinline__ float step_fast(float f, float g, float fn, float mlc, float m2c, float upc, float P, float P11,
+                                           float Q) {
     // production arithmetic of simulation_evaluator.py:99-115.  Down branch (:103-107) in fused form:
     //   ml = f + a (fn - f), a = (g - 2) ml_agg / 100;  f' = ml + (fn - ml) P = f + (fn - f) (a (1 - P) + P),  Q = 1 - P.
     // At the last step P = P11 = 1, so both branches land on f_n to within one rounding (the reference's float64 path has
     // the same property on its down branch).
-    const float a = fmaf(g, mlc, -2.0f * mlc);
+    const float a = fmaf(g, mlc, m2c);                      // m2c = -2 mlc, hoisted by the callers
     const float dn = fmaf(fn - f, fmaf(a, Q, P), f);
     const float up = fmaf(upc, fast_rcp(1.0f + g), f);
     const float un = fmaf(fn - up, P11, up);
@@ -195,7 +196,9 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     uint32_t sg_base = tb.sg_addr;
     asm volatile("" : "+r"(rec_base), "+r"(sg_base));   // keep them in registers
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
-    const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
+    uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
+    float m2c = -2.0f * mlc;
+    asm volatile("" : "+r"(end_addr), "+f"(m2c));       // loop invariants: keep them instead of recomputing them per block
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
     int nc = 0;                                                                // next checkpoint to capture
     int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[PARTIAL ? only_c : 0];   // padding lanes never capture
@@ -231,7 +234,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         // v <= 0 needs no test of its own: lg2 of a non-positive v^3 is NaN / -inf and the comparison fails
         bool ok = fast_lg2(u) < rhs;
         if constexpr (PARTIAL) ok = ok && addr < end_addr;
-        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, upc, pw.x, pw.y, pw.z);
+        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, m2c, upc, pw.x, pw.y, pw.z);
         ff = ok ? fnew : ff;
         if constexpr (HAS_SMOOTH) {
             const float fs = (ok && smooth) ? ff : 0.0f;

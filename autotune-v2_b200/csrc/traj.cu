@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
                 const float v3 = v * v * v;
                 const float rhs = fmaf(g[0], fast_lg2(v3), fmaf(-g[2], v3, fmaf(0.72134752044448170f, x * x, g[2])));
                 if (fast_lg2(u) < rhs) {
-                    ff = step_fast(ff, g[3] * v3, fn, mlc, upc, g[4], g[5], g[6]);
+                    ff = step_fast(ff, g[3] * v3, fn, mlc, -2.0f * mlc, upc, g[4], g[5], g[6]);
                     out[t] = ff;
                     ++t;
                 }
