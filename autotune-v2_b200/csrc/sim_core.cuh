@@ -198,7 +198,7 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
     uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     float m2c = -2.0f * mlc;
-    asm volatile("" : "+r"(end_addr), "+f"(m2c));       // loop invariants: keep them instead of recomputing them per block
+    asm volatile("" : "+r"(end_addr), "+f"(m2c), "+l"(ck));   // loop invariants: keep them instead of recomputing them per block
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
     int nc = 0;                                                                // next checkpoint to capture
     int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[PARTIAL ? only_c : 0];   // padding lanes never capture
