@@ -9,7 +9,8 @@
 // arm) pairs of the whole tile are spread flat over the lanes (G is chosen so that every round fills whole warps),
 // each lane re-simulates its arm from its stream's start up to the position the round reads (raw arms) or the end of the
 // Savitzky-Golay window of that read-out (smooth arms), and the round's losses land in shared memory; then the warp runs
-// that round of successive halving for each repetition.  Nothing is carried between rounds except the survivor ids.
+// that round of successive halving - repetition by repetition for wide rounds, 32 / n repetitions side by side for
+// rounds of n <= 16 arms.  Nothing is carried between rounds except the survivor ids.
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
@@ -28,6 +29,7 @@ struct LazyParams {
     const float* tables;
     long long n_reps, rep_offset, n_tiles;
     int G, npad, widest, keep_max, warp_bytes, dims;
+    int mixed;        // the families hold both raw and smoothed ones
     float* ofe;
     int* ofe_arm;
     float* best_xy;
@@ -36,7 +38,7 @@ struct LazyParams {
     int* survivors;
 };
 
-template <bool HAS_SMOOTH, int CK, bool GTAB>
+template <bool HAS_SMOOTH, bool GTAB>
 __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
@@ -89,25 +91,97 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                 const bool first_round = rd == p.plan.bracket_first_round[b];
                 const int keep = min(p.plan.round_keep[rd], n_cur);
                 // ---- simulate the alive arms of the whole tile up to what this round reads ----
-                const int n_items = g_eff * n_cur;
+                // A smoothed arm is read through its Savitzky-Golay window, so it has to run further than a raw arm read at
+                // the same checkpoint (R = 81, window 19: 19 steps against 0 at r = 1).  When the families mix both kinds
+                // and this round's two stopping points differ, the warp first lists a chunk's items raw-first (the family of
+                // an arm is one Philox block away) and runs the all-raw passes through the lean loop, to the raw stopping
+                // point; only the smoothed tail runs long.  The list aliases the sort scratch (idle until the halving below).
+                const int stop_raw = s_ckpos[c] + 1, stop_sm = HAS_SMOOTH ? s_sglast[c] + 1 : stop_raw;
+                const bool split = HAS_SMOOTH && p.mixed && stop_sm > stop_raw;
+                unsigned short* order = reinterpret_cast<unsigned short*>(keys);
+                const int cap = p.npad * 4;                                   // list entries: n_cur <= widest <= npad
+                const int rpc = split ? min(g_eff, cap / n_cur) : g_eff;      // repetitions per chunk
 #pragma unroll 1
-                for (int base = 0; base < n_items; base += 32) {
-                    const int q = base + lane;
-                    const bool active = q < n_items;
-                    const int g = active ? q / n_cur : 0, j = active ? q - g * n_cur : 0;
-                    const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
-                    const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
-                    const ArmDraw d = draw_arm(p.sp, gid, arm);
-                    const Fam<float> fam = p.fam[d.fam];
-                    const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
-                    const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
-                    const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-                    const int stop_t = (smooth ? s_sglast[c] : s_ckpos[c]) + 1;
-                    philox_trajectory<float, HAS_SMOOTH, CK, true, GTAB>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
-                                                                   p.sp.rk, stop_t, cur + g * p.widest + j, 0, C, c);
+                for (int g0 = 0; g0 < g_eff; g0 += rpc) {
+                    const int n_items = min(rpc, g_eff - g0) * n_cur;
+                    int n_raw = 0;
+                    if (split) {
+                        int n_sm = 0;
+#pragma unroll 1
+                        for (int base = 0; base < n_items; base += 32) {
+                            const int q = base + lane;
+                            const bool act = q < n_items;
+                            const int gl = act ? q / n_cur : 0, j = act ? q - gl * n_cur : 0, g = g0 + gl;
+                            const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                            const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
+                            const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
+                            const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
+                            const unsigned below = (1u << lane) - 1u;
+                            if (act) order[sm ? cap - 1 - (n_sm + __popc(m_sm & below)) : n_raw + __popc(m_raw & below)] = (unsigned short)q;
+                            n_raw += __popc(m_raw), n_sm += __popc(m_sm);
+                        }
+                        __syncwarp();
+                    }
+#pragma unroll 1
+                    for (int base = 0; base < n_items; base += 32) {
+                        const int qq = base + lane;
+                        const bool active = qq < n_items;
+                        const int q = !active ? 0 : (split ? (int)order[qq < n_raw ? qq : cap - 1 - (qq - n_raw)] : qq);
+                        const int gl = q / n_cur, j = q - gl * n_cur, g = g0 + gl;
+                        const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                        const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
+                        const ArmDraw d = draw_arm(p.sp, gid, arm);
+                        const Fam<float> fam = p.fam[d.fam];
+                        const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
+                        const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
+                        const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+                        float* dst = cur + g * p.widest + j;
+                        if (!HAS_SMOOTH || (split && base + 32 <= n_raw))
+                            philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
+                                                                           p.sp.rk, stop_raw, dst, 0, C, c);
+                        else
+                            philox_trajectory<float, HAS_SMOOTH, 1, true, GTAB>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off,
+                                                                                gid, p.sp.rk, smooth ? stop_sm : stop_raw, dst, 0, C, c);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
-                // ---- this round of successive halving, repetition by repetition ----
+                // ---- this round of successive halving ----
+                if (n_cur <= 16) {
+                    // narrow rounds: 32 / n_cur repetitions side by side in one warp, each segment of n_cur lanes ranks its
+                    // arms by counting (same stable order as warp_rank_by_counting); the lane that ranks first IS the
+                    // round-best of its repetition and does that repetition's bookkeeping
+                    const int S = 32 / n_cur, seg = lane / n_cur, j = lane - seg * n_cur;
+                    const unsigned seg_mask = (n_cur == 32 ? 0xffffffffu : (1u << n_cur) - 1u) << (seg < S ? seg * n_cur : 0);
+#pragma unroll 1
+                    for (int g0 = 0; g0 < g_eff; g0 += S) {
+                        const int g = g0 + seg;
+                        const bool act = seg < S && g < g_eff;
+                        const int ga = act ? g : 0;
+                        const long long rep_g = rep0 + ga;
+                        unsigned short* out = ids + (ga * 2 + (flip ^ 1)) * km;
+                        const int my_id = first_round ? first + j : (int)ids[(ga * 2 + flip) * km + j];
+                        const float my_loss = cur[ga * p.widest + j];
+                        const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
+                        int rank = 0;
+                        for (int k = 0; k < n_cur; ++k) rank += __shfl_sync(0xffffffffu, ord, seg * n_cur + k) < ord ? 1 : 0;
+                        rank += __popc(__match_any_sync(0xffffffffu, ord) & seg_mask & ((1u << lane) - 1u));
+                        const int sw = surv_w[ga];
+                        __syncwarp();
+                        if (act && rank < keep) {
+                            out[rank] = (unsigned short)my_id;
+                            if (p.survivors != nullptr) p.survivors[rep_g * p.plan.n_surv + sw + rank] = my_id;
+                        }
+                        if (act && rank == 0) {
+                            surv_w[ga] = sw + keep;
+                            if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = my_loss;
+                            if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = my_id;
+                            const int ba = best_arm[ga];
+                            const float bl = best[ga];
+                            if (ba < 0 || (desc ? my_loss > bl : my_loss < bl)) best[ga] = my_loss, best_arm[ga] = my_id;
+                        }
+                        __syncwarp();
+                    }
+                } else
                 for (int g = 0; g < g_eff; ++g) {
                     const long long rep_g = rep0 + g;
                     const float* loss = cur + g * p.widest;
@@ -151,9 +225,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     }
 }
 
-template <bool HS, int CK, bool GTAB = false>
+template <bool HS, bool GTAB = false>
 int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = hb_lazy_kernel<HS, CK, GTAB>;
+    auto kern = hb_lazy_kernel<HS, GTAB>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // persistent grid: never more CTAs than are resident at once (registers can bind before shared memory does)
@@ -195,6 +269,11 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
         p.fam[f].pw_off = f * (plan->R + 1);
     }
     p.dims = at2_func_dims(cfg->func);
+    {
+        int n_sm = 0;
+        for (int f = 0; f < cfg->n_families; ++f) n_sm += cfg->fam[f].is_smooth != 0;
+        p.mixed = n_sm > 0 && n_sm < cfg->n_families && getenv("AT2_HB_NO_SPLIT") == nullptr;   // env: tests / measurements
+    }
     p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
     p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
     p.sp.y_min = (float)cfg->y_min, p.sp.y_rng = (float)(cfg->y_max - cfg->y_min);
@@ -259,10 +338,8 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     if (grid > need) grid = need;
     cudaStream_t st = (cudaStream_t)stream;
     if (gtab)
-        return has_smooth ? launch_lazy<true, 16, true>(p, (int)grid, nwarps * 32, smem, st)
-                          : launch_lazy<false, 1, true>(p, (int)grid, nwarps * 32, smem, st);
-    if (!has_smooth) return launch_lazy<false, 1>(p, (int)grid, nwarps * 32, smem, st);
-    if (C <= 4) return launch_lazy<true, 4>(p, (int)grid, nwarps * 32, smem, st);
-    if (C <= 8) return launch_lazy<true, 8>(p, (int)grid, nwarps * 32, smem, st);
-    return launch_lazy<true, 16>(p, (int)grid, nwarps * 32, smem, st);
+        return has_smooth ? launch_lazy<true, true>(p, (int)grid, nwarps * 32, smem, st)
+                          : launch_lazy<false, true>(p, (int)grid, nwarps * 32, smem, st);
+    return has_smooth ? launch_lazy<true>(p, (int)grid, nwarps * 32, smem, st)
+                      : launch_lazy<false>(p, (int)grid, nwarps * 32, smem, st);
 }

@@ -118,6 +118,18 @@ __device__ __forceinline__ float4 tab128(const unsigned char* gbase, uint32_t ad
     else
         return lds128(addr);
 }
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <bool GTAB>
+__device__ __forceinline__ float tab32(const unsigned char* gbase, uint32_t addr) {
+    if constexpr (GTAB)
+        return __ldg(reinterpret_cast<const float*>(gbase + addr));
+    else
+        return lds32(addr);
+}
 __device__ __forceinline__ void team_barrier(int team, int team_warps) {
     if (team_warps == 1)
         __syncwarp();
@@ -183,8 +195,9 @@ struct SimTables {
 // before the current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
 //
 // PARTIAL = true (early-stopping evaluation): every lane has its own stop_t and stops advancing there, and only checkpoint
-// `only_c` is produced, into ck[0].  The stream and the arithmetic are the same as in the full run, so the value equals
-// the one the full run reads at that checkpoint, bit for bit.
+// `only_c` is produced, into ck[0] (instantiate with CK = 1: a smoothed arm then accumulates that one Savitzky-Golay
+// read-out - one scalar table fetch and one FMA per step instead of all C of them).  The stream and the arithmetic are
+// the same as in the full run, so the value equals the one the full run reads at that checkpoint, bit for bit.
 template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
                                                   float mlc, float upc, int pw_off, unsigned long long gid,
@@ -193,7 +206,8 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     const int R = tb.R;
     const unsigned char* const gbase = tb.gbase;
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
-    uint32_t sg_base = tb.sg_addr;
+    static_assert(!PARTIAL || CK == 1, "a partial run produces one checkpoint");
+    uint32_t sg_base = tb.sg_addr + (PARTIAL ? (uint32_t)only_c * 4u : 0u);   // PARTIAL: column only_c of sg
     asm volatile("" : "+r"(rec_base), "+r"(sg_base));   // keep them in registers
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
     uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
@@ -206,7 +220,9 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     float acc[CK];
 #pragma unroll
     for (int c = 0; c < CK; ++c) acc[c] = 0.0f;
-    if constexpr (HAS_SMOOTH) {
+    if constexpr (HAS_SMOOTH && PARTIAL) {
+        acc[0] = tab32<GTAB>(gbase, sg_base) * ((active && smooth) ? ff : 0.0f);
+    } else if constexpr (HAS_SMOOTH) {
         const float f0 = (active && smooth) ? ff : 0.0f;
 #pragma unroll
         for (int c4 = 0; c4 < CK; c4 += 4) {                                  // sg[0][c] * fs[0]
@@ -236,7 +252,10 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         if constexpr (PARTIAL) ok = ok && addr < end_addr;
         const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, m2c, upc, pw.x, pw.y, pw.z);
         ff = ok ? fnew : ff;
-        if constexpr (HAS_SMOOTH) {
+        if constexpr (HAS_SMOOTH && PARTIAL) {
+            const float fs = (ok && smooth) ? ff : 0.0f;
+            acc[0] = fmaf(tab32<GTAB>(gbase, sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4)), fs, acc[0]);
+        } else if constexpr (HAS_SMOOTH) {
             const float fs = (ok && smooth) ? ff : 0.0f;
             const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4);
 #pragma unroll
@@ -286,19 +305,13 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
 #pragma unroll
             for (int c = 0; c < CK; ++c) {
                 if (PARTIAL) {
-                    if (c == only_c) ck[0] = (T)acc[c];
+                    ck[0] = (T)acc[0];
                 } else if (c < C) {
                     ck[c * stride] = (T)acc[c];
                 }
             }
         }
     }
-}
-
-__device__ __forceinline__ float lds32(uint32_t addr) {
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-    return v;
 }
 
 // The recurrence is affine in its two inputs: f_t = A_t f_1 + (1 - A_t) f_n + C_t, where (A_t, C_t) depend only on the arm's
