@@ -10,8 +10,9 @@
 // each lane re-simulates its arm from its stream's start up to the position the round reads (raw arms) or the end of the
 // Savitzky-Golay window of that read-out (smooth arms), and the round's losses land in shared memory; then the warp runs
 // that round of successive halving - repetition by repetition for wide rounds, 32 / n repetitions side by side for
-// rounds of n <= 16 arms.  Nothing is carried between rounds except the survivor ids.
+// rounds of n <= 32 arms.  Nothing is carried between rounds except the survivor ids.
 #include <cfloat>
+#include <cmath>
 #include <climits>
 #include <cstdlib>
 
@@ -29,6 +30,7 @@ struct LazyParams {
     const float* tables;
     long long n_reps, rep_offset, n_tiles;
     int G, npad, widest, keep_max, warp_bytes, dims;
+    int cur_cap;      // floats in a warp's loss buffer (>= widest bracket)
     int mixed;        // the families hold both raw and smoothed ones
     float* ofe;
     int* ofe_arm;
@@ -37,6 +39,8 @@ struct LazyParams {
     int* round_best_arm;
     int* survivors;
 };
+
+__host__ __device__ inline size_t lazy_keys_offset(int cur_cap, int G) { return ((size_t)cur_cap * 4 + (size_t)G * 12 + 7) & ~(size_t)7; }
 
 template <bool HAS_SMOOTH, bool GTAB>
 __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
@@ -66,13 +70,13 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * 4) : (uint32_t)__cvta_generic_to_shared(s_rec),
                        GTAB ? (uint32_t)(L.off_sg() * 4) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R, L.sg_stride,
                        reinterpret_cast<const unsigned char*>(p.tables)};
-    // warp-private: losses of the current round [G][widest], survivor ids [G][2][keep_max], per-repetition state, sort scratch
+    // warp-private: losses of the current round chunk [cur_cap], survivor ids [G][2][keep_max], per-repetition state, sort scratch
     unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
-    float* cur = reinterpret_cast<float*>(mine);
-    float* best = cur + (size_t)G * p.widest;                       // [G] running OFE
+    float* cur = reinterpret_cast<float*>(mine);                    // [cur_cap] losses of the round chunk at hand
+    float* best = cur + p.cur_cap;                                  // [G] running OFE
     int* best_arm = reinterpret_cast<int*>(best + G);               // [G]
     int* surv_w = best_arm + G;                                     // [G] survivors written so far
-    Key32* keys = reinterpret_cast<Key32*>(surv_w + G);             // [npad]
+    Key32* keys = reinterpret_cast<Key32*>(mine + lazy_keys_offset(p.cur_cap, G));   // [npad]
     unsigned short* ids = reinterpret_cast<unsigned short*>(keys + p.npad);   // [G][2][keep_max]
     const bool desc = p.descending != 0;
     const int km = p.keep_max;
@@ -99,11 +103,15 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                 const int stop_raw = s_ckpos[c] + 1, stop_sm = HAS_SMOOTH ? s_sglast[c] + 1 : stop_raw;
                 const bool split = HAS_SMOOTH && p.mixed && stop_sm > stop_raw;
                 unsigned short* order = reinterpret_cast<unsigned short*>(keys);
-                const int cap = p.npad * 4;                                   // list entries: n_cur <= widest <= npad
-                const int rpc = split ? min(g_eff, cap / n_cur) : g_eff;      // repetitions per chunk
+                const int cap = p.npad * 4;                  // list entries; cur_cap <= cap
+                // The round is worked through in chunks of as many repetitions as the loss buffer holds (cur_cap floats: a
+                // few repetitions of a bracket's wide first round, the whole tile of a narrow late round - which is what
+                // lets a tile be 32 repetitions wide, so that the long single-arm rounds still fill the warp).
+                const int rpc = min(g_eff, p.cur_cap / n_cur);
 #pragma unroll 1
                 for (int g0 = 0; g0 < g_eff; g0 += rpc) {
-                    const int n_items = min(rpc, g_eff - g0) * n_cur;
+                    const int gc = min(rpc, g_eff - g0);     // repetitions g0 .. g0 + gc - 1; losses at cur[(g - g0) * n_cur + j]
+                    const int n_items = gc * n_cur;
                     int n_raw = 0;
                     if (split) {
                         int n_sm = 0;
@@ -135,7 +143,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                         const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
                         const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-                        float* dst = cur + g * p.widest + j;
+                        float* dst = cur + q;
                         if (!HAS_SMOOTH || (split && base + 32 <= n_raw))
                             philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
                                                                            p.sp.rk, stop_raw, dst, 0, C, c);
@@ -144,66 +152,68 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                                                                                 gid, p.sp.rk, smooth ? stop_sm : stop_raw, dst, 0, C, c);
                     }
                     __syncwarp();
-                }
-                // ---- this round of successive halving ----
-                if (n_cur <= 16) {
-                    // narrow rounds: 32 / n_cur repetitions side by side in one warp, each segment of n_cur lanes ranks its
-                    // arms by counting (same stable order as warp_rank_by_counting); the lane that ranks first IS the
-                    // round-best of its repetition and does that repetition's bookkeeping
-                    const int S = 32 / n_cur, seg = lane / n_cur, j = lane - seg * n_cur;
-                    const unsigned seg_mask = (n_cur == 32 ? 0xffffffffu : (1u << n_cur) - 1u) << (seg < S ? seg * n_cur : 0);
+                    // ---- this round of successive halving for the chunk's repetitions ----
+                    if (n_cur <= 32) {
+                        // narrow rounds: 32 / n_cur repetitions side by side in one warp, each segment of n_cur lanes ranks
+                        // its arms by counting (same stable order as warp_rank_by_counting); the lane that ranks first IS the
+                        // round-best of its repetition and does that repetition's bookkeeping
+                        const int S = 32 / n_cur, seg = lane / n_cur, j = lane - seg * n_cur;
+                        const unsigned seg_mask = (n_cur == 32 ? 0xffffffffu : (1u << n_cur) - 1u) << (seg < S ? seg * n_cur : 0);
 #pragma unroll 1
-                    for (int g0 = 0; g0 < g_eff; g0 += S) {
-                        const int g = g0 + seg;
-                        const bool act = seg < S && g < g_eff;
-                        const int ga = act ? g : 0;
-                        const long long rep_g = rep0 + ga;
-                        unsigned short* out = ids + (ga * 2 + (flip ^ 1)) * km;
-                        const int my_id = first_round ? first + j : (int)ids[(ga * 2 + flip) * km + j];
-                        const float my_loss = cur[ga * p.widest + j];
-                        const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
-                        int rank = 0;
-                        for (int k = 0; k < n_cur; ++k) rank += __shfl_sync(0xffffffffu, ord, seg * n_cur + k) < ord ? 1 : 0;
-                        rank += __popc(__match_any_sync(0xffffffffu, ord) & seg_mask & ((1u << lane) - 1u));
-                        const int sw = surv_w[ga];
-                        __syncwarp();
-                        if (act && rank < keep) {
-                            out[rank] = (unsigned short)my_id;
-                            if (p.survivors != nullptr) p.survivors[rep_g * p.plan.n_surv + sw + rank] = my_id;
+                        for (int h0 = 0; h0 < gc; h0 += S) {
+                            const bool act = seg < S && h0 + seg < gc;
+                            const int gl = act ? h0 + seg : 0, g = g0 + gl;
+                            const long long rep_g = rep0 + g;
+                            unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
+                            const int my_id = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                            const float my_loss = cur[gl * n_cur + j];
+                            const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
+                            int rank = 0;
+                            for (int k = 0; k < n_cur; ++k) rank += __shfl_sync(0xffffffffu, ord, seg * n_cur + k) < ord ? 1 : 0;
+                            rank += __popc(__match_any_sync(0xffffffffu, ord) & seg_mask & ((1u << lane) - 1u));
+                            const int sw = surv_w[g];
+                            __syncwarp();
+                            if (act && rank < keep) {
+                                out[rank] = (unsigned short)my_id;
+                                if (p.survivors != nullptr) p.survivors[rep_g * p.plan.n_surv + sw + rank] = my_id;
+                            }
+                            if (act && rank == 0) {
+                                surv_w[g] = sw + keep;
+                                if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = my_loss;
+                                if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = my_id;
+                                const int ba = best_arm[g];
+                                const float bl = best[g];
+                                if (ba < 0 || (desc ? my_loss > bl : my_loss < bl)) best[g] = my_loss, best_arm[g] = my_id;
+                            }
+                            __syncwarp();
                         }
-                        if (act && rank == 0) {
-                            surv_w[ga] = sw + keep;
-                            if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = my_loss;
-                            if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = my_id;
-                            const int ba = best_arm[ga];
-                            const float bl = best[ga];
-                            if (ba < 0 || (desc ? my_loss > bl : my_loss < bl)) best[ga] = my_loss, best_arm[ga] = my_id;
+                    } else {
+#pragma unroll 1
+                        for (int gl = 0; gl < gc; ++gl) {
+                            const int g = g0 + gl;
+                            const long long rep_g = rep0 + g;
+                            const float* loss = cur + gl * n_cur;
+                            const unsigned short* in = ids + (g * 2 + flip) * km;
+                            unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
+                            float rb_loss;
+                            int rb_arm;
+                            warp_halving_round_f32(n_cur, keep, first_round, first, in, out, keys, desc, lane,
+                                                   [&](int j, int) { return loss[j]; }, rb_loss, rb_arm);
+                            __syncwarp();
+                            const int sw = surv_w[g];
+                            if (p.survivors != nullptr)
+                                for (int j = lane; j < keep; j += 32) p.survivors[rep_g * p.plan.n_surv + sw + j] = (int)out[j];
+                            if (lane == 0) {
+                                surv_w[g] = sw + keep;
+                                if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = rb_loss;
+                                if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = rb_arm;
+                                const int ba = best_arm[g];
+                                const float bl = best[g];
+                                if (ba < 0 || (desc ? rb_loss > bl : rb_loss < bl)) best[g] = rb_loss, best_arm[g] = rb_arm;
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                     }
-                } else
-                for (int g = 0; g < g_eff; ++g) {
-                    const long long rep_g = rep0 + g;
-                    const float* loss = cur + g * p.widest;
-                    const unsigned short* in = ids + (g * 2 + flip) * km;
-                    unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
-                    float rb_loss;
-                    int rb_arm;
-                    warp_halving_round_f32(n_cur, keep, first_round, first, in, out, keys, desc, lane,
-                                           [&](int j, int) { return loss[j]; }, rb_loss, rb_arm);
-                    __syncwarp();
-                    const int sw = surv_w[g];
-                    if (p.survivors != nullptr)
-                        for (int j = lane; j < keep; j += 32) p.survivors[rep_g * p.plan.n_surv + sw + j] = (int)out[j];
-                    if (lane == 0) {
-                        surv_w[g] = sw + keep;
-                        if (p.round_best != nullptr) p.round_best[rep_g * p.plan.n_rounds + rd] = rb_loss;
-                        if (p.round_best_arm != nullptr) p.round_best_arm[rep_g * p.plan.n_rounds + rd] = rb_arm;
-                        const int ba = best_arm[g];
-                        const float bl = best[g];
-                        if (ba < 0 || (desc ? rb_loss > bl : rb_loss < bl)) best[g] = rb_loss, best_arm[g] = rb_arm;
-                    }
-                    __syncwarp();
                 }
                 flip ^= 1;
                 n_cur = keep;
@@ -293,24 +303,49 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
-    int G = env_g != nullptr && atoi(env_g) > 0 ? atoi(env_g) : 16;
-    if ((long long)G > n_reps) G = (int)n_reps;
-    // a warp's tile state: round losses [G][widest], per-repetition state, sort scratch, survivor ids; wide plans get
-    // fewer repetitions per tile so that four warps still fit
+    // Loss buffer of a warp: the widest bracket has to fit; beyond that, 512 floats keep every chunk of a round at 15+
+    // warp passes (and it never exceeds the 4 * npad entries of the raw-first list that shares the sort scratch).
+    p.cur_cap = widest > 512 ? widest : 512;
+    if (p.cur_cap > 4 * p.npad) p.cur_cap = 4 * p.npad;
+    // a warp's tile state: loss buffer, per-repetition state, sort scratch, survivor ids
     auto warp_bytes_of = [&](int g) {
-        return (size_t)g * widest * 4 + (size_t)g * 12 + (size_t)p.npad * 8 + (size_t)g * 2 * keep_max * 2;
+        return lazy_keys_offset(p.cur_cap, g) + (size_t)p.npad * 8 + (size_t)g * 2 * keep_max * 2;
     };
-    while (G > 1 && warp_bytes_of(G) > 40 * 1024) G = (G + 1) / 2;
-    if (env_g == nullptr && G >= 8) {
-        // the warps deal the tiles out round-robin: pick the tile size in [G/2, G] whose busiest warp gets the fewest
-        // repetitions (10^5 repetitions over 3552 warps: 2 x 15 instead of 2 x 16)
+    // Tile width.  Up to 32 repetitions (the single-arm last rounds then fill the warp) as long as 24 warps per SM keep
+    // their state in shared memory; among those, the width whose busiest warp finishes first under a coarse cost model
+    // (warp passes x steps read + per-pass set-up + halving operations) - a small job is cut into narrow tiles so that
+    // it still covers the machine, a large one into wide ones.
+    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
+    int G = 32;
+    while (G > 1 && warp_bytes_of(G) > 8704) --G;
+    if ((long long)G > n_reps) G = (int)n_reps;
+    if (env_g != nullptr && atoi(env_g) > 0) {
+        G = atoi(env_g);
+        if ((long long)G > n_reps) G = (int)n_reps;
+        while (G > 1 && warp_bytes_of(G) > 40 * 1024) G = (G + 1) / 2;
+    } else {
         const long long warps = (long long)sms * 24;
-        long long best = -1;
+        double best_cost = -1.0;
         int best_g = G;
-        for (int g = G; g >= G / 2; --g) {
+        for (int g = G; g >= 1; --g) {
+            double cost = 0.0;
+            for (int b = 0; b < plan->n_brackets; ++b) {
+                int n_cur = plan->bracket_n[b];
+                for (int rd = plan->bracket_first_round[b]; rd < plan->bracket_first_round[b + 1]; ++rd) {
+                    const int keep = plan->round_keep[rd] < n_cur ? plan->round_keep[rd] : n_cur;
+                    const int steps = plan->ckpt_time[plan->round_ckpt[rd]] - 1;
+                    cost += (double)((g * n_cur + 31) / 32) * (steps + 6);                     // trajectories + arm set-up
+                    cost += n_cur <= 32 ? (double)((g + 32 / n_cur - 1) / (32 / n_cur)) * (0.5 + n_cur / 16.0)
+                                        : (double)g * (n_cur <= 128 ? 15.0 : 40.0);              // halving
+                    n_cur = keep;
+                }
+            }
             const long long tiles = (n_reps + g - 1) / g, rounds = (tiles + warps - 1) / warps;
-            if (best < 0 || rounds * g < best) best = rounds * g, best_g = g;
+            // a warp alone on its scheduler issues ~0.18 instructions per cycle, w of them together 1 - 0.82^w (six: 0.7,
+            // as ncu shows): a few wide tiles run faster per warp than many narrow ones
+            const double per_sched = (double)(tiles < warps ? tiles : warps) / (4.0 * sms);
+            cost *= (double)rounds * per_sched / (1.0 - pow(0.82, per_sched));
+            if (best_cost < 0.0 || cost < best_cost) best_cost = cost, best_g = g;
         }
         G = best_g;
     }

@@ -160,10 +160,14 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
     d.y = fmaf((float)(r.y >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
     d.fam = sp.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)sp.F) : arm % sp.F;
     const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
-    const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
-    d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
-    d.x2 = fmaf((float)(r2.y >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
-    d.y2 = fmaf((float)(r2.z >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
+    d.z = d.x2 = d.y2 = 0.0f;
+    // the second block feeds the initial noise and the extra coordinates only: nothing reads it on a noise-free 2-D problem
+    if (sp.noise != 0.0f || sp.func == AT2_FUNC_EGG4) {
+        const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
+        d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+        d.x2 = fmaf((float)(r2.y >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
+        d.y2 = fmaf((float)(r2.z >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
+    }
     return d;
 }
 

@@ -244,6 +244,30 @@ def test_unusual_plans_run_and_agree_with_independent_halving(func, families, R,
         assert spec.rounds()[0]['time'] == 729     # int(0.9999999999999999) == 0 -> python index -1 -> the last point
 
 
+@pytest.mark.parametrize('tile', [1, 3, 7, 16, 32])
+def test_early_stopping_tile_widths_do_not_change_outputs(monkeypatch, tile):
+    """The early-stopping kernel cuts a job into tiles of G repetitions per warp (chosen from the job size; a small job
+    gets narrow tiles), works through a round in chunks of repetitions, lists raw arms ahead of smoothed ones and ranks
+    narrow rounds 32 / n repetitions at a time.  None of that may change a bit: every width (forced here) must reproduce
+    the full simulation, ragged last tile and last chunk included."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    monkeypatch.setenv('AT2_HB_LAZY_REPS_PER_TILE', str(tile))
+    for func, fams, R, eta, noise, mom, n in (('rastrigin', FAM6, 81, 3, 10, 'min', 1000 + 13), ('branin', FLAT, 81, 3, 0, 'min', 997),
+                                              ('egg', FAM6[:3], 243, 3, 10, 'min', 101), ('wave', FAM6[2:3], 27, 3, 10, 'max', 500),
+                                              ('camel', FAM6, 16, 2, 1, 'min', 333)):
+        spec = HyperbandSimSpec(func, fams, R, eta, noise, 'uniform', mom)
+        full = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True)
+        lazy = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True, early_stop=True)
+        for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors'):
+            assert torch.equal(full[k], lazy[k]), (func, k)
+    monkeypatch.setenv('AT2_HB_NO_SPLIT', '1')          # mixed passes as before the raw-first list
+    spec = HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10)
+    a = run_hyperband_repetitions(spec, 700, seed=5, details=True)
+    b = run_hyperband_repetitions(spec, 700, seed=5, details=True, early_stop=True)
+    for k in ('ofe', 'ofe_arm', 'round_best', 'survivors'):
+        assert torch.equal(a[k], b[k]), k
+
+
 def test_egg4_extension_flat_family_ofe_is_the_function_value():
     """4-D Egg-holder of BASELINE.json config 5 - an EXTENSION with no reference equivalent, defined in
     include/at2.h and oracle/opt_functions.egg4.  With the flat family (no noise, no shifts) every loss of an arm equals
