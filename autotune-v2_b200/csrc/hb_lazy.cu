@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                 // few repetitions of a bracket's wide first round, the whole tile of a narrow late round - which is what
                 // lets a tile be 32 repetitions wide, so that the long single-arm rounds still fill the warp).
                 const int rpc = min(g_eff, p.cur_cap / n_cur);
+                // q / n_cur for item numbers q < 65536 by one multiply-high (exact: q * n_cur < 2^32)
+                const uint32_t div_magic = n_cur > 1 ? 0xffffffffu / (uint32_t)n_cur + 1u : 0u;
+                auto div_n = [&](int q) { return n_cur > 1 ? (int)__umulhi((uint32_t)q, div_magic) : q; };
 #pragma unroll 1
                 for (int g0 = 0; g0 < g_eff; g0 += rpc) {
                     const int gc = min(rpc, g_eff - g0);     // repetitions g0 .. g0 + gc - 1; losses at cur[(g - g0) * n_cur + j]
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         for (int base = 0; base < n_items; base += 32) {
                             const int q = base + lane;
                             const bool act = q < n_items;
-                            const int gl = act ? q / n_cur : 0, j = act ? q - gl * n_cur : 0, g = g0 + gl;
+                            const int gl = act ? div_n(q) : 0, j = act ? q - gl * n_cur : 0, g = g0 + gl;
                             const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
                             const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
                             const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const int qq = base + lane;
                         const bool active = qq < n_items;
                         const int q = !active ? 0 : (split ? (int)order[qq < n_raw ? qq : cap - 1 - (qq - n_raw)] : qq);
-                        const int gl = q / n_cur, j = q - gl * n_cur, g = g0 + gl;
+                        const int gl = div_n(q), j = q - gl * n_cur, g = g0 + gl;
                         const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
                         const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
                         const ArmDraw d = draw_arm(p.sp, gid, arm);
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         // narrow rounds: 32 / n_cur repetitions side by side in one warp, each segment of n_cur lanes ranks
                         // its arms by counting (same stable order as warp_rank_by_counting); the lane that ranks first IS the
                         // round-best of its repetition and does that repetition's bookkeeping
-                        const int S = 32 / n_cur, seg = lane / n_cur, j = lane - seg * n_cur;
+                        const int S = 32 / n_cur, seg = div_n(lane), j = lane - seg * n_cur;
                         const unsigned seg_mask = (n_cur == 32 ? 0xffffffffu : (1u << n_cur) - 1u) << (seg < S ? seg * n_cur : 0);
 #pragma unroll 1
                         for (int h0 = 0; h0 < gc; h0 += S) {
@@ -169,6 +172,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                             const float my_loss = cur[gl * n_cur + j];
                             const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
                             int rank = 0;
+#pragma unroll 3
                             for (int k = 0; k < n_cur; ++k) rank += __shfl_sync(0xffffffffu, ord, seg * n_cur + k) < ord ? 1 : 0;
                             rank += __popc(__match_any_sync(0xffffffffu, ord) & seg_mask & ((1u << lane) - 1u));
                             const int sw = surv_w[g];
