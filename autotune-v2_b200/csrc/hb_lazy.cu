@@ -29,7 +29,8 @@ struct LazyParams {
     int descending;
     const float* tables;
     long long n_reps, rep_offset, n_tiles;
-    int G, npad, widest, keep_max, warp_bytes, dims;
+    int G, npad, widest, warp_bytes, dims;
+    int km_a, km_b;   // entries of the two survivor-id buffers of a repetition (see the kernel)
     int cur_cap;      // floats in a warp's loss buffer (>= widest bracket)
     int mixed;        // the families hold both raw and smoothed ones
     float* ofe;
@@ -70,16 +71,20 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * 4) : (uint32_t)__cvta_generic_to_shared(s_rec),
                        GTAB ? (uint32_t)(L.off_sg() * 4) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R, L.sg_stride,
                        reinterpret_cast<const unsigned char*>(p.tables)};
-    // warp-private: losses of the current round chunk [cur_cap], survivor ids [G][2][keep_max], per-repetition state, sort scratch
+    // warp-private: losses of the current round chunk [cur_cap], survivor ids [G][km_a + km_b], per-repetition state, sort scratch
     unsigned char* mine = warp_base + (size_t)warp * p.warp_bytes;
     float* cur = reinterpret_cast<float*>(mine);                    // [cur_cap] losses of the round chunk at hand
     float* best = cur + p.cur_cap;                                  // [G] running OFE
     int* best_arm = reinterpret_cast<int*>(best + G);               // [G]
     int* surv_w = best_arm + G;                                     // [G] survivors written so far
     Key32* keys = reinterpret_cast<Key32*>(mine + lazy_keys_offset(p.cur_cap, G));   // [npad]
-    unsigned short* ids = reinterpret_cast<unsigned short*>(keys + p.npad);   // [G][2][keep_max]
+    // Survivor ids of a repetition alternate between two buffers: round i of a bracket reads the one round i - 1 wrote.
+    // Buffer A receives the survivors of a bracket's rounds 0, 2, 4, ..., buffer B those of rounds 1, 3, ... - a third of
+    // A's at eta = 3 - so they are sized separately (km_a, km_b entries).
+    unsigned short* ids = reinterpret_cast<unsigned short*>(keys + p.npad);   // [G][km_a + km_b]
+    const int kms = p.km_a + p.km_b;
+    auto idbuf = [&](int g, int fl) { return ids + g * kms + (fl ? 0 : p.km_a); };   // fl = 1: buffer A
     const bool desc = p.descending != 0;
-    const int km = p.keep_max;
 
     for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (long long)gridDim.x * nwarps) {
         const long long rep0 = tile * G;
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                             const int q = base + lane;
                             const bool act = q < n_items;
                             const int gl = act ? div_n(q) : 0, j = act ? q - gl * n_cur : 0, g = g0 + gl;
-                            const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                            const int arm = first_round ? first + j : (int)idbuf(g, flip)[j];
                             const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
                             const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
                             const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const bool active = qq < n_items;
                         const int q = !active ? 0 : (split ? (int)order[qq < n_raw ? qq : cap - 1 - (qq - n_raw)] : qq);
                         const int gl = div_n(q), j = q - gl * n_cur, g = g0 + gl;
-                        const int arm = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                        const int arm = first_round ? first + j : (int)idbuf(g, flip)[j];
                         const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
                         const ArmDraw d = draw_arm(p.sp, gid, arm);
                         const Fam<float> fam = p.fam[d.fam];
@@ -167,8 +172,8 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                             const bool act = seg < S && h0 + seg < gc;
                             const int gl = act ? h0 + seg : 0, g = g0 + gl;
                             const long long rep_g = rep0 + g;
-                            unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
-                            const int my_id = first_round ? first + j : (int)ids[(g * 2 + flip) * km + j];
+                            unsigned short* out = idbuf(g, flip ^ 1);
+                            const int my_id = first_round ? first + j : (int)idbuf(g, flip)[j];
                             const float my_loss = cur[gl * n_cur + j];
                             const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
                             int rank = 0;
@@ -197,8 +202,8 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                             const int g = g0 + gl;
                             const long long rep_g = rep0 + g;
                             const float* loss = cur + gl * n_cur;
-                            const unsigned short* in = ids + (g * 2 + flip) * km;
-                            unsigned short* out = ids + (g * 2 + (flip ^ 1)) * km;
+                            const unsigned short* in = idbuf(g, flip);
+                            unsigned short* out = idbuf(g, flip ^ 1);
                             float rb_loss;
                             int rb_arm;
                             warp_halving_round_f32(n_cur, keep, first_round, first, in, out, keys, desc, lane,
@@ -299,10 +304,15 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
     p.round_best = (float*)out->d_round_best, p.round_best_arm = out->d_round_best_arm, p.survivors = out->d_survivors;
     p.npad = halving_npad(plan);
-    int widest = 0, keep_max = 1;
-    for (int b = 0; b < plan->n_brackets; ++b) widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
-    for (int r = 0; r < plan->n_rounds; ++r) keep_max = plan->round_keep[r] > keep_max ? plan->round_keep[r] : keep_max;
-    p.widest = widest, p.keep_max = keep_max;
+    int widest = 0, km_a = 1, km_b = 1;
+    for (int b = 0; b < plan->n_brackets; ++b) {
+        widest = plan->bracket_n[b] > widest ? plan->bracket_n[b] : widest;
+        for (int rd = plan->bracket_first_round[b]; rd < plan->bracket_first_round[b + 1]; ++rd) {
+            int& km = ((rd - plan->bracket_first_round[b]) & 1) ? km_b : km_a;
+            km = plan->round_keep[rd] > km ? plan->round_keep[rd] : km;
+        }
+    }
+    p.widest = widest, p.km_a = km_a, p.km_b = km_b;
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -311,27 +321,49 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     // warp passes (and it never exceeds the 4 * npad entries of the raw-first list that shares the sort scratch).
     p.cur_cap = widest > 512 ? widest : 512;
     if (p.cur_cap > 4 * p.npad) p.cur_cap = 4 * p.npad;
-    // a warp's tile state: loss buffer, per-repetition state, sort scratch, survivor ids
-    auto warp_bytes_of = [&](int g) {
-        return lazy_keys_offset(p.cur_cap, g) + (size_t)p.npad * 8 + (size_t)g * 2 * keep_max * 2;
+    const int C = plan->n_ckpts;
+    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    const size_t tab_bytes = (size_t)((L.total() + 3) & ~3) * 4, fixed_small = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    const bool force_gtab = getenv("AT2_FORCE_GTAB") != nullptr;   // env: tests
+    // launch geometry of tile width g: a warp's tile state (loss buffer, per-repetition state, sort scratch, survivor ids),
+    // tables in shared or global memory, warps per CTA, CTAs per SM
+    struct Geo {
+        size_t warp_bytes, smem;
+        bool gtab;
+        int nwarps, per_sm;
     };
-    // Tile width.  Up to 32 repetitions (the single-arm last rounds then fill the warp) as long as 24 warps per SM keep
-    // their state in shared memory; among those, the width whose busiest warp finishes first under a coarse cost model
-    // (warp passes x steps read + per-pass set-up + halving operations) - a small job is cut into narrow tiles so that
-    // it still covers the machine, a large one into wide ones.
+    auto geometry = [&](int g) {
+        Geo q;
+        q.warp_bytes = (lazy_keys_offset(p.cur_cap, g) + (size_t)p.npad * 8 + (size_t)g * (km_a + km_b) * 2 + 15) & ~(size_t)15;
+        // plans whose tables do not fit beside two warps' state read them from global memory
+        q.gtab = tab_bytes + fixed_small + 2 * q.warp_bytes > (size_t)max_smem || force_gtab;
+        const size_t fixed = q.gtab ? fixed_small : tab_bytes + fixed_small;
+        q.nwarps = 8;
+        while (q.nwarps > 1 && fixed + (size_t)q.nwarps * q.warp_bytes > (size_t)max_smem) q.nwarps >>= 1;
+        q.smem = fixed + (size_t)q.nwarps * q.warp_bytes;
+        q.per_sm = (int)((size_t)(227 * 1024) / (q.smem + 1024));
+        if (q.per_sm < 1) q.per_sm = 1;
+        if (q.per_sm * q.nwarps > 24) q.per_sm = 24 / q.nwarps > 0 ? 24 / q.nwarps : 1;   // registers: 24 warps of 80
+        return q;
+    };
+    // Tile width: up to 32 repetitions (the single-arm last rounds then fill the warp).  The width whose busiest warp
+    // finishes first under a coarse cost model - warp passes x steps read + per-pass set-up + halving operations, scaled by
+    // what a warp's share of its scheduler is worth at that width's residency - so a small job is cut into narrow tiles
+    // that cover the machine, a large one into wide ones, and a plan with wide brackets (whose survivor lists eat shared
+    // memory) trades resident warps for fuller lanes only where that pays.
     const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
     int G = 32;
-    while (G > 1 && warp_bytes_of(G) > 8704) --G;
     if ((long long)G > n_reps) G = (int)n_reps;
     if (env_g != nullptr && atoi(env_g) > 0) {
         G = atoi(env_g);
         if ((long long)G > n_reps) G = (int)n_reps;
-        while (G > 1 && warp_bytes_of(G) > 40 * 1024) G = (G + 1) / 2;
+        while (G > 1 && geometry(G).warp_bytes > 40 * 1024) G = (G + 1) / 2;
     } else {
-        const long long warps = (long long)sms * 24;
         double best_cost = -1.0;
-        int best_g = G;
+        int best_g = 1;
         for (int g = G; g >= 1; --g) {
+            const Geo q = geometry(g);
+            if (g > 1 && q.warp_bytes > 40 * 1024) continue;
             double cost = 0.0;
             for (int b = 0; b < plan->n_brackets; ++b) {
                 int n_cur = plan->bracket_n[b];
@@ -344,6 +376,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
                     n_cur = keep;
                 }
             }
+            const long long warps = (long long)sms * q.per_sm * q.nwarps;
             const long long tiles = (n_reps + g - 1) / g, rounds = (tiles + warps - 1) / warps;
             // a warp alone on its scheduler issues ~0.18 instructions per cycle, w of them together 1 - 0.82^w (six: 0.7,
             // as ncu shows): a few wide tiles run faster per warp than many narrow ones
@@ -353,25 +386,18 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
         }
         G = best_g;
     }
+    const Geo geo = geometry(G);
     p.G = G;
-    p.warp_bytes = (int)((warp_bytes_of(G) + 15) & ~(size_t)15);
+    p.warp_bytes = (int)geo.warp_bytes;
     p.n_tiles = (n_reps + G - 1) / G;
-    const int C = plan->n_ckpts;
-    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
-    size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
-    // plans whose tables do not fit beside two warps' state read them from global memory
-    const bool gtab = fixed + 2 * (size_t)p.warp_bytes > (size_t)max_smem || getenv("AT2_FORCE_GTAB") != nullptr;   // env: tests
-    if (gtab) fixed = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
-    int nwarps = 8;
-    while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) nwarps >>= 1;
-    const size_t smem = fixed + (size_t)nwarps * p.warp_bytes;
+    const bool gtab = geo.gtab;
+    const int nwarps = geo.nwarps;
+    int per_sm = geo.per_sm;
+    const size_t smem = geo.smem;
     if (smem > (size_t)max_smem) {
         at2_set_error("at2_hb_sim_early_stop_f32 needs %zu B of shared memory per CTA; device limit %d B", smem, max_smem);
         return AT2_ELIMIT;
     }
-    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm * nwarps > 32) per_sm = 32 / nwarps > 0 ? 32 / nwarps : 1;
     long long grid = (long long)sms * per_sm;
     const long long need = (p.n_tiles + nwarps - 1) / nwarps;
     if (grid > need) grid = need;
