@@ -5,12 +5,13 @@
 // ("results are unaffected by lazy simulation"); with counter-based streams per arm the values read are
 // bit-identical to the full simulation's, so OFEs, survivor sets and round-bests are the same - at ~1/12 of the epochs.
 //
-// Mapping: a warp owns a tile of G repetitions and walks the plan round by round.  In a round, the (repetition, alive
-// arm) pairs of the whole tile are spread flat over the lanes (G is chosen so that every round fills whole warps),
-// each lane re-simulates its arm from its stream's start up to the position the round reads (raw arms) or the end of the
-// Savitzky-Golay window of that read-out (smooth arms), and the round's losses land in shared memory; then the warp runs
-// that round of successive halving - repetition by repetition for wide rounds, 32 / n repetitions side by side for
-// rounds of n <= 32 arms.  Nothing is carried between rounds except the survivor ids.
+// Mapping: a warp owns a tile of G <= 32 repetitions and walks the plan round by round (G comes from a cost model of the
+// job, see the entry point).  A round is worked through in chunks of repetitions: the (repetition, alive arm) pairs of a
+// chunk are spread flat over the lanes, each lane re-simulates its arm from its stream's start up to the position the
+// round reads (raw arms) or the end of the Savitzky-Golay window of that read-out (smoothed arms - listed behind the raw
+// ones so that only their passes run long), and the chunk's losses land in shared memory; then the warp runs that round
+// of successive halving - repetition by repetition for wide rounds, 32 / n repetitions side by side for rounds of
+// n <= 32 arms.  Nothing is carried between rounds except the survivor ids.
 #include <cfloat>
 #include <cmath>
 #include <climits>
