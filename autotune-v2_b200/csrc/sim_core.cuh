@@ -292,17 +292,20 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
             cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
         }
     };
-    uint32_t ctr = 1;
-    At2U4 ra = at2_philox10_rk(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, rk), rb;
-    while (true) {
-        if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-        rb = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
-        ++ctr;
-        consume(ra);
-        if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-        ra = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
-        ++ctr;
-        consume(rb);
+    // a partial run that reads the first point (r = 1) has no step to make: not even the first Philox block
+    if (!PARTIAL || __any_sync(0xffffffffu, addr < end_addr)) {
+        uint32_t ctr = 1;
+        At2U4 ra = at2_philox10_rk(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, rk), rb;
+        while (true) {
+            if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+            rb = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
+            ++ctr;
+            consume(ra);
+            if (!__any_sync(0xffffffffu, addr < end_addr)) break;
+            ra = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
+            ++ctr;
+            consume(rb);
+        }
     }
     if constexpr (HAS_SMOOTH) {
         if (active && smooth) {
