@@ -350,6 +350,108 @@ __device__ int warp_halving(const at2_plan& plan, const T* ck, int stride, typen
     return st.best_arm;
 }
 
+// Successive halving of the G repetitions of a warp's tile TOGETHER (float losses at ck[c * stride + g * A + arm]): the
+// rounds of a bracket are walked once for the whole tile; a round of n <= 32 arms ranks 32 / n repetitions side by side
+// (segments of n lanes, rank by counting with python's stable tie-break, as warp_rank_by_counting) and the lane that ranks
+// first does its repetition's bookkeeping; wider rounds go repetition by repetition through warp_halving_round_f32.
+// Results are those of warp_halving<float> per repetition, bit for bit.
+//   ids: G * (km_a + km_b) entries - a repetition's survivor ids alternate between buffer A (km_a entries: survivors of a
+//        bracket's rounds 0, 2, ..) and buffer B (km_b: rounds 1, 3, ..);  best / best_arm / surv_w: G entries each.
+// On return best[g] / best_arm[g] hold repetition g's OFE and its arm (also written to out.ofe / out.ofe_arm).
+__device__ __forceinline__ void tile_halving_f32(const at2_plan& plan, const float* ck, int stride, int A, int G, Key32* keys,
+                                                 unsigned short* ids, int km_a, int km_b, float* best, int* best_arm,
+                                                 int* surv_w, bool desc, int lane, long long rep0,
+                                                 const HalvingOut<float>& out) {
+    const int kms = km_a + km_b;
+    auto idbuf = [&](int g, int fl) { return ids + g * kms + (fl ? 0 : km_a); };   // fl = 1: buffer A
+    for (int g = lane; g < G; g += 32) best_arm[g] = -1, surv_w[g] = 0, best[g] = 0.0f;
+    __syncwarp();
+    for (int b = 0; b < plan.n_brackets; ++b) {
+        const int first = plan.bracket_first_arm[b];
+        int n_cur = plan.bracket_n[b];
+        int flip = 0;
+        for (int rd = plan.bracket_first_round[b]; rd < plan.bracket_first_round[b + 1]; ++rd) {
+            const float* col = ck + plan.round_ckpt[rd] * stride;
+            const bool first_round = rd == plan.bracket_first_round[b];
+            const int keep = min(plan.round_keep[rd], n_cur);
+            if (n_cur <= 32) {
+                const int S = 32 / n_cur, seg = lane / n_cur, j = lane - seg * n_cur;
+                const unsigned seg_mask = (n_cur == 32 ? 0xffffffffu : (1u << n_cur) - 1u) << (seg < S ? seg * n_cur : 0);
+#pragma unroll 1
+                for (int h0 = 0; h0 < G; h0 += S) {
+                    const bool act = seg < S && h0 + seg < G;
+                    const int g = act ? h0 + seg : 0;
+                    const long long rep_g = rep0 + g;
+                    const int my_id = first_round ? first + j : (int)idbuf(g, flip)[j];
+                    const float my_loss = col[g * A + my_id];
+                    const uint32_t ord = act ? orderable(my_loss, desc) : 0xffffffffu;
+                    int rank = 0;
+#pragma unroll 3
+                    for (int k = 0; k < n_cur; ++k) rank += __shfl_sync(0xffffffffu, ord, seg * n_cur + k) < ord ? 1 : 0;
+                    rank += __popc(__match_any_sync(0xffffffffu, ord) & seg_mask & ((1u << lane) - 1u));
+                    const int sw = surv_w[g];
+                    __syncwarp();
+                    if (act && rank < keep) {
+                        idbuf(g, flip ^ 1)[rank] = (unsigned short)my_id;
+                        if (out.survivors != nullptr) out.survivors[rep_g * plan.n_surv + sw + rank] = my_id;
+                    }
+                    if (act && rank == 0) {
+                        surv_w[g] = sw + keep;
+                        if (out.round_best != nullptr) out.round_best[rep_g * plan.n_rounds + rd] = my_loss;
+                        if (out.round_best_arm != nullptr) out.round_best_arm[rep_g * plan.n_rounds + rd] = my_id;
+                        // OFE = first optimum over the round-bests in history order (core/optimiser.py:67-68)
+                        const int ba = best_arm[g];
+                        const float bl = best[g];
+                        if (ba < 0 || (desc ? my_loss > bl : my_loss < bl)) best[g] = my_loss, best_arm[g] = my_id;
+                    }
+                    __syncwarp();
+                }
+            } else {
+#pragma unroll 1
+                for (int g = 0; g < G; ++g) {
+                    const long long rep_g = rep0 + g;
+                    const float* loss = col + g * A;
+                    unsigned short* nxt = idbuf(g, flip ^ 1);
+                    float rb_loss;
+                    int rb_arm;
+                    warp_halving_round_f32(n_cur, keep, first_round, first, idbuf(g, flip), nxt, keys, desc, lane,
+                                           [&](int, int id) { return loss[id]; }, rb_loss, rb_arm);
+                    __syncwarp();
+                    const int sw = surv_w[g];
+                    if (out.survivors != nullptr)
+                        for (int j = lane; j < keep; j += 32) out.survivors[rep_g * plan.n_surv + sw + j] = (int)nxt[j];
+                    if (lane == 0) {
+                        surv_w[g] = sw + keep;
+                        if (out.round_best != nullptr) out.round_best[rep_g * plan.n_rounds + rd] = rb_loss;
+                        if (out.round_best_arm != nullptr) out.round_best_arm[rep_g * plan.n_rounds + rd] = rb_arm;
+                        const int ba = best_arm[g];
+                        const float bl = best[g];
+                        if (ba < 0 || (desc ? rb_loss > bl : rb_loss < bl)) best[g] = rb_loss, best_arm[g] = rb_arm;
+                    }
+                    __syncwarp();
+                }
+            }
+            flip ^= 1;
+            n_cur = keep;
+        }
+    }
+    for (int g = lane; g < G; g += 32) {
+        if (out.ofe != nullptr) out.ofe[rep0 + g] = best[g];
+        if (out.ofe_arm != nullptr) out.ofe_arm[rep0 + g] = best_arm[g];
+    }
+    __syncwarp();
+}
+
+// entries of the two survivor-id buffers tile_halving_f32 needs per repetition
+inline void halving_id_buffer_sizes(const at2_plan* plan, int* km_a, int* km_b) {
+    *km_a = 1, *km_b = 1;
+    for (int b = 0; b < plan->n_brackets; ++b)
+        for (int rd = plan->bracket_first_round[b]; rd < plan->bracket_first_round[b + 1]; ++rd) {
+            int* km = ((rd - plan->bracket_first_round[b]) & 1) ? km_b : km_a;
+            *km = plan->round_keep[rd] > *km ? plan->round_keep[rd] : *km;
+        }
+}
+
 // bytes of warp-private sort scratch for brackets up to `npad` wide
 template <typename T>
 __host__ __device__ inline size_t halving_scratch_bytes(int npad) {

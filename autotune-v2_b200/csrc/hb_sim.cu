@@ -44,6 +44,8 @@ struct Params {
     long long n_tiles;
     long long n_tiles_full;   // tiles [0, n_tiles_full) hold G repetitions; the rest of the job is cut into 1-repetition tiles
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
+    int tile_halving; // float path, warp-private tiles: the tile's repetitions are halved together (halving.cuh tile_halving_f32)
+    int km_a, km_b;   // entries of a repetition's two survivor-id buffers in that mode
     int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
     int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
     int n_teams;      // teams per CTA
@@ -238,13 +240,32 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
             }
         }
 
-        // ---------------- phase 2: successive halving, one warp per repetition ----------------
+        // ---------------- phase 2: successive halving ----------------
+        // warp-private float tiles: the tile's repetitions together, narrow rounds side by side (the per-repetition state
+        // lives where the per-repetition path keeps its two id lists); otherwise one warp per repetition
+        float* t_best = nullptr;
+        int* t_best_arm = nullptr;
+        if constexpr (sizeof(T) == 4) {
+            if (p.tile_halving) {
+                const int n_ids = (p.G * (p.km_a + p.km_b) + 1) & ~1;
+                t_best = reinterpret_cast<float*>(ids_a + n_ids);
+                t_best_arm = reinterpret_cast<int*>(t_best + p.G);
+                HalvingOut<float> ho{p.ofe, p.ofe_arm, p.round_best, p.round_best_arm, p.survivors};
+                tile_halving_f32(p.plan, s_ck, p.stride, A, g_eff, keys, ids_a, p.km_a, p.km_b, t_best, t_best_arm,
+                                 t_best_arm + p.G, desc, lane, rep0, ho);
+            }
+        }
         for (int rep_l = wteam; rep_l < g_eff; rep_l += p.team_warps) {
             const long long rep_g = rep0 + rep_l;
-            HalvingOut<T> ho{p.ofe, p.ofe_arm, p.round_best, p.round_best_arm, p.survivors};
             T ofe_value;
-            const int best_arm = warp_halving<T>(p.plan, s_ck + rep_l * A, p.stride, keys, ids_a, ids_b, desc, lane,
-                                                 rep_g, ho, &ofe_value);
+            int best_arm;
+            if (t_best != nullptr) {
+                ofe_value = (T)t_best[rep_l], best_arm = t_best_arm[rep_l];
+            } else {
+                HalvingOut<T> ho{p.ofe, p.ofe_arm, p.round_best, p.round_best_arm, p.survivors};
+                best_arm = warp_halving<T>(p.plan, s_ck + rep_l * A, p.stride, keys, ids_a, ids_b, desc, lane, rep_g, ho,
+                                           &ofe_value);
+            }
             if (lane < p.n_gather) p.gather[lane][p.gather_base + rep_g] = ofe_value;   // one peer (or the multicast) per lane
             if (lane == 0 && p.best_xy != nullptr) {
                 if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
@@ -446,6 +467,13 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->split_cap = (n_smooth > 0 && n_smooth < cfg->n_families && (size_t)cap * 2 * lc->team_warps <= scratch &&
                     lc->stride < 65536 && getenv("AT2_HB_NO_SPLIT") == nullptr) ? cap : 0;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
+    // float path with warp-private tiles: the repetitions of a tile are halved together when their survivor-id buffers and
+    // running state fit where the per-repetition path keeps its two id lists (2 * npad entries);
+    // AT2_HB_NO_TILE_HALVING=1 disables it (development aid / tests)
+    halving_id_buffer_sizes(plan, &p->km_a, &p->km_b);
+    const size_t tile_state = (size_t)((lc->G * (p->km_a + p->km_b) + 1) & ~1) * 2 + (size_t)lc->G * 12;
+    p->tile_halving = (sizeof(T) == 4 && lc->team_warps == 1 && tile_state <= (size_t)lc->npad * 4 &&
+                       getenv("AT2_HB_NO_TILE_HALVING") == nullptr) ? 1 : 0;
     return AT2_OK;
 }
 

@@ -315,6 +315,25 @@ def test_global_memory_tables_are_bit_identical_to_shared_memory_tables(monkeypa
             assert torch.equal(al[k], bl[k]) and torch.equal(al[k], a[k]), (func, k)
 
 
+def test_tile_halving_is_bit_identical_to_per_repetition_halving(monkeypatch):
+    """Float path, warp-private tiles: the repetitions of a tile are halved together, narrow rounds side by side
+    (halving.cuh tile_halving_f32).  Every output must equal the per-repetition path's, ragged last tiles, maximisation,
+    eta = 2 / 4 plans and heavily tied losses included."""
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    for func, fams, R, eta, noise, mom, n in (('rastrigin', FAM6, 81, 3, 10, 'min', 2000 + 1), ('branin', FLAT, 81, 3, 0, 'min', 1999),
+                                              ('egg', FAM6[:3], 243, 3, 10, 'min', 301), ('wave', FAM6, 27, 3, 10, 'max', 1000),
+                                              ('camel', FAM6, 16, 2, 1, 'min', 777), ('rastrigin', FAM6, 64, 4, 10, 'min', 500),
+                                              ('rastrigin', FAM6, 100, 3, 10, 'min', 400), ('branin', FAM6[:2], 2, 2, 10, 'min', 100)):
+        spec = HyperbandSimSpec(func, fams, R, eta, noise, 'uniform', mom)
+        monkeypatch.delenv('AT2_HB_NO_TILE_HALVING', raising=False)
+        a = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True)
+        monkeypatch.setenv('AT2_HB_NO_TILE_HALVING', '1')
+        b = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True)
+        monkeypatch.delenv('AT2_HB_NO_TILE_HALVING')
+        for k in a:
+            assert torch.equal(a[k], b[k]), (func, R, k)
+
+
 def test_raw_smoothed_split_passes_do_not_change_outputs(monkeypatch):
     """Mixed families: raw and smoothed arms of a tile run in separate warp passes (hb_sim.cu).  Disabling the split must
     give the same bits."""
