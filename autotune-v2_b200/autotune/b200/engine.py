@@ -89,17 +89,20 @@ class HyperbandSimSpec:
                      time=p.round_time[r], ckpt=p.round_ckpt[r])
                 for b in range(p.n_brackets) for r in range(p.bracket_first_round[b], p.bracket_first_round[b + 1])]
 
-    def tables(self, device, dtype=torch.float32):
-        """Constant tables on `device` (built once per (device, dtype) by at2_hb_tables_build, pinned H2D copy)."""
+    def tables(self, device, dtype=torch.float32, plan=None):
+        """Constant tables on `device` (built once per (device, dtype, plan) by at2_hb_tables_build).  The tables belong
+        to a plan: the Savitzky-Golay columns and the checkpoint flags of the step records follow its checkpoints, so a
+        run under another plan (stand-alone TPE / random search: single_round_plan) gets its own."""
         device = torch.device(device)
-        key = (str(device), dtype)
+        plan = self.plan if plan is None else plan
+        key = (str(device), dtype, bytes(plan))
         if key not in self._tables:
             is64 = int(dtype == torch.float64)
-            nbytes = nat.lib.at2_hb_tables_bytes(C.byref(self.plan), C.byref(self.cfg), is64)
+            nbytes = nat.lib.at2_hb_tables_bytes(C.byref(plan), C.byref(self.cfg), is64)
             if nbytes < 0:
                 raise nat.At2Error(nat.lib.at2_last_error().decode())
             host = torch.empty(nbytes // (8 if is64 else 4), dtype=dtype)
-            nat.check(nat.lib.at2_hb_tables_build(C.byref(self.plan), C.byref(self.cfg), is64, host.data_ptr()))
+            nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(self.cfg), is64, host.data_ptr()))
             self._tables[key] = host.to(device)
         return self._tables[key]
 
@@ -125,6 +128,29 @@ def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, d
     outs = torch.ops.at2.hb_sim_f32(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes, int(n_reps),
                                     int(rep_offset), int(seed), bool(details))
     return dict(zip(ops.HB_OUTPUT_NAMES, outs))
+
+
+def arm_families(spec, seed, rep_ids, arm_ids):
+    """Index into spec.families of the shape family each (repetition, arm) pair drew on the device.
+
+    Round-robin: arm % F (core/shape_family_scheduler.py:75).  Uniform (:61): floor(F * z / 2**32) with z the third word of
+    block 0 of the arm's own Philox stream, keyed by (seed; global repetition id * n_arms + arm) - the draw of
+    csrc/sim_core.cuh draw_arm / arm_family, recomputed here through the ABI's at2_philox4x32_10 so that callers can rebuild an
+    arm's evaluator with the family it really had."""
+    F, A = len(spec.families), spec.n_arms
+    rep_ids, arm_ids = np.broadcast_arrays(np.asarray(rep_ids, np.int64), np.asarray(arm_ids, np.int64))
+    out = np.empty(arm_ids.shape, np.int64)
+    if spec.scheduler != 'uniform':
+        out[...] = arm_ids % F
+        return out
+    key = (C.c_uint32 * 2)(seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    ctr, res = (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    for idx in np.ndindex(*arm_ids.shape):
+        gid = int(rep_ids[idx]) * A + int(arm_ids[idx])
+        ctr[0], ctr[1], ctr[2], ctr[3] = 0, gid & 0xFFFFFFFF, (gid >> 32) & 0xFFFFFFFF, 0      # AT2_STREAM_ARM
+        nat.lib.at2_philox4x32_10(ctr, key, res)
+        out[idx] = (int(res[2]) * F) >> 32
+    return out
 
 
 def host_start_and_target(spec, xy, fam, z):
@@ -268,7 +294,7 @@ def run_optimiser_repetitions(spec, n_reps, tpe, seed=0, rep_offset=0, device=No
     `spec` (stand-alone TPE / random search use single_round_plan)."""
     device = _cuda_device(device)
     plan = spec.plan if plan is None else plan
-    outs = torch.ops.at2.tpe_sim(spec.tables(device, torch.float32), ops.struct_tensor(plan), spec.cfg_bytes,
+    outs = torch.ops.at2.tpe_sim(spec.tables(device, torch.float32, plan), ops.struct_tensor(plan), spec.cfg_bytes,
                                  ops.struct_tensor(tpe), int(n_reps), int(rep_offset), int(seed), bool(details))
     return dict(zip(ops.HB_OUTPUT_NAMES + ['arm_xy', 'obs_loss'] if details else ops.HB_OUTPUT_NAMES, outs))
 

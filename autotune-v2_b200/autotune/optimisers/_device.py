@@ -53,16 +53,20 @@ def fresh_seed():
     return int(np.random.randint(0, 2 ** 31 - 1))
 
 
-def history_from_rounds(optimiser, problem, spec, out, rep=0):
+def history_from_rounds(optimiser, problem, spec, out, seed, rep=0, rep_offset=0):
     """Fill optimiser.eval_history with the best evaluation of every round (hyperband_optimiser.py:98-99), built from
-    the device outputs of repetition `rep`; returns the best Evaluation (core/optimiser.py:67-68)."""
+    the device outputs of repetition `rep` of the job keyed by (seed, rep_offset); returns the best Evaluation
+    (core/optimiser.py:67-68).  Every evaluator is rebuilt with the shape family its arm really drew on the device
+    (the reference keeps the evaluator object itself, hyperband_optimiser.py:99-100)."""
+    from autotune.b200.engine import arm_families
     rb = out['round_best'][rep].tolist()
     rb_arm = out['round_best_arm'][rep].tolist()
     xy = out['arm_xy'][rep].tolist()
     fams = spec.families
-    for loss, arm_id in zip(rb, rb_arm):
+    fam_of = arm_families(spec, seed, rep_offset + rep, rb_arm).tolist()
+    for loss, arm_id, fam_id in zip(rb, rb_arm, fam_of):
         x, y = xy[arm_id]
-        evaluator = problem.get_evaluator(Arm(x=x, y=y), *fams[0], spec.R, spec.init_noise)
+        evaluator = problem.get_evaluator(Arm(x=x, y=y), *fams[fam_id], spec.R, spec.init_noise)
         optimiser.eval_history.append(Evaluation(evaluator, OptimisationGoals(fval=loss, test_error=-1,
                                                                                validation_error=-1)))
         optimiser._update_optimiser_metrics()

@@ -65,8 +65,9 @@ class HyperbandOptimiser(Optimiser):
         if not isinstance(problem, OptFunctionSimulationProblem):
             raise NotImplementedError(f'{type(problem).__name__}: no device path for this simulation problem')
         spec = _device.simulation_spec(self, problem)
-        out = run_optimiser_repetitions(spec, 1, self._tpe_config(), seed=_device.fresh_seed(), details=True)
-        return _device.history_from_rounds(self, problem, spec, out)
+        seed = _device.fresh_seed()
+        out = run_optimiser_repetitions(spec, 1, self._tpe_config(), seed=seed, details=True)
+        return _device.history_from_rounds(self, problem, spec, out, seed)
 
     def _run_knownfn(self, problem, run_knownfn_hyperband):
         from autotune.core import Arm, OptimisationGoals

@@ -31,12 +31,14 @@ class TpeOptimiser(Optimiser):
         _device.require_fval_objective(self.optimisation_func)
         spec = _device.simulation_spec(self, problem)
         plan = single_round_plan(spec.R, int(self.max_iter), int(self.n_resources))
-        out = run_optimiser_repetitions(spec, 1, tpe_config(self._tpe_enabled), seed=_device.fresh_seed(), details=True,
-                                        plan=plan)
+        from autotune.b200.engine import arm_families
+        seed = _device.fresh_seed()
+        out = run_optimiser_repetitions(spec, 1, tpe_config(self._tpe_enabled), seed=seed, details=True, plan=plan)
         losses = out['ckpt_loss'][0, :, 0].tolist()
         xy = out['arm_xy'][0].tolist()
-        for (x, y), loss in zip(xy, losses):           # every evaluation goes into the history (tpe_optimiser.py:56-58)
-            evaluator = problem.get_evaluator(Arm(x=x, y=y), *spec.families[0], spec.R, spec.init_noise)
+        fam_of = arm_families(spec, seed, 0, range(len(losses))).tolist()   # the family each arm drew on the device
+        for (x, y), loss, fam_id in zip(xy, losses, fam_of):   # every evaluation goes into the history (tpe_optimiser.py:56-58)
+            evaluator = problem.get_evaluator(Arm(x=x, y=y), *spec.families[fam_id], spec.R, spec.init_noise)
             self.eval_history.append(Evaluation(evaluator, OptimisationGoals(fval=loss, test_error=-1, validation_error=-1)))
             self._update_optimiser_metrics()
         return self._get_best_evaluation()

@@ -46,21 +46,30 @@ static int at2_resident_by_regs(Kern kern, int block, int* out) {
 }
 
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
-// rec[f][t] f in [0,F), t in [0,R]: 8 reals {d, c, d*log2(e), d*scale, P, P11, 1-P, 0}
-//          Marsaglia-Tsang constants of the Gamma draw of step t and the two time-aggressiveness powers
-//          (t/(R-1))**nec, (t/(R-1))**(1.1*nec) of family f - one 32-byte (float) record per (family, step), so a lane
-//          fetches everything step t needs from one address.  Row 0 is unused; row R is a sentinel whose c is NaN, so
-//          the acceptance test of a finished lane can never pass and no bounds check is needed in the inner loop.
+// rec[f][t] f in [0,F), t in [0,R]: one 8-real record per (family, step), so a lane fetches everything step t needs with
+//          two 128-bit loads from one address.  Row 0 is unused; row R is a sentinel whose c is NaN, so the acceptance
+//          test of a finished lane can never pass and no bounds check is needed in the inner loop.
+//   float tables (Philox paths): {d, c, d*log2(e), d*log2(e) + 32, +-w, K1w, K0, P11}
+//          d, c: Marsaglia-Tsang constants of the Gamma draw of step t; w = d * scale (Gamma draw g = w v^3), its SIGN BIT
+//          flags the steps whose position is a checkpoint of the plan the table was built for (the trajectory loop stores
+//          the loss of a flagged step, sim_core.cuh); K1w = w ml (1 - P), K0 = P - 2 ml (1 - P), ml = ml_agg / 100,
+//          P = (t/(R-1))**nec, P11 = (t/(R-1))**(1.1*nec): the folded down step k = v^3 K1w + K0 (sim_core.cuh mt_attempt).
+//   double tables (pre-drawn parity path): {d, c, d*log2(e), d*scale, P, P11, 1-P, 0}
 // sg[t][c]  t in [0,R], c in [0,sg_stride): Savitzky-Golay weight of raw[t] in the smoothed value at checkpoint c
 //          (present only when some family is smooth; row R is zero).
+// pw[f][t] 4 reals {K1 = ml (1 - P), K0, P11, 0}: the folded step on a given Gamma draw (pre-drawn float path only; the
+//          Philox kernels do not stage it).
 #define AT2_REC 8
+#define AT2_PW 4
 __host__ __device__ inline int at2_sg_stride(int n_ckpts) { return n_ckpts <= 4 ? 4 : (n_ckpts <= 8 ? 8 : 16); }
 
 struct At2TableLayout {
     int R, F, has_smooth, sg_stride;
     __host__ __device__ int off_rec() const { return 0; }
     __host__ __device__ int off_sg() const { return AT2_REC * F * (R + 1); }   // 32-byte aligned
-    __host__ __device__ int total() const { return off_sg() + (has_smooth ? sg_stride * (R + 1) : 0); }
+    __host__ __device__ int off_pw() const { return off_sg() + (has_smooth ? sg_stride * (R + 1) : 0); }
+    __host__ __device__ int total_philox() const { return off_pw(); }          // what a Philox kernel stages
+    __host__ __device__ int total() const { return off_pw() + AT2_PW * F * (R + 1); }
 };
 
 static inline int at2_cfg_has_smooth(const at2_sim_config* cfg) {

@@ -223,10 +223,13 @@ extern "C" int64_t at2_hb_tables_bytes(const at2_plan* plan, const at2_sim_confi
 template <typename T>
 static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out) {
     const int R = plan->R, F = cfg->n_families;
+    const bool f32 = sizeof(T) == 4;
     At2TableLayout L{R, F, at2_cfg_has_smooth(cfg), at2_sg_stride(plan->n_ckpts)};
     for (int i = 0; i < L.total(); ++i) out[i] = (T)0;
     const double k = 2.0;  // simulation_evaluator.py:94
+    const double log2e = 1.4426950408889634;
     T* rec = out + L.off_rec();
+    T* pwt = out + L.off_pw();
     const int rows = R + 1;
     for (int t = 1; t < R; ++t) {
         const double m = (double)((R + 1) - t);                 // n - time with n = R + 1 (:98)
@@ -237,20 +240,40 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
         const double d = alpha - 1.0 / 3.0;                     // Marsaglia & Tsang (2000)
         const double c = 1.0 / sqrt(9.0 * d);
         const double frac = (double)t / (double)(R - 1);
+        bool is_ckpt = false;                                   // position t is read by some round of the plan
+        for (int q = 0; q < plan->n_ckpts; ++q) is_ckpt |= plan->ckpt_time[q] - 1 == t;
         for (int f = 0; f < F; ++f) {
             T* row = rec + (size_t)AT2_REC * (f * rows + t);
+            const double P = pow(frac, cfg->fam[f].nec_agg);          // :105
+            const double P11 = pow(frac, 1.1 * cfg->fam[f].nec_agg);  // :112
+            const double ml = cfg->fam[f].ml_agg / 100.0, w = d * scale;
+            const double K1 = ml * (1.0 - P), K0 = P - 2.0 * ml * (1.0 - P);   // a (1-P) + P with a = (g-2) ml
             row[0] = (T)d;
             row[1] = (T)c;
-            row[2] = (T)(d * 1.4426950408889634);
-            row[3] = (T)(d * scale);
-            row[4] = (T)pow(frac, cfg->fam[f].nec_agg);          // :105
-            row[5] = (T)pow(frac, 1.1 * cfg->fam[f].nec_agg);    // :112
-            row[6] = (T)(1.0 - pow(frac, cfg->fam[f].nec_agg));  // 1 - P, for the fused form of :103-107
+            row[2] = (T)(d * log2e);
+            if (f32) {
+                row[3] = (T)(d * log2e + 32.0);
+                row[4] = (T)(is_ckpt ? -w : w);
+                row[5] = (T)(w * K1);
+                row[6] = (T)K0;
+                row[7] = (T)P11;
+            } else {
+                row[3] = (T)w;
+                row[4] = (T)P;
+                row[5] = (T)P11;
+                row[6] = (T)(1.0 - P);                            // 1 - P, for the fused form of :103-107
+            }
+            T* prow = pwt + (size_t)AT2_PW * (f * rows + t);
+            prow[0] = (T)K1, prow[1] = (T)K0, prow[2] = (T)P11;
         }
     }
     for (int f = 0; f < F; ++f) {   // sentinel row R: NaN slope -> the acceptance test can never pass
         T* row = rec + (size_t)AT2_REC * (f * rows + R);
-        row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)1.4426950408889634, row[3] = (T)1, row[4] = (T)1, row[5] = (T)1, row[6] = (T)0;
+        row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)log2e;
+        if (f32)
+            row[3] = (T)(log2e + 32.0), row[4] = (T)1, row[5] = (T)0, row[6] = (T)0, row[7] = (T)1;
+        else
+            row[3] = (T)1, row[4] = (T)1, row[5] = (T)1, row[6] = (T)0;
     }
     if (L.has_smooth) {
         int32_t rows[AT2_MAX_CKPTS];

@@ -49,14 +49,14 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
-    const int tab_elems = GTAB ? 0 : (L.total() + 3) & ~3;   // GTAB: tables stay in global memory (sim_core.cuh tab128)
+    const int tab_elems = GTAB ? 0 : (L.total_philox() + 3) & ~3;   // GTAB: tables stay in global memory (sim_core.cuh tab128)
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);
     int* s_sglast = s_ckpos + AT2_MAX_CKPTS + 4;
     unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_sglast + AT2_MAX_CKPTS + 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     if constexpr (!GTAB)
-        for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+        for (int i = tid; i < L.total_philox(); i += blockDim.x) s_tab[i] = p.tables[i];
     if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
     const float* s_rec = (GTAB ? p.tables : s_tab) + L.off_rec();
@@ -154,10 +154,10 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const bool smooth = HAS_SMOOTH && fam.smooth != 0;
                         float* dst = cur + q;
                         if (!HAS_SMOOTH || (split && base + 32 <= n_raw))
-                            philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.ml, fam.up, fam.pw_off, gid,
+                            philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.up, fam.pw_off, gid,
                                                                            p.sp.rk, stop_raw, dst, 0, C, c);
                         else
-                            philox_trajectory<float, HAS_SMOOTH, 1, true, GTAB>(tb, active, smooth, f1, fn, fam.ml, fam.up, fam.pw_off,
+                            philox_trajectory<float, HAS_SMOOTH, 1, true, GTAB>(tb, active, smooth, f1, fn, fam.up, fam.pw_off,
                                                                                 gid, p.sp.rk, smooth ? stop_sm : stop_raw, dst, 0, C, c);
                     }
                     __syncwarp();
@@ -324,7 +324,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     if (p.cur_cap > 4 * p.npad) p.cur_cap = 4 * p.npad;
     const int C = plan->n_ckpts;
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
-    const size_t tab_bytes = (size_t)((L.total() + 3) & ~3) * 4, fixed_small = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    const size_t tab_bytes = (size_t)((L.total_philox() + 3) & ~3) * 4, fixed_small = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     const bool force_gtab = getenv("AT2_FORCE_GTAB") != nullptr;   // env: tests
     // launch geometry of tile width g: a warp's tile state (loss buffer, per-repetition state, sort scratch, survivor ids),
     // tables in shared or global memory, warps per CTA, CTAs per SM

@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
     // GTAB: the tables stay in global memory (plans too large for shared memory), see sim_core.cuh tab128
-    const int tab_elems = GTAB ? 0 : (L.total() + 3) & ~3;
+    // the Philox kernels stage records + Savitzky-Golay rows; the pre-drawn paths also the folded-step table (pw)
+    const int tab_total = MODE == MODE_PHILOX ? L.total_philox() : L.total();
+    const int tab_elems = GTAB ? 0 : (tab_total + 3) & ~3;
     T* s_tab = reinterpret_cast<T*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4] positions, then INT_MAX
     unsigned char* team_base = reinterpret_cast<unsigned char*>(s_ckpos + AT2_MAX_CKPTS + 4);
@@ -94,11 +96,12 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int team = warp / p.team_warps, wteam = warp - team * p.team_warps;
     if constexpr (!GTAB)
-        for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+        for (int i = tid; i < tab_total; i += blockDim.x) s_tab[i] = p.tables[i];
     if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
     const T* s_rec = (GTAB ? p.tables : s_tab) + L.off_rec();
     const T* s_sg = (GTAB ? p.tables : s_tab) + L.off_sg();
+    const T* s_pw = (GTAB ? p.tables : s_tab) + L.off_pw();
     const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_rec),
                        GTAB ? (uint32_t)(L.off_sg() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
                        L.sg_stride, reinterpret_cast<const unsigned char*>(p.tables)};
@@ -158,10 +161,10 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                     const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                     const float fn = f - (float)fam.s1, f1 = (f + p.sp.noise * d.z) - (float)fam.s0;
                     if (k + 32 <= n_raw)
-                        philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.ml, (float)fam.up,
+                        philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.up,
                                                                     fam.pw_off, gid, p.sp.rk, R, s_ck + ii, p.stride, C);
                     else
-                        philox_trajectory<T, true, CK, false, GTAB>(tb, active, fam.smooth != 0, f1, fn, (float)fam.ml,
+                        philox_trajectory<T, true, CK, false, GTAB>(tb, active, fam.smooth != 0, f1, fn,
                                                                     (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
                                                                     p.stride, C);
                 }
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                 const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
-                philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn, (float)fam.ml,
+                philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
                                                                   (float)fam.up, fam.pw_off, gid, p.sp.rk, R,
                                                                   s_ck + ii, p.stride, C);
             } else {
@@ -205,13 +208,16 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                 for (int tt = 1; tt < R; ++tt) {
                     if (!active) break;
                     const T g = grow[tt - 1];
-                    const T P = s_rec[AT2_REC * (fam.pw_off + tt) + 4], P11 = s_rec[AT2_REC * (fam.pw_off + tt) + 5];
-                    if constexpr (sizeof(T) == 8)
+                    if constexpr (sizeof(T) == 8) {
+                        const T P = s_rec[AT2_REC * (fam.pw_off + tt) + 4], P11 = s_rec[AT2_REC * (fam.pw_off + tt) + 5];
                         f = (T)step_exact((double)f, (double)g, tt, R, (double)fn, (double)fam.ml, (double)fam.up,
                                           (double)P, (double)P11);
-                    else
-                        f = (T)step_fast((float)f, (float)g, (float)fn, (float)fam.ml, -2.0f * (float)fam.ml, (float)fam.up,
-                                         (float)P, (float)P11, (float)s_rec[AT2_REC * (fam.pw_off + tt) + 6]);
+                    } else {
+                        // the production arithmetic (sim_core.cuh mt_attempt) on the given Gamma draw
+                        const T* pw = s_pw + AT2_PW * (fam.pw_off + tt);
+                        f = (T)step_folded((float)f, (float)g, (float)fn, (float)fam.up, (float)pw[0], (float)pw[1],
+                                           (float)pw[2]);
+                    }
                     if (HAS_SMOOTH && smooth) {
 #pragma unroll
                         for (int c = 0; c < CK; ++c) acc[c] = fma(s_sg[tt * L.sg_stride + c], f, acc[c]);
@@ -300,7 +306,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <typename T>
-int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, LaunchCfg<T>* out) {
+int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, int mode, LaunchCfg<T>* out) {
     typedef typename KeyOf<T>::type K;
     const int A = plan->n_arms, C = plan->n_ckpts, R = plan->R;
     int widest = 0;
@@ -308,7 +314,8 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
     int npad = 64;
     while (npad < widest) npad <<= 1;
     At2TableLayout L{R, F, has_smooth, at2_sg_stride(C)};
-    size_t fixed = (size_t)((L.total() + 3) & ~3) * sizeof(T) + (AT2_MAX_CKPTS + 4) * sizeof(int);
+    size_t fixed = (size_t)(((mode == MODE_PHILOX ? L.total_philox() : L.total()) + 3) & ~3) * sizeof(T) +
+                   (AT2_MAX_CKPTS + 4) * sizeof(int);
     const size_t sort_per_warp = (size_t)npad * (sizeof(K) + 2 * sizeof(unsigned short));
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
@@ -422,7 +429,7 @@ int launch_dispatch(const Params<T>& p, const LaunchCfg<T>& lc, int has_smooth, 
 
 template <typename T>
 int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, long long n_reps,
-                const at2_hb_outputs* out, Params<T>* p, LaunchCfg<T>* lc) {
+                const at2_hb_outputs* out, int mode, Params<T>* p, LaunchCfg<T>* lc) {
     AT2_REQUIRE(plan && cfg && d_tables && out, "at2_hb_sim: NULL plan/config/tables/outputs");
     AT2_REQUIRE(n_reps > 0, "at2_hb_sim: n_reps must be positive (got %lld)", n_reps);
     AT2_REQUIRE(plan->n_arms > 0 && plan->n_rounds > 0 && plan->n_ckpts > 0 && plan->n_ckpts <= AT2_MAX_CKPTS,
@@ -453,7 +460,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->ofe = (T*)out->d_ofe, p->ofe_arm = out->d_ofe_arm, p->best_xy = (T*)out->d_best_xy;
     p->round_best = (T*)out->d_round_best, p->round_best_arm = out->d_round_best_arm;
     p->survivors = out->d_survivors, p->ckpt_loss = (T*)out->d_ckpt_loss;
-    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, lc);
+    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, mode, lc);
     if (rc != AT2_OK) return rc;
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
@@ -484,7 +491,7 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
-    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, MODE_PHILOX, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_f32: rep_offset must be >= 0");
     p.rep_offset = rep_offset;
@@ -499,7 +506,7 @@ extern "C" int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config*
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
-    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, MODE_PHILOX, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(rep_offset >= 0 && gather_base >= 0, "at2_hb_sim_gather_f32: rep_offset and gather_base must be >= 0");
     AT2_REQUIRE(d_gather != nullptr && n_gather >= 1 && n_gather <= AT2_MAX_PEERS,
@@ -522,7 +529,7 @@ extern "C" int at2_hb_sim_predrawn_f64(const at2_plan* plan, const at2_sim_confi
     at2_reset_launch_count();
     Params<double> p = {};
     LaunchCfg<double> lc;
-    const int rc = fill_params<double>(plan, cfg, d_tables, n_reps, out, &p, &lc);
+    const int rc = fill_params<double>(plan, cfg, d_tables, n_reps, out, MODE_PREDRAWN, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f64: NULL input array");
     p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;
@@ -536,7 +543,7 @@ extern "C" int at2_hb_sim_predrawn_f32(const at2_plan* plan, const at2_sim_confi
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
-    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, &p, &lc);
+    const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, MODE_PREDRAWN, &p, &lc);
     if (rc != AT2_OK) return rc;
     AT2_REQUIRE(d_f1 && d_fn && d_family && d_gamma, "at2_hb_sim_predrawn_f32: NULL input array");
     p.f1 = d_f1, p.fn = d_fn, p.family = d_family, p.gamma = d_gamma, p.xy = d_xy;

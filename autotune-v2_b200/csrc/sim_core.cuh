@@ -118,6 +118,10 @@ __device__ __forceinline__ float4 tab128(const unsigned char* gbase, uint32_t ad
     else
         return lds128(addr);
 }
+// st.shared under a predicate (ptxas turns an `if` around a store into a branch)
+__device__ __forceinline__ void sts32_if(uint32_t addr, float v, bool p) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(addr), "f"(v), "r"((int)p) : "memory");
+}
 __device__ __forceinline__ float lds32(uint32_t addr) {
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -187,16 +191,84 @@ struct SimTables {
     const unsigned char* gbase = nullptr;   // GTAB only: the table in global memory
 };
 
+// ---- the Philox word stream of a trajectory ---------------------------------------------------------------------------
+// Attempt pair j of a lane (attempts 2j, 2j+1) owns words 3j, 3j+1, 3j+2 of the lane's flat Philox4x32-10 word stream
+// (word i = component i % 4 of the block with counter i / 4, stream tag AT2_STREAM_TRAJ):
+//   words 3j, 3j+1 -> Box-Muller: radius from the first (all 32 bits), angle from the second -> two normals;
+//   word  3j+2     -> the two accept uniforms: its low half is the high half of the first, its high half the high half of
+//                     the second; the low halves are the low 16 bits of words 3j / 3j+1.  Box-Muller rounds those bits
+//                     away (I2F keeps 24), so they extend the accept uniforms to 32 bits at no cost: given the normal, the
+//                     low half acts as a dither that is equidistributed over the fine bits of the normal, on which the
+//                     acceptance threshold does not depend to O(2^-16) - the test is unbiased at 2^-32 resolution.
+// Three blocks (A, B, C) therefore feed four pairs = eight attempts: 1.5 words per attempt instead of 2.
+//   pair 0: A.x A.y | A.z     pair 1: A.w B.x | B.y     pair 2: B.z B.w | C.x     pair 3: C.y C.z | C.w
+// The mapping attempt -> words is a pure function of the attempt index: a partial run (early stopping, affine offsets,
+// full-trajectory output) walks exactly the prefix of the stream the full run walks.
+__device__ __forceinline__ void box_muller_pair(uint32_t wa, uint32_t wb, uint32_t wu, float& x0, float& x1, float& ku0,
+                                                float& ku1) {
+    const float u1 = fmaf((float)wa, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // (0,1]
+    const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                      // sqrt(-2 ln u1)
+    const float ang = (float)(int32_t)wb * 1.4629180792671596e-9f;                        // [-pi, pi)
+    x0 = rad * fast_cos(ang);
+    x1 = rad * fast_sin(ang);
+    ku0 = (float)__byte_perm(wa, wu, 0x5410);    // (lo16(wu) << 16) | lo16(wa): the uniform scaled by 2^32
+    ku1 = (float)__byte_perm(wb, wu, 0x7610);    // (hi16(wu) << 16) | lo16(wb)
+}
+
+// One Marsaglia-Tsang attempt at the step whose record sits at (gm, pw) - Marsaglia & Tsang 2000, full log test
+//   log2 U < log2e (x^2/2 + d - d v^3) + d log2 v^3,  with log2 U = log2(ku) - 32 folded into the record (gm.w = d log2e + 32)
+// - and the step of the recurrence it feeds (simulation_evaluator.py:99-115) in folded form:
+//   g = w v^3 (Gamma draw), g1 = 1 + g
+//   g > 2:  f' = f + (fn - f) k,            k = a (1 - P) + P, a = (g - 2) ml_agg / 100  ==  v^3 K1w + K0   (:103-107)
+//   g <= 2: up = f + up_spik / (1 + g),  f' = up + (fn - up) P11                                              (:108-115)
+// K1w = w ml (1 - P) and K0 = P - 2 ml (1 - P) are per-(family, step) constants of the table.  At the last step
+// P = P11 = 1, so both branches land on fn (:113-115).  g == 2 exactly (:100-101, f unchanged) has probability ~2^-24 per
+// draw with float g and is not singled out here; the pre-drawn paths, which are compared with the reference, keep it.
+// v <= 0 needs no test of its own: lg2 of a non-positive v^3 is NaN / -inf and the comparison fails; the sentinel record
+// of a finished lane has c = NaN and fails the same way.
+struct AttemptOut {
+    bool ok;
+    float fnew;
+};
+__device__ __forceinline__ AttemptOut mt_attempt(const float4 gm, const float4 pw, float x, float ku, float ff, float fn,
+                                                 float upc) {
+    const float v = fmaf(gm.y, x, 1.0f);
+    const float v3 = v * v * v;
+    const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.w)));
+    AttemptOut o;
+    o.ok = fast_lg2(ku) < rhs;
+    const float g1 = fmaf(fabsf(pw.x), v3, 1.0f);
+    const bool gt = g1 > 3.0f;
+    const float kdn = fmaf(v3, pw.y, pw.z);
+    const float base = fmaf(gt ? 0.0f : upc, fast_rcp(g1), ff);
+    const float k = gt ? kdn : pw.w;
+    o.fnew = fmaf(fn - base, k, base);
+    return o;
+}
+
+// the same step on a given Gamma draw g (pre-drawn float path, full-precision inputs): K1 = ml (1 - P), K0, P11
+__device__ __forceinline__ float step_folded(float f, float g, float fn, float upc, float K1, float K0, float P11) {
+    if (g == 2.0f) return f;                                                        // :100-101
+    const bool gt = g > 2.0f;
+    const float base = gt ? f : fmaf(upc, fast_rcp(1.0f + g), f);
+    const float k = gt ? fmaf(g, K1, K0) : P11;
+    return fmaf(fn - base, k, base);
+}
+
 // One arm per lane: runs the lane's Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang -> recurrence until every
 // lane of the warp has produced position stop_t - 1 (stop_t = R: the whole trajectory), writing the raw arms'
 // checkpoint losses to ck[c * stride] as their positions are produced and the smooth arms' Savitzky-Golay read-outs at
 // the end.  All 32 lanes must call it; lanes with active == false do nothing.
 //
-// One Philox block = 2 normals + 2 uniforms = 2 Marsaglia-Tsang attempts.  A lane's epoch is the shared-memory address
-// of its (family, step) record: an accepted attempt advances it by one record, a rejected one leaves it, a finished (or
-// padding) lane sits on the sentinel record whose NaN slope fails every acceptance test - so the attempt is branch-free
-// and needs no bounds check.  The rare checkpoint capture is tested once per Philox block.  The next block is issued
-// before the current one is consumed so its integer chain overlaps the MUFU/FP32 chain of the attempts.
+// A lane's epoch is the shared-memory address of its (family, step) record: an accepted attempt advances it by one
+// record, a rejected one leaves it, a finished (or padding) lane sits on the sentinel record whose NaN slope fails every
+// acceptance test - so the attempt is branch-free and needs no bounds check.  Checkpoints are flagged in the records
+// themselves (sign bit of w, set by at2_hb_tables_build for the plan's checkpoint positions): an accepted attempt at a
+// flagged step stores the new loss through the lane's row pointer and moves that pointer one row down - two predicated
+// instructions, no branch.  Every active lane needs at least R - 1 attempts, so the first (R - 1) / 8 superblocks (three
+// Philox blocks, eight attempts each) run as a counted loop with no vote and no divergence - one large basic block in
+// which the integer Philox rounds of the next blocks overlap the MUFU/FP32 chains of the attempts; only the tail, where
+// lanes finish one after the other, tests for completion (every four attempts).
 //
 // PARTIAL = true (early-stopping evaluation): every lane has its own stop_t and stops advancing there, and only checkpoint
 // `only_c` is produced, into ck[0] (instantiate with CK = 1: a smoothed arm then accumulates that one Savitzky-Golay
@@ -204,7 +276,7 @@ struct SimTables {
 // the same as in the full run, so the value equals the one the full run reads at that checkpoint, bit for bit.
 template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
-                                                  float mlc, float upc, int pw_off, unsigned long long gid,
+                                                  float upc, int pw_off, unsigned long long gid,
                                                   const uint32_t* __restrict__ rk, int stop_t, T* ck, int stride, int C,
                                                   int only_c = 0) {
     const int R = tb.R;
@@ -212,15 +284,14 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
     static_assert(!PARTIAL || CK == 1, "a partial run produces one checkpoint");
     uint32_t sg_base = tb.sg_addr + (PARTIAL ? (uint32_t)only_c * 4u : 0u);   // PARTIAL: column only_c of sg
-    asm volatile("" : "+r"(rec_base), "+r"(sg_base));   // keep them in registers
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
-    uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
-    float m2c = -2.0f * mlc;
-    asm volatile("" : "+r"(end_addr), "+f"(m2c), "+l"(ck));   // loop invariants: keep them instead of recomputing them per block
+    const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
-    int nc = 0;                                                                // next checkpoint to capture
-    int next_pos = (smooth || !active) ? INT_MAX : tb.ckpos[PARTIAL ? only_c : 0];   // padding lanes never capture
     float ff = f1;
+    static_assert(sizeof(T) == 4, "the Philox paths are float");
+    // row of the next checkpoint to capture, as a shared-space address (ck always lives in shared memory)
+    uint32_t ckp = (uint32_t)__cvta_generic_to_shared(ck);
+    const uint32_t row_bytes = (uint32_t)stride * 4u;
     float acc[CK];
 #pragma unroll
     for (int c = 0; c < CK; ++c) acc[c] = 0.0f;
@@ -237,25 +308,26 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
             if (c4 + 3 < CK) acc[c4 + 3] = w.w * f0;
         }
     }
-    if (active && next_pos == 0) {
-        ck[0] = (T)ff;
-        nc = 1;
-        next_pos = PARTIAL ? INT_MAX : tb.ckpos[1];
+    if constexpr (!PARTIAL) {
+        if (active && tb.ckpos[0] == 0) {          // position 0 is the start value
+            sts32_if(ckp, ff, true);
+            ckp += row_bytes;
+        }
     }
-    uint32_t cap_addr = next_pos == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)next_pos * (AT2_REC * 4u);
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-    auto attempt = [&](float x, float u) {
-        const float4 gm = tab128<GTAB>(gbase, addr);                               // d, c, d*log2e, d*scale
-        const float4 pw = tab128<GTAB>(gbase, addr + 16u);                         // P, P11, 1 - P, -
-        const float v = fmaf(gm.y, x, 1.0f);
-        const float v3 = v * v * v;
-        // log2 U < log2e * (x^2/2 + d - d v^3) + d log2 v^3     (Marsaglia & Tsang 2000, full test)
-        const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-        // v <= 0 needs no test of its own: lg2 of a non-positive v^3 is NaN / -inf and the comparison fails
-        bool ok = fast_lg2(u) < rhs;
+    auto attempt = [&](float x, float ku) {
+        const float4 gm = tab128<GTAB>(gbase, addr);                               // d, c, d log2e, d log2e + 32
+        const float4 pw = tab128<GTAB>(gbase, addr + 16u);                         // +-w, K1w, K0, P11
+        const AttemptOut o = mt_attempt(gm, pw, x, ku, ff, fnf, upc);
+        bool ok = o.ok;
         if constexpr (PARTIAL) ok = ok && addr < end_addr;
-        const float fnew = step_fast(ff, gm.w * v3, fnf, mlc, m2c, upc, pw.x, pw.y, pw.z);
-        ff = ok ? fnew : ff;
+        ff = ok ? o.fnew : ff;
+        if constexpr (!PARTIAL) {
+            // smooth lanes store too (into rows the read-outs below overwrite): no test of their own
+            const bool cap = ok && __float_as_int(pw.x) < 0;
+            sts32_if(ckp, ff, cap);                  // predicated store: no branch in the attempt
+            ckp += cap ? row_bytes : 0u;
+        }
         if constexpr (HAS_SMOOTH && PARTIAL) {
             const float fs = (ok && smooth) ? ff : 0.0f;
             acc[0] = fmaf(tab32<GTAB>(gbase, sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4)), fs, acc[0]);
@@ -271,52 +343,58 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
                 if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
             }
         }
-        addr += ok ? (AT2_REC * 4u) : 0u;
+        if (ok) addr += AT2_REC * 4u;
     };
-    auto consume = [&](const At2U4& r) {
-        const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (0,1]
-        const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));                     // sqrt(-2 ln u1)
-        const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;                       // [-pi, pi)
-        const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));                    // (0,1]
-        const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
-        attempt(rad * fast_cos(ang), ua);
-        const float f_mid = ff;
-        const uint32_t addr_mid = addr;
-        attempt(rad * fast_sin(ang), ub);
-        // checkpoint capture (raw arms): position cap was produced by the first attempt if the epoch had already moved
-        // past it in between, by the second otherwise
-        while (addr > cap_addr) {
-            ck[PARTIAL ? 0 : nc * stride] = (T)(addr_mid > cap_addr ? f_mid : ff);
-            ++nc;
-            const int np = PARTIAL ? INT_MAX : tb.ckpos[nc];
-            cap_addr = np == INT_MAX ? 0xffffffffu : rec_base + (uint32_t)np * (AT2_REC * 4u);
-        }
+    auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu) {
+        float x0, x1, ku0, ku1;
+        box_muller_pair(wa, wb, wu, x0, x1, ku0, ku1);
+        attempt(x0, ku0);
+        attempt(x1, ku1);
     };
+    auto block = [&](uint32_t ctr) { return at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk); };
+    auto unfinished = [&]() { return __any_sync(0xffffffffu, addr < end_addr); };
     // a partial run that reads the first point (r = 1) has no step to make: not even the first Philox block
-    if (!PARTIAL || __any_sync(0xffffffffu, addr < end_addr)) {
-        uint32_t ctr = 1;
-        At2U4 ra = at2_philox10_rk(At2U4{0u, g_lo, g_hi, AT2_STREAM_TRAJ}, rk), rb;
+    if (!PARTIAL || unfinished()) {
+        // every unfinished lane needs at least this many more attempts
+        const unsigned need = __reduce_min_sync(0xffffffffu, active ? (unsigned)(stop_t - 1) : 0xffffffffu);
+        const int n_main = need == 0xffffffffu ? 0 : (int)(need >> 3);
+        uint32_t ctr = 0;
+        At2U4 A = block(0), B, Cb;
+#pragma unroll 1
+        for (int it = 0; it < n_main; ++it) {
+            B = block(ctr + 1);
+            Cb = block(ctr + 2);
+            const At2U4 An = block(ctr + 3);
+            ctr += 3;
+            pair(A.x, A.y, A.z);
+            pair(A.w, B.x, B.y);
+            pair(B.z, B.w, Cb.x);
+            pair(Cb.y, Cb.z, Cb.w);
+            A = An;
+        }
+#pragma unroll 1
         while (true) {
-            if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-            rb = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
-            ++ctr;
-            consume(ra);
-            if (!__any_sync(0xffffffffu, addr < end_addr)) break;
-            ra = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
-            ++ctr;
-            consume(rb);
+            if (!unfinished()) break;
+            B = block(ctr + 1);
+            pair(A.x, A.y, A.z);
+            pair(A.w, B.x, B.y);
+            if (!unfinished()) break;
+            Cb = block(ctr + 2);
+            const At2U4 An = block(ctr + 3);
+            ctr += 3;
+            pair(B.z, B.w, Cb.x);
+            pair(Cb.y, Cb.z, Cb.w);
+            A = An;
         }
     }
-    if constexpr (HAS_SMOOTH) {
+    if constexpr (PARTIAL) {
+        // the run stopped where the read-out is: a raw arm's value is the loss it stands on
+        if (active) ck[0] = (T)((HAS_SMOOTH && smooth) ? acc[0] : ff);
+    } else if constexpr (HAS_SMOOTH) {
         if (active && smooth) {
 #pragma unroll
-            for (int c = 0; c < CK; ++c) {
-                if (PARTIAL) {
-                    ck[0] = (T)acc[0];
-                } else if (c < C) {
-                    ck[c * stride] = (T)acc[c];
-                }
-            }
+            for (int c = 0; c < CK; ++c)
+                if (c < C) ck[c * stride] = (T)acc[c];
         }
     }
 }
@@ -325,13 +403,13 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
 // Gamma stream and family (down step: f' = (1-k) f + k f_n; up step: f' = (1-P11)(f + up/(1+g)) + P11 f_n) - and so is the
 // Savitzky-Golay read-out (its rows sum to one).  Since f_1 = f + (noise z - start_shift) and f_n = f - end_shift, the loss
 // an arm shows at a checkpoint is  f(x, y) + offset  with an offset that is known BEFORE the arm's hyperparameters are.
-// This walks the lane's stream (same Philox blocks, same acceptance arithmetic as philox_trajectory, so the same Gamma
+// This walks the lane's stream (same Philox words, same acceptance arithmetic as philox_trajectory, so the same Gamma
 // draws) up to the read-out of checkpoint c and returns that offset.  The TPE kernel computes it for all arms of a bracket
 // in parallel (one arm per lane) before its sequential suggest -> observe loop, instead of re-walking each arm's stream
 // with 32 redundant lanes once its hyperparameters have been suggested.  All 32 lanes must call it.
 //   dz = noise z - start_shift (f_1 - f), s1 = end_shift (f - f_n); stop_t: 1 + last position the read-out needs.
 template <bool HAS_SMOOTH>
-__device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool active, bool smooth, float mlc, float upc,
+__device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool active, bool smooth, float upc,
                                                       int pw_off, unsigned long long gid, const uint32_t* __restrict__ rk,
                                                       int stop_t, int c, float dz, float s1) {
     const uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
@@ -342,19 +420,19 @@ __device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool 
     float A = 1.0f, Cc = 0.0f, accA = 0.0f, accC = 0.0f;
     if constexpr (HAS_SMOOTH) accA = smooth ? lds32(sg_col) : 0.0f;      // sg[0][c] * (A_0 = 1)
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-    auto attempt = [&](float x, float u) {
+    auto attempt = [&](float x, float ku) {
         const float4 gm = lds128(addr);
         const float4 pw = lds128(addr + 16u);
         const float v = fmaf(gm.y, x, 1.0f);
         const float v3 = v * v * v;
-        const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.z)));
-        const bool ok = fast_lg2(u) < rhs && addr < end_addr;
-        const float g = gm.w * v3;
-        const float k = fmaf(fmaf(g, mlc, -2.0f * mlc), pw.z, pw.x);
-        const float q = 1.0f - pw.y;
-        const bool dn = g > 2.0f, up = g < 2.0f;
-        const float An = dn ? fmaf(-k, A, A) : (up ? q * A : A);
-        const float Cn = dn ? fmaf(-k, Cc, Cc) : (up ? q * fmaf(upc, fast_rcp(1.0f + g), Cc) : Cc);
+        const float rhs = fmaf(gm.x, fast_lg2(v3), fmaf(-gm.z, v3, fmaf(0.72134752044448170f, x * x, gm.w)));
+        const bool ok = fast_lg2(ku) < rhs && addr < end_addr;
+        const float g1 = fmaf(fabsf(pw.x), v3, 1.0f);
+        const bool dn = g1 > 3.0f;
+        const float k = fmaf(v3, pw.y, pw.z);
+        const float q = 1.0f - pw.w;
+        const float An = dn ? fmaf(-k, A, A) : q * A;
+        const float Cn = dn ? fmaf(-k, Cc, Cc) : q * fmaf(upc, fast_rcp(g1), Cc);
         A = ok ? An : A, Cc = ok ? Cn : Cc;
         if constexpr (HAS_SMOOTH) {
             const float w = (ok && smooth) ? lds32(sg_col + ((addr - rec_base) >> 5) * sg_row) : 0.0f;
@@ -362,17 +440,25 @@ __device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool 
         }
         addr += ok ? (AT2_REC * 4u) : 0u;
     };
+    auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu) {
+        float x0, x1, ku0, ku1;
+        box_muller_pair(wa, wb, wu, x0, x1, ku0, ku1);
+        attempt(x0, ku0);
+        attempt(x1, ku1);
+    };
+    auto block = [&](uint32_t ctr) { return at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk); };
+    auto unfinished = [&]() { return __any_sync(0xffffffffu, addr < end_addr); };
     uint32_t ctr = 0;
-    while (__any_sync(0xffffffffu, addr < end_addr)) {
-        const At2U4 r = at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk);
-        ++ctr;
-        const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-        const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));
-        const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;
-        const float ua = 2.0f - __uint_as_float(0x3f800000u | (r.z >> 9));
-        const float ub = 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9));
-        attempt(rad * fast_cos(ang), ua);
-        attempt(rad * fast_sin(ang), ub);
+#pragma unroll 1
+    while (unfinished()) {
+        const At2U4 A4 = block(ctr), B4 = block(ctr + 1);
+        pair(A4.x, A4.y, A4.z);
+        pair(A4.w, B4.x, B4.y);
+        if (!unfinished()) break;
+        const At2U4 C4 = block(ctr + 2);
+        ctr += 3;
+        pair(B4.z, B4.w, C4.x);
+        pair(C4.y, C4.z, C4.w);
     }
     if (HAS_SMOOTH && smooth) A = accA, Cc = accC;
     return fmaf(A, dz, fmaf(A, s1, -s1)) + Cc;                           // A dz - (1 - A) s1 + C

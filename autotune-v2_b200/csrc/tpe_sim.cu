@@ -352,13 +352,13 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, cap = p.cap;
     const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
-    const int tab_elems = (L.total() + 3) & ~3;
+    const int tab_elems = (L.total_philox() + 3) & ~3;
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4]
     int* s_sglast = s_ckpos + AT2_MAX_CKPTS + 4;                     // [AT2_MAX_CKPTS + 4] last position a smooth read-out needs
     unsigned char* warp_base = reinterpret_cast<unsigned char*>(s_sglast + AT2_MAX_CKPTS + 4);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    for (int i = tid; i < L.total(); i += blockDim.x) s_tab[i] = p.tables[i];
+    for (int i = tid; i < L.total_philox(); i += blockDim.x) s_tab[i] = p.tables[i];
     if (tid < AT2_MAX_CKPTS + 4) s_ckpos[tid] = tid < C ? p.plan.ckpt_time[tid] - 1 : INT_MAX;
     __syncthreads();
     const float* s_rec = s_tab + L.off_rec();
@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                 if (use_tpe) {
                     const Fam<float> fam = p.fam[d.fam];
                     const bool sm = HAS_SMOOTH && fam.smooth != 0;
-                    off = philox_affine_offset<HAS_SMOOTH>(tb, act, sm, fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.rk,
+                    off = philox_affine_offset<HAS_SMOOTH>(tb, act, sm, fam.up, fam.pw_off, gid0 + arm, p.sp.rk,
                                                            (sm ? s_sglast[c0] : s_ckpos[c0]) + 1, c0,
                                                            p.sp.noise * d.z - fam.s0, fam.s1);
                 }
@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                 const float f = base_function(p.sp.func, w.ax[arm], w.ay[arm]);
                 __syncwarp();                                         // row 0 of ck is overwritten below
                 philox_trajectory<float, HAS_SMOOTH, CK>(tb, act, HAS_SMOOTH && fam.smooth != 0, (f + p.sp.noise * d.z) - fam.s0,
-                                                         f - fam.s1, fam.ml, fam.up, fam.pw_off, gid0 + arm, p.sp.rk, R,
+                                                         f - fam.s1, fam.up, fam.pw_off, gid0 + arm, p.sp.rk, R,
                                                          w.ck + arm, cap, C);
             }
             __syncwarp();
@@ -680,7 +680,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     size_t wb = (size_t)p.cap * ((C + 5) * 4 + 3 * 2 + 2) + 32 * 2 + scratch;
     p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
-    const size_t fixed = (size_t)((L.total() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
+    const size_t fixed = (size_t)((L.total_philox() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));

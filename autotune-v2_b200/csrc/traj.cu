@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
     const Fam<float> fams[8] = {f0, f1_, f2, f3, f4, f5, f6, f7};
     for (long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x; a < n_arms; a += (long long)gridDim.x * blockDim.x) {
         const Fam<float> fam = fams[d_family[a]];
-        const float fn = d_fn[a], mlc = fam.ml, upc = fam.up;
+        const float fn = d_fn[a], upc = fam.up;
         const unsigned long long gid = d_gid[a];
         const float* rec = s_tab + L.off_rec() + (size_t)AT2_REC * fam.pw_off;
         float ff = d_f1[a];
@@ -29,28 +29,33 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
         out[0] = ff;
         int t = 1;
         uint32_t ctr = 0;
-        while (t < R) {
-            const At2U4 r = at2_philox10(At2U4{ctr, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_TRAJ}, key0, key1);
-            ++ctr;
-            const float u1 = fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-            const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));
-            const float ang = (float)(int32_t)r.y * 1.4629180792671596e-9f;
-            const float xs[2] = {rad * fast_cos(ang), rad * fast_sin(ang)};
-            const float us[2] = {2.0f - __uint_as_float(0x3f800000u | (r.z >> 9)), 2.0f - __uint_as_float(0x3f800000u | (r.w >> 9))};
+        const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
+        // the word stream of sim_core.cuh: three blocks feed four attempt pairs
+        auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu) {
+            float xs[2], ku[2];
+            box_muller_pair(wa, wb, wu, xs[0], xs[1], ku[0], ku[1]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (t >= R) break;
-                const float* g = rec + AT2_REC * t;
-                const float x = xs[k], u = us[k];
-                const float v = fmaf(g[1], x, 1.0f);
-                const float v3 = v * v * v;
-                const float rhs = fmaf(g[0], fast_lg2(v3), fmaf(-g[2], v3, fmaf(0.72134752044448170f, x * x, g[2])));
-                if (fast_lg2(u) < rhs) {
-                    ff = step_fast(ff, g[3] * v3, fn, mlc, -2.0f * mlc, upc, g[4], g[5], g[6]);
+                const float4 gm = *reinterpret_cast<const float4*>(rec + AT2_REC * t);
+                const float4 pw = *reinterpret_cast<const float4*>(rec + AT2_REC * t + 4);
+                const AttemptOut o = mt_attempt(gm, pw, xs[k], ku[k], ff, fn, upc);
+                if (o.ok) {
+                    ff = o.fnew;
                     out[t] = ff;
                     ++t;
                 }
             }
+        };
+        while (t < R) {
+            const At2U4 A4 = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
+            const At2U4 B4 = at2_philox10(At2U4{ctr + 1, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
+            const At2U4 C4 = at2_philox10(At2U4{ctr + 2, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
+            ctr += 3;
+            pair(A4.x, A4.y, A4.z);
+            pair(A4.w, B4.x, B4.y);
+            pair(B4.z, B4.w, C4.x);
+            pair(C4.y, C4.z, C4.w);
         }
     }
 }

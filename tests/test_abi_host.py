@@ -123,11 +123,45 @@ def test_tables_f64_bit_exact_with_python_floats(R):
         assert np.isnan(rec[f, R, 1])                                 # sentinel row: acceptance can never pass
     # Savitzky-Golay rows at the checkpoints agree with scipy's operator to rounding
     W = gp.savgol_operator(R)
-    sg = buf[8 * F * (R + 1):].reshape(R + 1, 8 if plan.n_ckpts > 4 else 4)
+    sgw = 8 if plan.n_ckpts > 4 else 4
+    sg = buf[8 * F * (R + 1):8 * F * (R + 1) + sgw * (R + 1)].reshape(R + 1, sgw)
     for c in range(plan.n_ckpts):
         row = plan.ckpt_time[c] - 1
         assert np.max(np.abs(sg[:R, c] - W[row])) < 1e-12
     assert np.all(sg[:, plan.n_ckpts:] == 0) and np.all(sg[R] == 0)
+
+
+@pytest.mark.parametrize('R', [27, 81])
+def test_tables_f32_folded_records(R):
+    """Float tables (Philox paths): {d, c, d log2e, d log2e + 32, +-w, K1w, K0, P11}; the sign of w flags the plan's
+    checkpoint positions; pw[f][t] = {K1, K0, P11, 0} follows the Savitzky-Golay rows (include/at2.h)."""
+    plan = nat.bracket_plan(R, 3)
+    cfg = _cfg(FAM6)
+    nbytes = nat.lib.at2_hb_tables_bytes(C.byref(plan), C.byref(cfg), 0)
+    buf = np.zeros(nbytes // 4, np.float32)
+    nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 0, buf.ctypes.data))
+    F = len(FAM6)
+    sgw = 8 if plan.n_ckpts > 4 else 4
+    rec = buf[:8 * F * (R + 1)].reshape(F, R + 1, 8)
+    pw = buf[8 * F * (R + 1) + sgw * (R + 1):].reshape(F, R + 1, 4)
+    ckpos = {plan.ckpt_time[c] - 1 for c in range(plan.n_ckpts)}
+    f32 = np.float32
+    for f, fam in enumerate(FAM6):
+        for t in range(1, R):
+            a, s = gp.gamma_shape_scale(t, R)
+            d = a - 1.0 / 3.0
+            P, P11, ml = (t / (R - 1)) ** fam[1], (t / (R - 1)) ** (1.1 * fam[1]), fam[0] / 100.0
+            w = d * s
+            assert rec[f, t, 0] == f32(d) and rec[f, t, 2] == f32(d * 1.4426950408889634)
+            assert rec[f, t, 3] == f32(d * 1.4426950408889634 + 32.0)
+            assert rec[f, t, 4] == f32(-w if t in ckpos else w)
+            assert rec[f, t, 5] == f32(w * (ml * (1.0 - P))) and rec[f, t, 6] == f32(P - 2.0 * ml * (1.0 - P))
+            assert rec[f, t, 7] == f32(P11)
+            assert tuple(pw[f, t]) == (f32(ml * (1.0 - P)), f32(P - 2.0 * ml * (1.0 - P)), f32(P11), f32(0))
+            # the folded form is the reference's down step: k = a (1 - P) + P with a = (g - 2) ml_agg / 100
+            g = 3.7
+            assert abs((g * pw[f, t, 0] + pw[f, t, 1]) - ((g - 2) * ml * (1 - P) + P)) < 1e-6
+        assert np.isnan(rec[f, R, 1]) and rec[f, R, 4] > 0       # sentinel: never accepts, never captures
 
 
 def test_savgol_rows_all_rows_and_window_error():
