@@ -63,6 +63,11 @@ class HbOutputs(C.Structure):
                 ('d_ckpt_loss', C.c_void_p)]
 
 
+class Gather(C.Structure):
+    _fields_ = [('d_target', C.c_void_p * MAX_PEERS), ('n_targets', C.c_int32), ('is_multicast', C.c_int32),
+                ('base', C.c_int64)]
+
+
 class At2Error(RuntimeError):
     pass
 
@@ -86,7 +91,10 @@ def _load():
         'at2_hb_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
                                      C.POINTER(HbOutputs), vp]),
         'at2_hb_sim_gather_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64, C.POINTER(HbOutputs),
-                                            C.POINTER(C.c_void_p), i32, i64, vp]),
+                                            C.POINTER(Gather), vp]),
+        'at2_hb_sim_early_stop_gather_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
+                                                       C.POINTER(HbOutputs), C.POINTER(Gather), vp]),
+        'at2_debug_option': (C.c_int, [C.c_char_p, i32]),
         'at2_hb_sim_early_stop_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, i64, u64,
                                                 C.POINTER(HbOutputs), vp]),
         'at2_hb_sim_predrawn_f64': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, vp,
@@ -131,3 +139,20 @@ def bracket_plan(R, eta):
     if rc != 0:
         raise ValueError(lib.at2_last_error().decode())
     return plan
+
+
+class debug_options:
+    """Context manager over at2_debug_option (include/at2.h): tile / CTA shapes and code-path switches for tests and
+    measurements - `with debug_options(hb_no_split=1): ...`.  Everything is reset on exit (the options are process-wide)."""
+
+    def __init__(self, **opts):
+        self.opts = opts
+
+    def __enter__(self):
+        for k, v in self.opts.items():
+            check(lib.at2_debug_option(k.encode(), int(v)))
+        return self
+
+    def __exit__(self, *exc):
+        check(lib.at2_debug_option(b'reset', 0))
+        return False

@@ -113,13 +113,20 @@ def _cuda_device(device):
     return torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
 
 
-def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False, early_stop=False):
+def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, details=False, early_stop=None):
     """`n_reps` independent Hyperband repetitions on the simulation problem of `spec`, one fused kernel launch.
 
     Returns a dict of device tensors: ofe[n], ofe_arm[n], best_xy[n,2] ([n,4] for the egg4 extension) and, with details=True, round_best[n,rounds],
     round_best_arm, survivors[n, n_surv], ckpt_loss[n, arms, ckpts].  Repetition i is keyed by (seed, rep_offset+i).
+
+    early_stop: None (default) = the early-stopping kernel unless `details` asks for the checkpoint losses of every arm
+    (which only the full simulation computes); True / False force one or the other.  Both give the same OFEs, winning arms,
+    round-bests and survivor lists bit for bit (tests/test_hb_gpu.py) - early stopping just does not simulate what no round
+    reads (benchmarks/opt_function_simulation_problem.py:67-76 simulates every arm to R on its first evaluate()).
     """
     device = _cuda_device(device)
+    if early_stop is None:
+        early_stop = not details
     if early_stop:
         # arms are simulated only as far as the round that reads them needs; same streams, bit-identical outputs
         outs = torch.ops.at2.hb_sim_early_stop(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes,

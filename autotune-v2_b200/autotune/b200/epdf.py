@@ -94,14 +94,15 @@ class FusedGather:
             return None
         return cls(n_total, device, group, bufs, handles, use_multicast)
 
-    def run(self, spec, seed):
+    def run(self, spec, seed, early_stop=True):
         """This rank's share of the job's repetitions; returns the gathered [n_total] OFE vector (a view of a symmetric
-        buffer that stays valid until the job after the next one)."""
+        buffer that stays valid until the job after the next one).  early_stop: the early-stopping kernel (the product's
+        default; same OFEs bit for bit) or the full simulation."""
         lo, hi = shard_range(self.n_total, self.rank, self.world)
         buf, hdl, targets = self.bufs[self.turn], self.handles[self.turn], self.targets[self.turn]
         self.turn ^= 1
         torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo, lo,
-                                    int(seed), buf, targets, lo)
+                                    int(seed), buf, targets, lo, self.multicast, bool(early_stop))
         hdl.barrier(channel=0)          # on the current stream: every rank's stores are in every buffer after it
         return buf
 
@@ -123,13 +124,14 @@ def summary_stats(ofes):
 
 
 def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=1000, kernel='epanechnikov',
-                 group=None, device=None, runner=None, fused=None):
+                 group=None, device=None, runner=None, fused=None, early_stop=True):
     """The whole job: this rank's share of `n_reps` Hyperband repetitions -> all-gather -> KDE.
 
     Returns {'ofes': [n_reps] float32 (all ranks' OFEs, in repetition order), 'density': [grid_points], 'grid': ...}.
     `runner(spec, n, seed, rep_offset, device)` defaults to the fused Hyperband kernel; other optimisers plug in here.
     `fused`: a FusedGather for (n_reps, device, group) - the kernel then scatters its OFEs into every rank's buffer itself
     and no NCCL collective runs (plain Hyperband only); the gathered vector is bit-identical either way.
+    `early_stop` (default True): the early-stopping kernel; False simulates every arm to R like the reference - same OFEs.
     """
     from .engine import _cuda_device, run_hyperband_repetitions
     device = _cuda_device(device)
@@ -138,13 +140,13 @@ def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=100
     if fused is not None and runner is None:
         if fused.n_total != int(n_reps):
             raise ValueError(f'FusedGather was built for {fused.n_total} repetitions, not {n_reps}')
-        ofes = fused.run(spec, seed)
+        ofes = fused.run(spec, seed, early_stop)
         return {'ofes': ofes, 'density': density(ofes, start, end, bandwidth, grid_points, kernel),
                 'grid': np.linspace(start, end, grid_points)}
     lo, hi = shard_range(n_reps, rank, world)
     if runner is None:
         def runner(spec_, n, seed_, off, dev):
-            return run_hyperband_repetitions(spec_, n, seed=seed_, rep_offset=off, device=dev)['ofe']
+            return run_hyperband_repetitions(spec_, n, seed=seed_, rep_offset=off, device=dev, early_stop=early_stop)['ofe']
     local = runner(spec, hi - lo, seed, lo, device) if hi > lo else torch.empty(0, device=device)
     ofes = gather_slices(local, n_reps, group)
     dens = density(ofes, start, end, bandwidth, grid_points, kernel)

@@ -67,23 +67,29 @@ def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.
 
 @torch.library.custom_op('at2::hb_sim_gather', mutates_args=('gathered',), device_types='cuda')
 def hb_sim_gather(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
-                  seed: int, gathered: torch.Tensor, gather_ptrs: List[int], gather_base: int) -> List[torch.Tensor]:
-    """at2::hb_sim_f32 fused with the all-gather of the OFEs (at2_hb_sim_gather_f32): the OFE of repetition i is also stored
-    to element gather_base + i of every buffer in `gather_ptrs` (device addresses of the peers' symmetric-memory buffers, or
-    one NVSwitch multicast address).  `gathered` is this rank's own buffer (declared mutated; it must be among the targets)."""
+                  seed: int, gathered: torch.Tensor, gather_ptrs: List[int], gather_base: int, multicast: bool = False,
+                  early_stop: bool = False) -> List[torch.Tensor]:
+    """at2::hb_sim_f32 (or, with early_stop, at2::hb_sim_early_stop) fused with the all-gather of the OFEs
+    (at2_hb_sim_gather_f32 / at2_hb_sim_early_stop_gather_f32): the OFE of repetition i is also stored to element
+    gather_base + i of every buffer in `gather_ptrs` (device addresses of the peers' symmetric-memory buffers), or - with
+    multicast=True - through the one NVSwitch multicast address in `gather_ptrs` (multimem.st).  `gathered` is this rank's
+    own buffer (declared mutated; it must be among the targets)."""
     _require_cuda(tables, 'tables')
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
-    if not 1 <= len(gather_ptrs) <= nat.MAX_PEERS:
-        raise RuntimeError(f'between 1 and {nat.MAX_PEERS} gather buffers')
+    if not 1 <= len(gather_ptrs) <= nat.MAX_PEERS or (multicast and len(gather_ptrs) != 1):
+        raise RuntimeError(f'between 1 and {nat.MAX_PEERS} gather buffers (exactly one multicast address)')
     if gathered.dtype != torch.float32 or gather_base < 0 or gather_base + n_reps > gathered.numel():
         raise RuntimeError('gathered must be a float32 buffer holding elements gather_base .. gather_base + n_reps')
     with torch.cuda.device(tables.device):
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, False, dims=nat.lib.at2_func_dims(cfg.func))
         if n_reps > 0:
-            ptrs = (C.c_void_p * len(gather_ptrs))(*gather_ptrs)
-            nat.check(nat.lib.at2_hb_sim_gather_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
-                                                    seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), ptrs, len(gather_ptrs),
-                                                    gather_base, _stream_ptr(tables.device)))
+            g = nat.Gather()
+            for i, ptr in enumerate(gather_ptrs):
+                g.d_target[i] = ptr
+            g.n_targets, g.is_multicast, g.base = len(gather_ptrs), int(multicast), gather_base
+            fn = nat.lib.at2_hb_sim_early_stop_gather_f32 if early_stop else nat.lib.at2_hb_sim_gather_f32
+            nat.check(fn(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset, seed & 0xFFFFFFFFFFFFFFFF,
+                         C.byref(outs), C.byref(g), _stream_ptr(tables.device)))
     return tensors
 
 

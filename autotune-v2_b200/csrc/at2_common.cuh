@@ -30,6 +30,18 @@ void at2_reset_launch_count();
         }                               \
     } while (0)
 
+// ---- debug options (include/at2.h at2_debug_option): tile / CTA shapes and code-path switches used by tests and
+// measurements.  Process-wide, all zero by default (= the library decides); never read from the environment.
+struct At2Debug {
+    int hb_reps_per_tile, hb_team_warps, hb_warps_per_cta;   // > 0: override choose_launch (hb_sim.cu)
+    int hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
+    int force_gtab;                                           // constant tables from global memory on any plan
+    int lazy_reps_per_tile;                                   // hb_lazy.cu tile width
+    int tpe_warps_per_cta;                                    // tpe_sim.cu
+    int kf_warps_per_cta, kf_reps_per_tile;                   // nn_lookup.cu hb_knownfn_kernel
+};
+const At2Debug& at2_debug();
+
 // CTAs of `kern` resident per SM as far as registers and threads go (shared memory is budgeted by the caller): a
 // persistent grid must not exceed what is resident at once, or the surplus CTAs form a half-empty second wave.
 template <typename Kern>
@@ -71,6 +83,14 @@ struct At2TableLayout {
     __host__ __device__ int total_philox() const { return off_pw(); }          // what a Philox kernel stages
     __host__ __device__ int total() const { return off_pw() + AT2_PW * F * (R + 1); }
 };
+
+static inline int at2_check_gather(const at2_gather* g, const char* who) {
+    AT2_REQUIRE(g != nullptr && g->n_targets >= 1 && g->n_targets <= AT2_MAX_PEERS, "%s: need 1..%d gather targets", who, AT2_MAX_PEERS);
+    AT2_REQUIRE(g->base >= 0, "%s: gather base must be >= 0", who);
+    AT2_REQUIRE(!g->is_multicast || g->n_targets == 1, "%s: a multicast gather has exactly one target address", who);
+    for (int r = 0; r < g->n_targets; ++r) AT2_REQUIRE(g->d_target[r] != nullptr, "%s: gather target %d is NULL", who, r);
+    return AT2_OK;
+}
 
 static inline int at2_cfg_has_smooth(const at2_sim_config* cfg) {
     for (int f = 0; f < cfg->n_families; ++f)
@@ -134,6 +154,12 @@ static inline void at2_round_keys(uint64_t seed, uint32_t* rk) {
         rk[2 * r] = k0, rk[2 * r + 1] = k1;
         k0 += AT2_PHILOX_W0, k1 += AT2_PHILOX_W1;
     }
+}
+
+// One 4-byte store to an NVSwitch multicast (multimem) address: the switch replicates it to every GPU of the group.  Only
+// multimem.* instructions may touch such an address (PTX ISA 8.1+: any other access is undefined behaviour).
+__device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
 }
 
 // RNG stream tags (4th counter word)

@@ -17,7 +17,33 @@ void at2_set_error(const char* fmt, ...) {
 void at2_count_launch(int n) { g_launches += n; }
 void at2_reset_launch_count() { g_launches = 0; }
 
-extern "C" const char* at2_version(void) { return "at2_b200 0.1 (sm_100a)"; }
+static At2Debug g_debug = {};
+const At2Debug& at2_debug() { return g_debug; }
+
+extern "C" int at2_debug_option(const char* name, int32_t value) {
+    AT2_REQUIRE(name != nullptr, "at2_debug_option: name is NULL");
+    if (strcmp(name, "reset") == 0) {
+        g_debug = At2Debug{};
+        return AT2_OK;
+    }
+    const struct { const char* name; int* field; } table[] = {
+        {"hb_reps_per_tile", &g_debug.hb_reps_per_tile}, {"hb_team_warps", &g_debug.hb_team_warps},
+        {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split},
+        {"hb_equal_tiles", &g_debug.hb_equal_tiles}, {"hb_no_tile_halving", &g_debug.hb_no_tile_halving},
+        {"hb_static_schedule", &g_debug.hb_static_schedule}, {"hb_singles", &g_debug.hb_singles},
+        {"force_gtab", &g_debug.force_gtab}, {"lazy_reps_per_tile", &g_debug.lazy_reps_per_tile},
+        {"tpe_warps_per_cta", &g_debug.tpe_warps_per_cta}, {"kf_warps_per_cta", &g_debug.kf_warps_per_cta},
+        {"kf_reps_per_tile", &g_debug.kf_reps_per_tile}};
+    for (const auto& e : table)
+        if (strcmp(name, e.name) == 0) {
+            *e.field = value;
+            return AT2_OK;
+        }
+    at2_set_error("at2_debug_option: unknown option '%s'", name);
+    return AT2_EINVAL;
+}
+
+extern "C" const char* at2_version(void) { return "at2_b200 0.2 (sm_100a)"; }
 extern "C" const char* at2_last_error(void) { return g_err; }
 extern "C" int32_t at2_last_launch_count(void) { return g_launches; }
 

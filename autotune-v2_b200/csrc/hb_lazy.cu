@@ -40,6 +40,10 @@ struct LazyParams {
     float* round_best;
     int* round_best_arm;
     int* survivors;
+    // fused all-gather of the OFEs (see hb_sim.cu): repetition i also lands in element gather_base + i of every gather[r]
+    float* gather[AT2_MAX_PEERS];
+    int n_gather, gather_multicast;
+    long long gather_base;
 };
 
 __host__ __device__ inline size_t lazy_keys_offset(int cur_cap, int G) { return ((size_t)cur_cap * 4 + (size_t)G * 12 + 7) & ~(size_t)7; }
@@ -106,7 +110,10 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                 // and this round's two stopping points differ, the warp first lists a chunk's items raw-first (the family of
                 // an arm is one Philox block away) and runs the all-raw passes through the lean loop, to the raw stopping
                 // point; only the smoothed tail runs long.  The list aliases the sort scratch (idle until the halving below).
-                const int stop_raw = s_ckpos[c] + 1, stop_sm = HAS_SMOOTH ? s_sglast[c] + 1 : stop_raw;
+                // A raw arm read at R stands on its target f_n by construction (P = P11 = 1 at the last step,
+                // core/simulation_evaluator.py:105-107,113-115; sim_core.cuh mt_attempt lands on it exactly): no run at all.
+                const bool raw_at_target = s_ckpos[c] == R - 1;
+                const int stop_raw = raw_at_target ? 1 : s_ckpos[c] + 1, stop_sm = HAS_SMOOTH ? s_sglast[c] + 1 : s_ckpos[c] + 1;
                 const bool split = HAS_SMOOTH && p.mixed && stop_sm > stop_raw;
                 unsigned short* order = reinterpret_cast<unsigned short*>(keys);
                 const int cap = p.npad * 4;                  // list entries; cur_cap <= cap
@@ -150,8 +157,9 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const ArmDraw d = draw_arm(p.sp, gid, arm);
                         const Fam<float> fam = p.fam[d.fam];
                         const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
-                        const float fn = f - fam.s1, f1 = (f + p.sp.noise * d.z) - fam.s0;
+                        const float fn = f - fam.s1;
                         const bool smooth = HAS_SMOOTH && fam.smooth != 0;
+                        const float f1 = (raw_at_target && !smooth) ? fn : (f + p.sp.noise * d.z) - fam.s0;
                         float* dst = cur + q;
                         if (!HAS_SMOOTH || (split && base + 32 <= n_raw))
                             philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.up, fam.pw_off, gid,
@@ -233,6 +241,10 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
             const long long rep_g = rep0 + g;
             if (p.ofe != nullptr) p.ofe[rep_g] = best[g];
             if (p.ofe_arm != nullptr) p.ofe_arm[rep_g] = best_arm[g];
+            if (p.gather_multicast)
+                multimem_st_f32(p.gather[0] + p.gather_base + rep_g, best[g]);
+            else
+                for (int r = 0; r < p.n_gather; ++r) p.gather[r][p.gather_base + rep_g] = best[g];
             if (p.best_xy != nullptr) {
                 const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm[g];
                 const ArmDraw d = draw_arm(p.sp, gid, best_arm[g]);
@@ -264,8 +276,9 @@ int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStrea
 
 }  // namespace
 
-extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
-                                         int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream) {
+static int early_stop_impl(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                           int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, const at2_gather* gather,
+                           void* stream) {
     at2_reset_launch_count();
     AT2_REQUIRE(plan && cfg && d_tables && out, "at2_hb_sim_early_stop_f32: NULL plan/config/tables/outputs");
     AT2_REQUIRE(n_reps > 0 && rep_offset >= 0, "at2_hb_sim_early_stop_f32: n_reps must be positive and rep_offset >= 0");
@@ -279,6 +292,12 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
                 "If mode is 'interp', window_length must be less than or equal to the size of x.");
     LazyParams p = {};
+    if (gather != nullptr) {
+        const int grc = at2_check_gather(gather, "at2_hb_sim_early_stop_gather_f32");
+        if (grc != AT2_OK) return grc;
+        for (int r = 0; r < gather->n_targets; ++r) p.gather[r] = gather->d_target[r];
+        p.n_gather = gather->n_targets, p.gather_multicast = gather->is_multicast, p.gather_base = gather->base;
+    }
     p.plan = *plan;
     for (int f = 0; f < cfg->n_families; ++f) {
         p.fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
@@ -292,7 +311,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     {
         int n_sm = 0;
         for (int f = 0; f < cfg->n_families; ++f) n_sm += cfg->fam[f].is_smooth != 0;
-        p.mixed = n_sm > 0 && n_sm < cfg->n_families && getenv("AT2_HB_NO_SPLIT") == nullptr;   // env: tests / measurements
+        p.mixed = n_sm > 0 && n_sm < cfg->n_families && !at2_debug().hb_no_split;
     }
     p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
     p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
@@ -325,7 +344,7 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     const int C = plan->n_ckpts;
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
     const size_t tab_bytes = (size_t)((L.total_philox() + 3) & ~3) * 4, fixed_small = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
-    const bool force_gtab = getenv("AT2_FORCE_GTAB") != nullptr;   // env: tests
+    const bool force_gtab = at2_debug().force_gtab != 0;
     // launch geometry of tile width g: a warp's tile state (loss buffer, per-repetition state, sort scratch, survivor ids),
     // tables in shared or global memory, warps per CTA, CTAs per SM
     struct Geo {
@@ -352,11 +371,10 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
     // what a warp's share of its scheduler is worth at that width's residency - so a small job is cut into narrow tiles
     // that cover the machine, a large one into wide ones, and a plan with wide brackets (whose survivor lists eat shared
     // memory) trades resident warps for fuller lanes only where that pays.
-    const char* env_g = getenv("AT2_HB_LAZY_REPS_PER_TILE");
     int G = 32;
     if ((long long)G > n_reps) G = (int)n_reps;
-    if (env_g != nullptr && atoi(env_g) > 0) {
-        G = atoi(env_g);
+    if (at2_debug().lazy_reps_per_tile > 0) {
+        G = at2_debug().lazy_reps_per_tile;
         if ((long long)G > n_reps) G = (int)n_reps;
         while (G > 1 && geometry(G).warp_bytes > 40 * 1024) G = (G + 1) / 2;
     } else {
@@ -408,4 +426,16 @@ extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_con
                           : launch_lazy<false, true>(p, (int)grid, nwarps * 32, smem, st);
     return has_smooth ? launch_lazy<true>(p, (int)grid, nwarps * 32, smem, st)
                       : launch_lazy<false>(p, (int)grid, nwarps * 32, smem, st);
+}
+
+extern "C" int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                                         int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream) {
+    return early_stop_impl(plan, cfg, d_tables, n_reps, rep_offset, seed, out, nullptr, stream);
+}
+
+extern "C" int at2_hb_sim_early_stop_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables,
+                                                int64_t n_reps, int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out,
+                                                const at2_gather* gather, void* stream) {
+    AT2_REQUIRE(gather != nullptr, "at2_hb_sim_early_stop_gather_f32: gather is NULL");
+    return early_stop_impl(plan, cfg, d_tables, n_reps, rep_offset, seed, out, gather, stream);
 }

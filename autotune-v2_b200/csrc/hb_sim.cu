@@ -23,6 +23,7 @@
 //   optimisers/sequential/hyperband_optimiser.py:46-57,74-106    stable top-k, round-best, OFE (core/optimiser.py:67-68)
 #include <cfloat>
 #include <climits>
+#include <atomic>
 #include <cstdlib>
 
 #include "at2_common.cuh"
@@ -44,6 +45,7 @@ struct Params {
     long long n_tiles;
     long long n_tiles_full;   // tiles [0, n_tiles_full) hold G repetitions; the rest of the job is cut into 1-repetition tiles
     int team_warps;   // warps cooperating on one tile (1 = warp-private tiles, no block-level barriers at all)
+    int dyn_slot;     // >= 0: warp-private tiles are handed out through the device counter pair g_sched[dyn_slot]
     int tile_halving; // float path, warp-private tiles: the tile's repetitions are halved together (halving.cuh tile_halving_f32)
     int km_a, km_b;   // entries of a repetition's two survivor-id buffers in that mode
     int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
@@ -61,7 +63,7 @@ struct Params {
     // fused all-gather of the OFEs: repetition i of this call also lands in element gather_base + i of every gather[r]
     // (the peers' symmetric buffers, written over NVLink), or of the one NVSwitch multicast address that fans out to all
     T* gather[AT2_MAX_PEERS];
-    int n_gather;
+    int n_gather, gather_multicast;
     long long gather_base;
     // outputs
     T* ofe;
@@ -72,6 +74,21 @@ struct Params {
     int* survivors;
     T* ckpt_loss;
 };
+
+// Dynamic tile schedule (warp-private tiles).  The warp scheduler's arbitration is not fair (ncu: 4.8 of 6 warps per
+// scheduler resident on average with a static round-robin schedule - the favoured warps finish their share early and the
+// SM runs its tail half empty), so a warp takes its next tile from a device counter instead: all warps finish within one
+// tile of each other.  Tile ids are handed out in increasing order - the G-repetition tiles first, the single repetitions
+// (launch_one) last.  Which warp runs a tile does not matter: streams are keyed by the repetition id.  A launch owns one
+// slot of the counter array (round-robin on the host; launches that overlap in time must hold different slots, 64 slots);
+// the last warp to run dry resets its slot, so a slot is zero whenever it is handed out.
+struct SchedSlot {
+    unsigned long long next;   // next tile id
+    unsigned int done;         // warps that have run dry
+    unsigned int pad;
+};
+#define AT2_SCHED_SLOTS 64
+__device__ SchedSlot g_sched[AT2_SCHED_SLOTS];
 
 // Register cap 80 (65536 / 768): shared memory (a 3-repetition tile per warp) holds about 24 warps per SM anyway - three
 // 8-warp CTAs when the constant tables are small, ONE 24-warp CTA when they are large (six families: 18 KB per CTA), see
@@ -116,7 +133,14 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
 
     const long long team_global = (long long)blockIdx.x * p.n_teams + team;
     const long long team_stride = (long long)gridDim.x * p.n_teams;
-    for (long long tile = team_global; tile < p.n_tiles; tile += team_stride) {
+    const bool dynamic = p.dyn_slot >= 0;        // host: only with warp-private tiles
+    auto next_tile = [&](long long cur) -> long long {
+        if (!dynamic) return cur < 0 ? team_global : cur + team_stride;
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&g_sched[p.dyn_slot].next, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    for (long long tile = next_tile(-1); tile < p.n_tiles; tile = next_tile(tile)) {
         // whole rounds of G-repetition tiles, then the remainder of the job as single repetitions: the teams' shares then
         // differ by one repetition at most, not by one tile (see launch_one)
         const bool full = tile < p.n_tiles_full;
@@ -272,7 +296,13 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                 best_arm = warp_halving<T>(p.plan, s_ck + rep_l * A, p.stride, keys, ids_a, ids_b, desc, lane, rep_g, ho,
                                            &ofe_value);
             }
-            if (lane < p.n_gather) p.gather[lane][p.gather_base + rep_g] = ofe_value;   // one peer (or the multicast) per lane
+            if constexpr (sizeof(T) == 4) {
+                if (p.gather_multicast) {       // one multimem store, replicated by the switch
+                    if (lane == 0) multimem_st_f32(reinterpret_cast<float*>(p.gather[0]) + p.gather_base + rep_g, (float)ofe_value);
+                } else if (lane < p.n_gather) {
+                    p.gather[lane][p.gather_base + rep_g] = ofe_value;   // one peer per lane
+                }
+            }
             if (lane == 0 && p.best_xy != nullptr) {
                 if constexpr (MODE == MODE_PHILOX) {   // re-draw the winner's hyperparameters from its stream
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + best_arm;
@@ -289,6 +319,15 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
         }
         team_barrier(team, p.team_warps);
     }
+    if (dynamic && lane == 0) {
+        // this warp has run dry; the last one to do so hands the slot back zeroed
+        __threadfence();
+        if (atomicAdd(&g_sched[p.dyn_slot].done, 1u) == (unsigned)team_stride - 1u) {
+            g_sched[p.dyn_slot].next = 0ull;
+            g_sched[p.dyn_slot].done = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // ---- launch plumbing ---------------------------------------------------------------------------------------------------
@@ -300,10 +339,7 @@ struct LaunchCfg {
     size_t smem;
 };
 
-static int env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return (v != nullptr && atoi(v) > 0) ? atoi(v) : dflt;
-}
+static int opt_int(int v, int dflt) { return v > 0 ? v : dflt; }   // a debug option, or the library's own choice
 
 template <typename T>
 int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, int mode, LaunchCfg<T>* out) {
@@ -344,14 +380,14 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
         }
     }
     if (best_score < 0) best_tw = 8, best_g = 1;
-    best_tw = env_int("AT2_HB_TEAM_WARPS", best_tw);
-    best_g = env_int("AT2_HB_REPS_PER_TILE", best_g);
+    best_tw = opt_int(at2_debug().hb_team_warps, best_tw);
+    best_g = opt_int(at2_debug().hb_reps_per_tile, best_g);
     if ((long long)best_g > n_reps) best_g = (int)n_reps;
     const int stride = (best_g * A + 31) & ~31;
     size_t team_bytes = (size_t)C * stride * sizeof(T) + (best_tw < best_g ? best_tw : best_g) * sort_per_warp;
     team_bytes = (team_bytes + 15) & ~(size_t)15;
     // plans whose tables do not fit beside one team's state (R ~ 1000 with six families) read them from global memory
-    out->gtab = (fixed + team_bytes > (size_t)max_smem || getenv("AT2_FORCE_GTAB") != nullptr) ? 1 : 0;   // env: tests
+    out->gtab = (fixed + team_bytes > (size_t)max_smem || at2_debug().force_gtab != 0) ? 1 : 0;
     if (out->gtab) fixed = (AT2_MAX_CKPTS + 4) * sizeof(int);
     // Warps per CTA: every CTA carries its own copy of the constant tables (`fixed`), so with large tables fewer, bigger
     // CTAs keep more warps resident.  Take the size with the most resident warps per SM (shared memory, 80 registers per
@@ -368,7 +404,7 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps,
         ctas = ctas < by_threads ? ctas : by_threads;
         if (ctas * wpc > best_resident) best_resident = ctas * wpc, warps_per_cta = wpc;
     }
-    warps_per_cta = env_int("AT2_HB_WARPS_PER_CTA", warps_per_cta);
+    warps_per_cta = opt_int(at2_debug().hb_warps_per_cta, warps_per_cta);
     if (warps_per_cta < best_tw) warps_per_cta = best_tw;
     if (warps_per_cta > AT2_HB_MAX_WARPS) warps_per_cta = AT2_HB_MAX_WARPS;
     int n_teams = warps_per_cta / best_tw;
@@ -408,7 +444,17 @@ int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
     // (< teams * G + G repetitions) goes out as single repetitions.  Repetition ids do not change, results neither.
     Params<T> q = p;
     const long long teams = (long long)grid * q.n_teams, full_tiles = q.n_reps / q.G;
-    q.n_tiles_full = getenv("AT2_HB_EQUAL_TILES") != nullptr ? full_tiles : (full_tiles / teams) * teams;
+    static std::atomic<unsigned> launch_seq{0};
+    q.dyn_slot = (q.team_warps == 1 && !at2_debug().hb_static_schedule) ? (int)(launch_seq.fetch_add(1) % AT2_SCHED_SLOTS) : -1;
+    if (q.dyn_slot >= 0) {
+        // dynamic: G-repetition tiles, then `singles` single repetitions per warp to even out the finish
+        const int singles = opt_int(at2_debug().hb_singles, 1);
+        const long long body = q.n_reps - teams * singles;
+        q.n_tiles_full = body > 0 ? body / q.G : 0;
+        if (q.n_tiles_full > full_tiles) q.n_tiles_full = full_tiles;
+    } else {
+        q.n_tiles_full = at2_debug().hb_equal_tiles ? full_tiles : (full_tiles / teams) * teams;
+    }
     q.n_tiles = q.n_tiles_full + (q.n_reps - q.n_tiles_full * q.G);
     kern<<<grid, lc.block, lc.smem, st>>>(q);
     AT2_CUDA_CHECK(cudaGetLastError());
@@ -466,21 +512,21 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
     p->sort_warps = lc->team_warps < lc->G ? lc->team_warps : lc->G;
     // raw / smoothed arms in separate warp passes when the families mix both and a warp's order list fits in the team's sort
-    // scratch, which it aliases (see the kernel); AT2_HB_NO_SPLIT=1 disables it (development aid)
+    // scratch, which it aliases (see the kernel); debug option hb_no_split disables it
     int n_smooth = 0;
     for (int f = 0; f < cfg->n_families; ++f) n_smooth += cfg->fam[f].is_smooth ? 1 : 0;
     const int cap = ((lc->stride / 32 + lc->team_warps - 1) / lc->team_warps) * 32;
     const size_t scratch = (size_t)p->sort_warps * lc->npad * (sizeof(typename KeyOf<T>::type) + 2 * sizeof(unsigned short));
     p->split_cap = (n_smooth > 0 && n_smooth < cfg->n_families && (size_t)cap * 2 * lc->team_warps <= scratch &&
-                    lc->stride < 65536 && getenv("AT2_HB_NO_SPLIT") == nullptr) ? cap : 0;
+                    lc->stride < 65536 && !at2_debug().hb_no_split) ? cap : 0;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     // float path with warp-private tiles: the repetitions of a tile are halved together when their survivor-id buffers and
     // running state fit where the per-repetition path keeps its two id lists (2 * npad entries);
-    // AT2_HB_NO_TILE_HALVING=1 disables it (development aid / tests)
+    // debug option hb_no_tile_halving disables it (tests)
     halving_id_buffer_sizes(plan, &p->km_a, &p->km_b);
     const size_t tile_state = (size_t)((lc->G * (p->km_a + p->km_b) + 1) & ~1) * 2 + (size_t)lc->G * 12;
     p->tile_halving = (sizeof(T) == 4 && lc->team_warps == 1 && tile_state <= (size_t)lc->npad * 4 &&
-                       getenv("AT2_HB_NO_TILE_HALVING") == nullptr) ? 1 : 0;
+                       !at2_debug().hb_no_tile_halving) ? 1 : 0;
     return AT2_OK;
 }
 
@@ -501,21 +547,18 @@ extern "C" int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, c
 }
 
 extern "C" int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
-                                     int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* const* d_gather,
-                                     int32_t n_gather, int64_t gather_base, void* stream) {
+                                     int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, const at2_gather* gather,
+                                     void* stream) {
     at2_reset_launch_count();
     Params<float> p = {};
     LaunchCfg<float> lc;
     const int rc = fill_params<float>(plan, cfg, d_tables, n_reps, out, MODE_PHILOX, &p, &lc);
     if (rc != AT2_OK) return rc;
-    AT2_REQUIRE(rep_offset >= 0 && gather_base >= 0, "at2_hb_sim_gather_f32: rep_offset and gather_base must be >= 0");
-    AT2_REQUIRE(d_gather != nullptr && n_gather >= 1 && n_gather <= AT2_MAX_PEERS,
-                "at2_hb_sim_gather_f32: need 1..%d gather buffers", AT2_MAX_PEERS);
-    for (int r = 0; r < n_gather; ++r) {
-        AT2_REQUIRE(d_gather[r] != nullptr, "at2_hb_sim_gather_f32: gather buffer %d is NULL", r);
-        p.gather[r] = d_gather[r];
-    }
-    p.n_gather = n_gather, p.gather_base = gather_base;
+    AT2_REQUIRE(rep_offset >= 0, "at2_hb_sim_gather_f32: rep_offset must be >= 0");
+    const int grc = at2_check_gather(gather, "at2_hb_sim_gather_f32");
+    if (grc != AT2_OK) return grc;
+    for (int r = 0; r < gather->n_targets; ++r) p.gather[r] = gather->d_target[r];
+    p.n_gather = gather->n_targets, p.gather_multicast = gather->is_multicast, p.gather_base = gather->base;
     p.rep_offset = rep_offset;
     p.sp.key0 = (uint32_t)seed, p.sp.key1 = (uint32_t)(seed >> 32);
     at2_round_keys(seed, p.sp.rk);

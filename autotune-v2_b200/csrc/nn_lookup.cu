@@ -379,14 +379,13 @@ extern "C" int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int nwarps = 4;
     {
-        const char* env_w = getenv("AT2_KF_WARPS_PER_CTA");      // development aid
-        if (env_w != nullptr && atoi(env_w) > 0 && atoi(env_w) <= 8) nwarps = atoi(env_w);
+        const int w = at2_debug().kf_warps_per_cta;
+        if (w > 0 && w <= 8) nwarps = w;
     }
     p.npad = halving_npad(plan);
     p.G = 1;
     {
-        const char* env_g = getenv("AT2_KF_REPS_PER_TILE");      // development aid
-        if (env_g != nullptr && atoi(env_g) > 0) p.G = atoi(env_g);
+        if (at2_debug().kf_reps_per_tile > 0) p.G = at2_debug().kf_reps_per_tile;
         if ((long long)p.G > n_reps) p.G = (int)n_reps;
     }
     p.stride = (p.G * plan->n_arms + 31) & ~31;

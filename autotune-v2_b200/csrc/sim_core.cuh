@@ -219,8 +219,8 @@ __device__ __forceinline__ void box_muller_pair(uint32_t wa, uint32_t wb, uint32
 //   log2 U < log2e (x^2/2 + d - d v^3) + d log2 v^3,  with log2 U = log2(ku) - 32 folded into the record (gm.w = d log2e + 32)
 // - and the step of the recurrence it feeds (simulation_evaluator.py:99-115) in folded form:
 //   g = w v^3 (Gamma draw), g1 = 1 + g
-//   g > 2:  f' = f + (fn - f) k,            k = a (1 - P) + P, a = (g - 2) ml_agg / 100  ==  v^3 K1w + K0   (:103-107)
-//   g <= 2: up = f + up_spik / (1 + g),  f' = up + (fn - up) P11                                              (:108-115)
+//   g > 2:  f' = k fn + (1 - k) f,          k = a (1 - P) + P, a = (g - 2) ml_agg / 100  ==  v^3 K1w + K0   (:103-107)
+//   g <= 2: up = f + up_spik / (1 + g),  f' = P11 fn + (1 - P11) up                                           (:108-115)
 // K1w = w ml (1 - P) and K0 = P - 2 ml (1 - P) are per-(family, step) constants of the table.  At the last step
 // P = P11 = 1, so both branches land on fn (:113-115).  g == 2 exactly (:100-101, f unchanged) has probability ~2^-24 per
 // draw with float g and is not singled out here; the pre-drawn paths, which are compared with the reference, keep it.
@@ -242,7 +242,10 @@ __device__ __forceinline__ AttemptOut mt_attempt(const float4 gm, const float4 p
     const float kdn = fmaf(v3, pw.y, pw.z);
     const float base = fmaf(gt ? 0.0f : upc, fast_rcp(g1), ff);
     const float k = gt ? kdn : pw.w;
-    o.fnew = fmaf(fn - base, k, base);
+    // k fn + (1 - k) base in the form that lands EXACTLY on fn when k == 1 (base - base == 0): the last step of every
+    // trajectory (K1w = 0, K0 = P11 = 1 there), so that a raw arm read at R shows fn itself - which lets the early-stopping
+    // kernel skip that run altogether (hb_lazy.cu) and stay bit-identical
+    o.fnew = fmaf(k, fn, fmaf(-k, base, base));
     return o;
 }
 
@@ -252,7 +255,7 @@ __device__ __forceinline__ float step_folded(float f, float g, float fn, float u
     const bool gt = g > 2.0f;
     const float base = gt ? f : fmaf(upc, fast_rcp(1.0f + g), f);
     const float k = gt ? fmaf(g, K1, K0) : P11;
-    return fmaf(fn - base, k, base);
+    return fmaf(k, fn, fmaf(-k, base, base));
 }
 
 // One arm per lane: runs the lane's Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang -> recurrence until every

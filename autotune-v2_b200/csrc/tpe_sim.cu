@@ -687,8 +687,8 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     int nwarps = AT2_TPE_MAX_WARPS;
     {
-        const char* env_w = getenv("AT2_TPE_WARPS_PER_CTA");
-        if (env_w != nullptr && atoi(env_w) > 0 && atoi(env_w) <= AT2_TPE_MAX_WARPS) nwarps = atoi(env_w);
+        const int w = at2_debug().tpe_warps_per_cta;
+        if (w > 0 && w <= AT2_TPE_MAX_WARPS) nwarps = w;
     }
     while (nwarps > 1 && fixed + (size_t)nwarps * p.warp_bytes > (size_t)max_smem) --nwarps;
     if ((long long)nwarps > n_reps) nwarps = (int)n_reps;

@@ -102,6 +102,12 @@ int32_t at2_func_dims(int32_t func);
 const char* at2_version(void);
 const char* at2_last_error(void);
 
+/* Debug options (tests and measurements only; all zero by default = the library chooses): tile / CTA shapes and code-path
+ * switches that never change a result.  Process-wide; the library never reads the environment.  Names: hb_reps_per_tile,
+ * hb_team_warps, hb_warps_per_cta, hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles,
+ * force_gtab, lazy_reps_per_tile, tpe_warps_per_cta, kf_warps_per_cta, kf_reps_per_tile; "reset" clears all. */
+int at2_debug_option(const char* name, int32_t value);
+
 /* ---- host-only helpers ------------------------------------------------------------------------------------------ */
 
 /* Fill `plan` for Hyperband(R, eta) with the reference's float arithmetic (hyperband_optimiser.py:66-97).
@@ -113,11 +119,15 @@ int at2_bracket_plan(int32_t R, int32_t eta, at2_plan* plan);
 int32_t at2_savgol_window(int32_t R);
 int at2_savgol_rows(int32_t R, int32_t n_rows, const int32_t* rows, double* out);
 
-/* Size in bytes / contents of the per-configuration constant tables consumed by at2_hb_sim_*:
- * Gamma-step parameters (core/simulation_evaluator.py:36-42), the two time-aggressiveness powers
- * (t/(R-1))**nec and (t/(R-1))**(1.1*nec) (:105,:112) per family, and the Savitzky-Golay rows at the checkpoints.
- * `is_f64` selects double (parity path) or float (production path) entries.  The caller copies `host_out` to the
- * device and passes it as `d_tables`. */
+/* Size in bytes / contents of the per-configuration constant tables consumed by at2_hb_sim_*, at2_tpe_sim_f32 and
+ * at2_sim_trajectories_f32: one record per (family, step) with the Marsaglia-Tsang constants of the step's Gamma draw
+ * (core/simulation_evaluator.py:36-42) and the folded constants of the recurrence step built from the two
+ * time-aggressiveness powers (t/(R-1))**nec and (t/(R-1))**(1.1*nec) (:105,:112), the Savitzky-Golay rows at the plan's
+ * checkpoints, and (float) the folded-step table of the pre-drawn path.  `is_f64` selects double (parity path) or float
+ * (production path) entries.  The tables BELONG TO THE PLAN they were built for: the float records flag the plan's
+ * checkpoint positions (the trajectory loop stores a loss where a record is flagged) and the Savitzky-Golay columns are
+ * the plan's checkpoints - pass the same plan to the build and to the launch.  The caller copies `host_out` to the device
+ * and passes it as `d_tables`. */
 int64_t at2_hb_tables_bytes(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64);
 int at2_hb_tables_build(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64, void* host_out);
 
@@ -142,23 +152,35 @@ typedef struct at2_hb_outputs {
 int at2_hb_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                    int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
 
-/* at2_hb_sim_f32 fused with the all-gather of the OFE vector (the one collective of the path: the OFEs of all ranks feed
- * the KDE, experiments/run_simulation.py:156-157 + simulation_evaluation/plot_results.py:11-17).  The OFE of repetition i of
- * this call is additionally stored to element gather_base + i of each of the n_gather device buffers in d_gather (a HOST
- * array of device pointers): the peers' symmetric-memory buffers mapped into this process (stores travel over
- * NVLink / NVSwitch while the kernel is still simulating), or a single NVSwitch multicast address that fans one store out
- * to every GPU.  The caller orders the stores against the readers (a barrier across the ranks after the launch).  Every
- * other argument and output as in at2_hb_sim_f32; out->d_ofe may be NULL. */
-int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
-                          int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* const* d_gather,
-                          int32_t n_gather, int64_t gather_base, void* stream);
+/* Targets of the fused all-gather of the OFE vector (the one collective of the path: the OFEs of all ranks feed the KDE,
+ * experiments/run_simulation.py:156-157 + simulation_evaluation/plot_results.py:11-17).  The OFE of repetition i of a call is
+ * additionally stored to element base + i of every target: the peers' symmetric-memory buffers mapped into this process
+ * (stores travel over NVLink / NVSwitch while the kernel is still simulating), or ONE NVSwitch multicast address that fans a
+ * store out to every GPU - then is_multicast must be 1: the kernel issues multimem.st (the only kind of access the PTX ISA
+ * defines on a multimem address).  The caller orders the stores against the readers (a barrier across the ranks). */
+typedef struct at2_gather {
+    float* d_target[AT2_MAX_PEERS];
+    int32_t n_targets;      /* 1..AT2_MAX_PEERS; exactly 1 when is_multicast */
+    int32_t is_multicast;
+    int64_t base;
+} at2_gather;
 
-/* Same repetitions with early stopping: an arm is only simulated as far as the round that reads it needs (the reference
- * simulates every arm to R on its first evaluate() but only ever reads the checkpoints - SURVEY D5).  Streams and
- * arithmetic are those of at2_hb_sim_f32, so every output is bit-identical to it; out->d_ckpt_loss must be NULL (the
- * losses of unread checkpoints are never computed). */
+/* at2_hb_sim_f32 fused with that all-gather.  Every other argument and output as in at2_hb_sim_f32; out->d_ofe may be NULL. */
+int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                          int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, const at2_gather* gather,
+                          void* stream);
+
+/* Same repetitions with early stopping - the product's default whenever the caller does not ask for the losses of unread
+ * checkpoints: an arm is only simulated as far as the round that reads it needs (the reference simulates every arm to R on
+ * its first evaluate(), benchmarks/opt_function_simulation_problem.py:67-76, but only ever reads the checkpoints - SURVEY
+ * D5), and a raw arm read at R is its target f_n without any simulation (core/simulation_evaluator.py:105-107,113-115).
+ * Streams and arithmetic are those of at2_hb_sim_f32, so every output is bit-identical to it; out->d_ckpt_loss must be NULL
+ * (the losses of unread checkpoints are never computed).  The _gather variant adds the fused all-gather of the OFEs. */
 int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                               int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
+int at2_hb_sim_early_stop_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
+                                     int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, const at2_gather* gather,
+                                     void* stream);
 
 /* Pre-drawn inputs (parity paths): nothing is sampled; the kernel only runs the recurrence, the checkpoint read-out
  * and successive halving.  Per arm: first and target values f_1, f_n (opt_function_simulation_problem.py:61-64),

@@ -6,6 +6,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'autotune-v2_b200'))
 import torch
+from autotune.b200._native import check, lib
 from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
 
 FAM6 = [(1.5, 10, 15, False, 0, 200), (0.5, 7, 10, False, 0, 200), (0.2, 4, 7, True, 0, 200),
@@ -24,9 +25,9 @@ for w in which:
     for n in ns:
         for G in gs:
             if G > 0:
-                os.environ['AT2_HB_LAZY_REPS_PER_TILE'] = str(G)
+                check(lib.at2_debug_option(b'lazy_reps_per_tile', int(G)))
             else:
-                os.environ.pop('AT2_HB_LAZY_REPS_PER_TILE', None)
+                check(lib.at2_debug_option(b'reset', 0))
             for _ in range(5):
                 run_hyperband_repetitions(spec, n, seed=0, early_stop=True)
             torch.cuda.synchronize()

@@ -16,13 +16,13 @@ for name, spec, n in [('branin-flat R81', HyperbandSimSpec('branin', FLAT, 81, 3
                       ('rastrigin-6fam R81', HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10), 100000),
                       ('egg-3fam R243', HyperbandSimSpec('egg', EGG, 243, 3, 10), 20000)]:
     for _ in range(30):          # ~100 ms of work: lets the clocks ramp up before timing
-        run_hyperband_repetitions(spec, n, seed=0)
+        run_hyperband_repetitions(spec, n, seed=0, early_stop=False)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
     e0.record()
     for i in range(reps):
-        out = run_hyperband_repetitions(spec, n, seed=i)
+        out = run_hyperband_repetitions(spec, n, seed=i, early_stop=False)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps

@@ -9,6 +9,7 @@ sys.path.insert(0, os.path.join(ROOT, 'autotune-v2_b200'))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+from autotune.b200._native import check, lib
 from autotune.b200.engine import (HyperbandSimSpec, KnownFnSpec, run_hybrid_repetitions, run_hyperband_repetitions,  # noqa: E402
                                   run_knownfn_hyperband, run_random_repetitions, run_tpe_repetitions)
 from autotune.b200.epdf import density  # noqa: E402
@@ -32,10 +33,10 @@ for func, fams, R, eta in (('rastrigin', FAM6, 81, 3), ('branin', FLAT, 81, 3), 
 spec = HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10)
 run_tpe_repetitions(spec, n, 24, 81, seed=2)
 run_random_repetitions(spec, n, 24, 81, seed=2)
-os.environ['AT2_FORCE_GTAB'] = '1'
+check(lib.at2_debug_option(b'force_gtab', 1))
 run_hyperband_repetitions(spec, n, seed=1, details=True)
 run_hyperband_repetitions(spec, n, seed=1, details=True, early_stop=True)
-del os.environ['AT2_FORCE_GTAB']
+check(lib.at2_debug_option(b'reset', 0))
 for mk, n_arms in ((mnist_domain_problem, 425), (cifar_domain_problem, 300)):
     with redirect_stdout(io.StringIO()):
         prob = mk()

@@ -245,27 +245,28 @@ def test_unusual_plans_run_and_agree_with_independent_halving(func, families, R,
 
 
 @pytest.mark.parametrize('tile', [1, 3, 7, 16, 32])
-def test_early_stopping_tile_widths_do_not_change_outputs(monkeypatch, tile):
+def test_early_stopping_tile_widths_do_not_change_outputs(tile):
     """The early-stopping kernel cuts a job into tiles of G repetitions per warp (chosen from the job size; a small job
     gets narrow tiles), works through a round in chunks of repetitions, lists raw arms ahead of smoothed ones and ranks
     narrow rounds 32 / n repetitions at a time.  None of that may change a bit: every width (forced here) must reproduce
     the full simulation, ragged last tile and last chunk included."""
+    from autotune.b200._native import debug_options
     from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
-    monkeypatch.setenv('AT2_HB_LAZY_REPS_PER_TILE', str(tile))
-    for func, fams, R, eta, noise, mom, n in (('rastrigin', FAM6, 81, 3, 10, 'min', 1000 + 13), ('branin', FLAT, 81, 3, 0, 'min', 997),
-                                              ('egg', FAM6[:3], 243, 3, 10, 'min', 101), ('wave', FAM6[2:3], 27, 3, 10, 'max', 500),
-                                              ('camel', FAM6, 16, 2, 1, 'min', 333)):
-        spec = HyperbandSimSpec(func, fams, R, eta, noise, 'uniform', mom)
-        full = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True)
-        lazy = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True, early_stop=True)
-        for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors'):
-            assert torch.equal(full[k], lazy[k]), (func, k)
-    monkeypatch.setenv('AT2_HB_NO_SPLIT', '1')          # mixed passes as before the raw-first list
-    spec = HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10)
-    a = run_hyperband_repetitions(spec, 700, seed=5, details=True)
-    b = run_hyperband_repetitions(spec, 700, seed=5, details=True, early_stop=True)
-    for k in ('ofe', 'ofe_arm', 'round_best', 'survivors'):
-        assert torch.equal(a[k], b[k]), k
+    with debug_options(lazy_reps_per_tile=tile):
+        for func, fams, R, eta, noise, mom, n in (('rastrigin', FAM6, 81, 3, 10, 'min', 1000 + 13), ('branin', FLAT, 81, 3, 0, 'min', 997),
+                                                  ('egg', FAM6[:3], 243, 3, 10, 'min', 101), ('wave', FAM6[2:3], 27, 3, 10, 'max', 500),
+                                                  ('camel', FAM6, 16, 2, 1, 'min', 333)):
+            spec = HyperbandSimSpec(func, fams, R, eta, noise, 'uniform', mom)
+            full = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True, early_stop=False)
+            lazy = run_hyperband_repetitions(spec, n, seed=29, rep_offset=3, details=True, early_stop=True)
+            for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors'):
+                assert torch.equal(full[k], lazy[k]), (func, k)
+    with debug_options(lazy_reps_per_tile=tile, hb_no_split=1):          # mixed passes as before the raw-first list
+        spec = HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10)
+        a = run_hyperband_repetitions(spec, 700, seed=5, details=True, early_stop=False)
+        b = run_hyperband_repetitions(spec, 700, seed=5, details=True, early_stop=True)
+        for k in ('ofe', 'ofe_arm', 'round_best', 'survivors'):
+            assert torch.equal(a[k], b[k]), k
 
 
 def test_egg4_extension_flat_family_ofe_is_the_function_value():
@@ -295,27 +296,26 @@ def test_egg4_extension_flat_family_ofe_is_the_function_value():
         run_hybrid_repetitions(spec, 10, 'none')
 
 
-def test_global_memory_tables_are_bit_identical_to_shared_memory_tables(monkeypatch):
+def test_global_memory_tables_are_bit_identical_to_shared_memory_tables():
     """Plans too large for shared memory read their constant tables from global memory (GTAB kernel variants); forced
     here on ordinary plans, every output must equal the shared-memory variant's bit for bit - full and early-stopping."""
     from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
     for func, fams, R in (('rastrigin', FAM6, 81), ('branin', FLAT, 81), ('egg', FAM6[:3], 243)):
         spec = HyperbandSimSpec(func, fams, R, 3, 10)
         n = 600 if R < 243 else 150
-        monkeypatch.delenv('AT2_FORCE_GTAB', raising=False)
-        a = run_hyperband_repetitions(spec, n, seed=23, details=True)
+        from autotune.b200._native import debug_options
+        a = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=False)
         al = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=True)
-        monkeypatch.setenv('AT2_FORCE_GTAB', '1')
-        b = run_hyperband_repetitions(spec, n, seed=23, details=True)
-        bl = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=True)
-        monkeypatch.delenv('AT2_FORCE_GTAB')
+        with debug_options(force_gtab=1):
+            b = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=False)
+            bl = run_hyperband_repetitions(spec, n, seed=23, details=True, early_stop=True)
         for k in a:
             assert torch.equal(a[k], b[k]), (func, k)
         for k in al:
             assert torch.equal(al[k], bl[k]) and torch.equal(al[k], a[k]), (func, k)
 
 
-def test_tile_halving_is_bit_identical_to_per_repetition_halving(monkeypatch):
+def test_tile_halving_is_bit_identical_to_per_repetition_halving():
     """Float path, warp-private tiles: the repetitions of a tile are halved together, narrow rounds side by side
     (halving.cuh tile_halving_f32).  Every output must equal the per-repetition path's, ragged last tiles, maximisation,
     eta = 2 / 4 plans and heavily tied losses included."""
@@ -325,26 +325,24 @@ def test_tile_halving_is_bit_identical_to_per_repetition_halving(monkeypatch):
                                               ('camel', FAM6, 16, 2, 1, 'min', 777), ('rastrigin', FAM6, 64, 4, 10, 'min', 500),
                                               ('rastrigin', FAM6, 100, 3, 10, 'min', 400), ('branin', FAM6[:2], 2, 2, 10, 'min', 100)):
         spec = HyperbandSimSpec(func, fams, R, eta, noise, 'uniform', mom)
-        monkeypatch.delenv('AT2_HB_NO_TILE_HALVING', raising=False)
-        a = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True)
-        monkeypatch.setenv('AT2_HB_NO_TILE_HALVING', '1')
-        b = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True)
-        monkeypatch.delenv('AT2_HB_NO_TILE_HALVING')
+        from autotune.b200._native import debug_options
+        a = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True, early_stop=False)
+        with debug_options(hb_no_tile_halving=1):
+            b = run_hyperband_repetitions(spec, n, seed=31, rep_offset=5, details=True, early_stop=False)
         for k in a:
             assert torch.equal(a[k], b[k]), (func, R, k)
 
 
-def test_raw_smoothed_split_passes_do_not_change_outputs(monkeypatch):
+def test_raw_smoothed_split_passes_do_not_change_outputs():
     """Mixed families: raw and smoothed arms of a tile run in separate warp passes (hb_sim.cu).  Disabling the split must
     give the same bits."""
     from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
     for func, fams, R, sched in (('rastrigin', FAM6, 81, 'uniform'), ('egg', FAM6[:3], 243, 'round-robin'), ('wave', FAM6, 27, 'uniform')):
         spec = HyperbandSimSpec(func, fams, R, 3, 10, sched)
-        monkeypatch.delenv('AT2_HB_NO_SPLIT', raising=False)
-        a = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True)
-        monkeypatch.setenv('AT2_HB_NO_SPLIT', '1')
-        b = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True)
-        monkeypatch.delenv('AT2_HB_NO_SPLIT')
+        from autotune.b200._native import debug_options
+        a = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True, early_stop=False)
+        with debug_options(hb_no_split=1):
+            b = run_hyperband_repetitions(spec, 500, seed=29, rep_offset=3, details=True, early_stop=False)
         for k in a:
             assert torch.equal(a[k], b[k]), (func, k)
 
@@ -391,6 +389,12 @@ def test_fused_gather_entry_point_on_one_gpu():
     for buf in (a, b):
         assert torch.equal(buf[base:base + n], want['ofe'])
         assert (buf[:base] == -7.0).all() and (buf[base + n:] == -7.0).all()
+    # the early-stopping kernel with the same fused gather (the product's default path at N > 1)
+    c = torch.full((total,), -7.0, device=dev)
+    outs = torch.ops.at2.hb_sim_gather(spec.tables(dev, torch.float32), spec.plan_bytes, spec.cfg_bytes, n, base, 8, c,
+                                       [c.data_ptr()], base, False, True)
+    assert torch.equal(outs[0], want['ofe']) and torch.equal(c[base:base + n], want['ofe'])
+    assert (c[:base] == -7.0).all() and (c[base + n:] == -7.0).all()
     with pytest.raises(RuntimeError):
         torch.ops.at2.hb_sim_gather(spec.tables(dev, torch.float32), spec.plan_bytes, spec.cfg_bytes, n, base, 8, a,
                                     [a.data_ptr()], total - 5)            # would write past the buffer

@@ -191,11 +191,17 @@ def test_history_evaluators_carry_the_arms_real_family():
         with redirect_stdout(io.StringIO()):
             opt.run_optimisation(problem)
         distinct = set()
-        for e in opt.eval_history:
+        times = [r['time'] for r in spec.rounds()]
+        for i, e in enumerate(opt.eval_history):
             ev = e.evaluator
             fxy = NOISE_FREE_FUNCTIONS['branin'](ev.arm.x, ev.arm.y)
-            distinct.add(ev.start_shift if hasattr(ev, 'start_shift') else None)
-            if isinstance(opt, TpeOptimiser):
-                # evaluated at r = 1: the recorded loss is the start value f - start_shift of the evaluator's family
-                assert abs((fxy - e.optimisation_goals.fval) - ev.start_shift) < 1e-2
-        assert len(distinct) > 1
+            distinct.add(ev.start_shift)
+            gap = fxy - e.optimisation_goals.fval
+            if isinstance(opt, TpeOptimiser) or times[i] == 1:
+                # read at r = 1: the recorded loss is the start value f - start_shift of the arm's real family
+                assert abs(gap - ev.start_shift) < 1e-2, (i, gap, ev.start_shift)
+            elif times[i] == 81:
+                # read at r = R: a raw arm has landed on f_n = f - end_shift of its real family
+                assert abs(gap - ev.end_shift) < 1e-2, (i, gap, ev.end_shift)
+        if isinstance(opt, TpeOptimiser):
+            assert len(distinct) > 1          # 30 random arms: several families
