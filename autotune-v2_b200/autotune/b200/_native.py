@@ -118,6 +118,9 @@ def _load():
         'at2_ks_statistic_f32': (C.c_int, [vp, i64, vp, i64, vp, vp]),
         'at2_kde_workspace_floats': (i64, [i64, i32]),
         'at2_kde_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, vp, vp, i64, vp]),
+        'at2_kde_partial_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, C.POINTER(C.c_void_p), i32, i32,
+                                          i64, vp, i64, vp]),
+        'at2_kde_combine_f64': (C.c_int, [vp, i32, i32, i64, C.c_double, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

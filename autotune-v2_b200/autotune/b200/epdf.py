@@ -53,15 +53,22 @@ class FusedGather:
     Built by the collective `FusedGather.create`, which returns None (on every rank alike) when symmetric memory cannot be
     set up; callers then fall back to `gather_slices` (NCCL)."""
 
-    def __init__(self, n_total, device, group, bufs, handles, use_multicast):
+    MAX_GRID = 4096      # grid points a sharded KDE can exchange (the reference uses 1000)
+
+    def __init__(self, n_total, device, group, bufs, handles, use_multicast, kbufs=None, khandles=None):
         self.group = group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.n_total, self.device = int(n_total), torch.device(device)
         self.bufs, self.handles, self.targets = bufs, handles, []
-        for hdl in handles:
+
+        def targets_of(hdl):
             mc = int(getattr(hdl, 'multicast_ptr', 0) or 0) if use_multicast else 0
-            self.targets.append([mc] if mc else [int(p) for p in hdl.buffer_ptrs])
+            return [mc] if mc else [int(p) for p in hdl.buffer_ptrs]
+        self.targets = [targets_of(h) for h in handles]
         self.multicast = len(self.targets[0]) == 1 and self.world > 1
+        # float64 slots [world][MAX_GRID] for the ranks' partial kernel sums of the sharded KDE (two alternate, like bufs)
+        self.kbufs, self.khandles = kbufs, khandles
+        self.ktargets = [targets_of(h) for h in khandles] if khandles else None
         self.turn = 0
 
     @classmethod
@@ -85,6 +92,7 @@ class FusedGather:
             bufs = None
         if not all_ok(bufs is not None):
             return None
+        kbufs = khandles = None
         try:
             handles = [symm_mem.rendezvous(b, group) for b in bufs]
             ok = all(len(h.buffer_ptrs) == dist.get_world_size(group) for h in handles)
@@ -92,7 +100,16 @@ class FusedGather:
             ok = False
         if not all_ok(ok):
             return None
-        return cls(n_total, device, group, bufs, handles, use_multicast)
+        try:   # optional: the slots of the sharded KDE; without them the KDE runs over the gathered vector on every rank
+            kbufs = [symm_mem.empty(dist.get_world_size(group) * cls.MAX_GRID, dtype=torch.float64, device=torch.device(device))
+                     for _ in range(2)]
+            khandles = [symm_mem.rendezvous(b, group) for b in kbufs]
+            kok = all(len(h.buffer_ptrs) == dist.get_world_size(group) for h in khandles)
+        except Exception:  # noqa: BLE001
+            kok = False
+        if not all_ok(kok):
+            kbufs = khandles = None
+        return cls(n_total, device, group, bufs, handles, use_multicast, kbufs, khandles)
 
     def run(self, spec, seed, early_stop=True):
         """This rank's share of the job's repetitions; returns the gathered [n_total] OFE vector (a view of a symmetric
@@ -105,6 +122,29 @@ class FusedGather:
                                     int(seed), buf, targets, lo, self.multicast, bool(early_stop))
         hdl.barrier(channel=0)          # on the current stream: every rank's stores are in every buffer after it
         return buf
+
+    def run_epdf(self, spec, seed, start, end, bandwidth, grid_points=1000, kernel='epanechnikov', early_stop=True):
+        """The whole EPDF-OFE step with the KDE sharded as well: this rank's repetitions (OFEs scattered into every rank's
+        buffer by the kernel) -> kernel sums of its OWN slice on the grid (float64, scattered into every rank's slot array the
+        same way) -> ONE barrier across the ranks -> the ranks' sums added in rank order and normalised.  Every rank ends up
+        with the same gathered vector and the same density bits, and evaluates only 1/world of the N x G pair terms.
+        Returns (ofes [n_total], density [grid_points])."""
+        if self.ktargets is None or grid_points > self.MAX_GRID:
+            ofes = self.run(spec, seed, early_stop)
+            return ofes, density(ofes, start, end, bandwidth, grid_points, kernel)
+        lo, hi = shard_range(self.n_total, self.rank, self.world)
+        turn = self.turn
+        buf, hdl, targets = self.bufs[turn], self.handles[turn], self.targets[turn]
+        kbuf, ktargets = self.kbufs[turn], self.ktargets[turn]
+        self.turn ^= 1
+        local = torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo,
+                                            lo, int(seed), buf, targets, lo, self.multicast, bool(early_stop))[0]
+        # the kernel sums are taken over the launch's own (locally written) OFE output, not over the symmetric buffer
+        torch.ops.at2.kde_partial(local, float(start), float(end), int(grid_points), float(bandwidth), KERNEL_IDS[kernel], kbuf,
+                                  ktargets, self.multicast, self.rank * int(grid_points))
+        hdl.barrier(channel=0)          # covers both scatters: they precede it in stream order on every rank
+        dens = torch.ops.at2.kde_combine(kbuf, self.world, int(grid_points), self.n_total, float(bandwidth), KERNEL_IDS[kernel])
+        return buf, dens
 
 
 def density(ofes, start, end, bandwidth, grid_points=1000, kernel='epanechnikov'):
@@ -140,9 +180,8 @@ def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=100
     if fused is not None and runner is None:
         if fused.n_total != int(n_reps):
             raise ValueError(f'FusedGather was built for {fused.n_total} repetitions, not {n_reps}')
-        ofes = fused.run(spec, seed, early_stop)
-        return {'ofes': ofes, 'density': density(ofes, start, end, bandwidth, grid_points, kernel),
-                'grid': np.linspace(start, end, grid_points)}
+        ofes, dens = fused.run_epdf(spec, seed, start, end, bandwidth, grid_points, kernel, early_stop)
+        return {'ofes': ofes, 'density': dens, 'grid': np.linspace(start, end, grid_points)}
     lo, hi = shard_range(n_reps, rank, world)
     if runner is None:
         def runner(spec_, n, seed_, off, dev):

@@ -167,6 +167,42 @@ def kde(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: 
     return dens
 
 
+@torch.library.custom_op('at2::kde_partial', mutates_args=('parts',), device_types='cuda')
+def kde_partial(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int,
+                parts: torch.Tensor, target_ptrs: List[int], multicast: bool, slot_offset: int) -> None:
+    """The sharded form of at2::kde (at2_kde_partial_f32): the UNNORMALISED float64 kernel sums of the samples `x` go to
+    elements slot_offset .. slot_offset + grid_points - 1 of every buffer in `target_ptrs` (device addresses of the ranks'
+    symmetric buffers, or one NVSwitch multicast address with multicast=True).  `parts` is this rank's own buffer (declared
+    mutated; it must be among the targets)."""
+    _require_cuda(x, 'x')
+    if x.dtype != torch.float32 or x.dim() != 1 or not x.is_contiguous():
+        raise RuntimeError('x must be a contiguous 1-D float32 tensor')
+    if parts.dtype != torch.float64 or slot_offset < 0 or slot_offset + grid_points > parts.numel():
+        raise RuntimeError('parts must be a float64 buffer holding elements slot_offset .. slot_offset + grid_points')
+    if not 1 <= len(target_ptrs) <= nat.MAX_PEERS or (multicast and len(target_ptrs) != 1):
+        raise RuntimeError(f'between 1 and {nat.MAX_PEERS} targets (exactly one multicast address)')
+    n = x.numel()
+    with torch.cuda.device(x.device):
+        ws_n = nat.lib.at2_kde_workspace_floats(n, grid_points)
+        ws = torch.empty(max(ws_n, 1), device=x.device, dtype=torch.float32)
+        ptrs = (C.c_void_p * len(target_ptrs))(*target_ptrs)
+        nat.check(nat.lib.at2_kde_partial_f32(x.data_ptr(), n, start, end, grid_points, bandwidth, kernel, ptrs, len(target_ptrs),
+                                              int(multicast), slot_offset, ws.data_ptr(), ws_n, _stream_ptr(x.device)))
+
+
+@torch.library.custom_op('at2::kde_combine', mutates_args=(), device_types='cuda')
+def kde_combine(parts: torch.Tensor, n_parts: int, grid_points: int, n_total: int, bandwidth: float, kernel: int) -> torch.Tensor:
+    """density = norm * (sum of the first n_parts slots of `parts`, in slot order) (at2_kde_combine_f64)."""
+    _require_cuda(parts, 'parts')
+    if parts.dtype != torch.float64 or not parts.is_contiguous() or parts.numel() < n_parts * grid_points:
+        raise RuntimeError('parts must be a contiguous float64 buffer of at least n_parts * grid_points elements')
+    with torch.cuda.device(parts.device):
+        dens = torch.empty(grid_points, device=parts.device, dtype=torch.float32)
+        nat.check(nat.lib.at2_kde_combine_f64(parts.data_ptr(), n_parts, grid_points, n_total, bandwidth, kernel,
+                                              dens.data_ptr(), _stream_ptr(parts.device)))
+    return dens
+
+
 def _opt_ptr(t):
     return t.data_ptr() if t is not None and t.numel() > 0 else None
 

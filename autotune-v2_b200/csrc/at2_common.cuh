@@ -34,7 +34,7 @@ void at2_reset_launch_count();
 // measurements.  Process-wide, all zero by default (= the library decides); never read from the environment.
 struct At2Debug {
     int hb_reps_per_tile, hb_team_warps, hb_warps_per_cta;   // > 0: override choose_launch (hb_sim.cu)
-    int hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
+    int hb_no_split, hb_family_sort, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
     int force_gtab;                                           // constant tables from global memory on any plan
     int lazy_reps_per_tile;                                   // hb_lazy.cu tile width
     int tpe_warps_per_cta;                                    // tpe_sim.cu
@@ -58,30 +58,39 @@ static int at2_resident_by_regs(Kern kern, int block, int* out) {
 }
 
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
-// rec[f][t] f in [0,F), t in [0,R]: one 8-real record per (family, step), so a lane fetches everything step t needs with
-//          two 128-bit loads from one address.  Row 0 is unused; row R is a sentinel whose c is NaN, so the acceptance
-//          test of a finished lane can never pass and no bounds check is needed in the inner loop.
-//   float tables (Philox paths): {d, c, d*log2(e), d*log2(e) + 32, +-w, K1w, K0, P11}
+// rec: one 12-real record per (family, step): row r = f * rows + t with t in [0,R] and rows = at2_rec_rows(R) (R + 1
+//      made odd, see below).  Row t = 0 of a family is unused; row R is a sentinel whose c is NaN, so the acceptance test
+//      of a finished lane can never pass and no bounds check is needed in the inner loop.
+//   float tables (Philox paths): two 128-bit loads from one address (+0, +16 bytes), 16 bytes spare:
+//          {d, c, d*log2(e), d*log2(e) + 32 | +-w, K1w, K0, P11 | 0, 0, 0, 0}
 //          d, c: Marsaglia-Tsang constants of the Gamma draw of step t; w = d * scale (Gamma draw g = w v^3), its SIGN BIT
 //          flags the steps whose position is a checkpoint of the plan the table was built for (the trajectory loop stores
 //          the loss of a flagged step, sim_core.cuh); K1w = w ml (1 - P), K0 = P - 2 ml (1 - P), ml = ml_agg / 100,
 //          P = (t/(R-1))**nec, P11 = (t/(R-1))**(1.1*nec): the folded down step k = v^3 K1w + K0 (sim_core.cuh mt_attempt).
-//   double tables (pre-drawn parity path): {d, c, d*log2(e), d*scale, P, P11, 1-P, 0}
+//          Why 48-byte records: a 128-bit shared-memory load is served per quarter warp, conflict-free when its distinct
+//          16-byte words fall into distinct word slots modulo 8.  With 32-byte records each of the two loads used only
+//          every other slot (ncu, six families: the first use of a record was the top stall); a stride of three slots
+//          walks through all eight, so lanes spread over up to 8 consecutive steps of one family never collide, and the
+//          odd `rows` puts the same step of different families into different slots.
+//   double tables (pre-drawn parity path): {d, c, d*log2(e), d*scale, P, P11, 1-P, 0, 0, 0, 0, 0}
 // sg[t][c]  t in [0,R], c in [0,sg_stride): Savitzky-Golay weight of raw[t] in the smoothed value at checkpoint c
-//          (present only when some family is smooth; row R is zero).
-// pw[f][t] 4 reals {K1 = ml (1 - P), K0, P11, 0}: the folded step on a given Gamma draw (pre-drawn float path only; the
+//          (present only when some family is smooth; row R is zero).  sg_stride = 12 (the record stride, so that the row of
+//          a lane's step is its record offset away from sg[0]) up to 12 checkpoints, 24 above.
+// pwt[r] 4 reals {K1 = ml (1 - P), K0, P11, 0}: the folded step on a given Gamma draw (pre-drawn float path only; the
 //          Philox kernels do not stage it).
-#define AT2_REC 8
+#define AT2_REC 12
 #define AT2_PW 4
-__host__ __device__ inline int at2_sg_stride(int n_ckpts) { return n_ckpts <= 4 ? 4 : (n_ckpts <= 8 ? 8 : 16); }
+__host__ __device__ inline int at2_sg_stride(int n_ckpts) { return n_ckpts <= 12 ? 12 : 24; }
+__host__ __device__ inline int at2_rec_rows(int R) { return (R + 1) | 1; }
 
 struct At2TableLayout {
     int R, F, has_smooth, sg_stride;
+    __host__ __device__ int rows() const { return at2_rec_rows(R); }
     __host__ __device__ int off_rec() const { return 0; }
-    __host__ __device__ int off_sg() const { return AT2_REC * F * (R + 1); }   // 32-byte aligned
+    __host__ __device__ int off_sg() const { return AT2_REC * F * rows(); }    // 16-byte aligned
     __host__ __device__ int off_pw() const { return off_sg() + (has_smooth ? sg_stride * (R + 1) : 0); }
     __host__ __device__ int total_philox() const { return off_pw(); }          // what a Philox kernel stages
-    __host__ __device__ int total() const { return off_pw() + AT2_PW * F * (R + 1); }
+    __host__ __device__ int total() const { return off_pw() + AT2_PW * F * rows(); }
 };
 
 static inline int at2_check_gather(const at2_gather* g, const char* who) {
@@ -160,6 +169,10 @@ static inline void at2_round_keys(uint64_t seed, uint32_t* rk) {
 // multimem.* instructions may touch such an address (PTX ISA 8.1+: any other access is undefined behaviour).
 __device__ __forceinline__ void multimem_st_f32(float* mc_addr, float v) {
     asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+
+__device__ __forceinline__ void multimem_st_f64(double* mc_addr, double v) {
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc_addr), "d"(v) : "memory");
 }
 
 // RNG stream tags (4th counter word)

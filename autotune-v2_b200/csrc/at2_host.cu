@@ -28,7 +28,7 @@ extern "C" int at2_debug_option(const char* name, int32_t value) {
     }
     const struct { const char* name; int* field; } table[] = {
         {"hb_reps_per_tile", &g_debug.hb_reps_per_tile}, {"hb_team_warps", &g_debug.hb_team_warps},
-        {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split},
+        {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split}, {"hb_family_sort", &g_debug.hb_family_sort},
         {"hb_equal_tiles", &g_debug.hb_equal_tiles}, {"hb_no_tile_halving", &g_debug.hb_no_tile_halving},
         {"hb_static_schedule", &g_debug.hb_static_schedule}, {"hb_singles", &g_debug.hb_singles},
         {"force_gtab", &g_debug.force_gtab}, {"lazy_reps_per_tile", &g_debug.lazy_reps_per_tile},
@@ -256,7 +256,7 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
     const double log2e = 1.4426950408889634;
     T* rec = out + L.off_rec();
     T* pwt = out + L.off_pw();
-    const int rows = R + 1;
+    const int rows = L.rows();
     for (int t = 1; t < R; ++t) {
         const double m = (double)((R + 1) - t);                 // n - time with n = R + 1 (:98)
         const double root = sqrt(k * k + 4 * m);                // :37
@@ -270,6 +270,7 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
         for (int q = 0; q < plan->n_ckpts; ++q) is_ckpt |= plan->ckpt_time[q] - 1 == t;
         for (int f = 0; f < F; ++f) {
             T* row = rec + (size_t)AT2_REC * (f * rows + t);
+            T* rpw = row + 4;
             const double P = pow(frac, cfg->fam[f].nec_agg);          // :105
             const double P11 = pow(frac, 1.1 * cfg->fam[f].nec_agg);  // :112
             const double ml = cfg->fam[f].ml_agg / 100.0, w = d * scale;
@@ -279,10 +280,10 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
             row[2] = (T)(d * log2e);
             if (f32) {
                 row[3] = (T)(d * log2e + 32.0);
-                row[4] = (T)(is_ckpt ? -w : w);
-                row[5] = (T)(w * K1);
-                row[6] = (T)K0;
-                row[7] = (T)P11;
+                rpw[0] = (T)(is_ckpt ? -w : w);
+                rpw[1] = (T)(w * K1);
+                rpw[2] = (T)K0;
+                rpw[3] = (T)P11;
             } else {
                 row[3] = (T)w;
                 row[4] = (T)P;
@@ -295,9 +296,10 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
     }
     for (int f = 0; f < F; ++f) {   // sentinel row R: NaN slope -> the acceptance test can never pass
         T* row = rec + (size_t)AT2_REC * (f * rows + R);
+        T* rpw = row + 4;
         row[0] = (T)1, row[1] = (T)NAN, row[2] = (T)log2e;
         if (f32)
-            row[3] = (T)(log2e + 32.0), row[4] = (T)1, row[5] = (T)0, row[6] = (T)0, row[7] = (T)1;
+            row[3] = (T)(log2e + 32.0), rpw[0] = (T)1, rpw[1] = (T)0, rpw[2] = (T)0, rpw[3] = (T)1;
         else
             row[3] = (T)1, row[4] = (T)1, row[5] = (T)1, row[6] = (T)0;
     }

@@ -305,7 +305,7 @@ static int early_stop_impl(const at2_plan* plan, const at2_sim_config* cfg, cons
         p.fam[f].s0 = (float)cfg->fam[f].start_shift;
         p.fam[f].s1 = (float)cfg->fam[f].end_shift;
         p.fam[f].smooth = cfg->fam[f].is_smooth;
-        p.fam[f].pw_off = f * (plan->R + 1);
+        p.fam[f].pw_off = f * at2_rec_rows(plan->R);
     }
     p.dims = at2_func_dims(cfg->func);
     {

@@ -48,6 +48,7 @@ struct Params {
     int dyn_slot;     // >= 0: warp-private tiles are handed out through the device counter pair g_sched[dyn_slot]
     int tile_halving; // float path, warp-private tiles: the tile's repetitions are halved together (halving.cuh tile_halving_f32)
     int km_a, km_b;   // entries of a repetition's two survivor-id buffers in that mode
+    int class_sort_only;   // debug: sort the tile's arms into raw / smoothed only, not by family
     int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
     int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
     int n_teams;      // teams per CTA
@@ -89,6 +90,7 @@ struct SchedSlot {
 };
 #define AT2_SCHED_SLOTS 64
 __device__ SchedSlot g_sched[AT2_SCHED_SLOTS];
+static std::atomic<unsigned> g_launch_seq{0};   // one sequence for every kernel variant: consecutive launches, distinct slots
 
 // Register cap 80 (65536 / 768): shared memory (a 3-repetition tile per warp) holds about 24 warps per SM anyway - three
 // 8-warp CTAs when the constant tables are small, ONE 24-warp CTA when they are large (six families: 18 KB per CTA), see
@@ -150,47 +152,83 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
 
         // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
         bool split_done = false;
-        if constexpr (MODE == MODE_PHILOX && HAS_SMOOTH) {
+        if constexpr (MODE == MODE_PHILOX) {
             if (p.split_cap > 0) {
                 // Families mix raw and Savitzky-Golay-smoothed arms.  A smoothed arm accumulates C dot products along its
-                // trajectory; in a mixed warp pass every lane pays for them.  So this warp first lists its items with the raw
-                // arms in front and the smoothed ones at the back (the family of an arm is one Philox block away), then runs
-                // the passes that hold only raw arms through the lean loop.  The list aliases the halving sort scratch.
-                // Every arm is simulated by the same arithmetic either way: outputs do not change by a bit.
-                unsigned short* order = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride)) +
-                                        (size_t)wteam * p.split_cap;
+                // trajectory and in a mixed warp pass every lane pays for them.  So this warp first lists its items with the raw
+                // arms in front and the smoothed ones at the back (the family of an arm is one Philox block away; a counting
+                // sort over classes - or, debug option hb_family_sort, over families), then runs the passes that hold only raw
+                // arms through the lean loop.  The list and the classes noted by the counting sweep alias the halving sort
+                // scratch.  Every arm is simulated by the same arithmetic either way: outputs do not change by a bit.
                 const int cap = p.split_cap;
-                int n_raw = 0, n_sm = 0;
-                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
+                unsigned short* order = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride)) +
+                                        (size_t)wteam * ((cap * 3 + 1) / 2);
+                unsigned char* famb = reinterpret_cast<unsigned char*>(order + cap);
+                int cnt[AT2_MAX_FAMILIES];
+#pragma unroll
+                for (int f = 0; f < AT2_MAX_FAMILIES; ++f) cnt[f] = 0;
+                int slot = lane;
+                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32, slot += 32) {
                     const int i = base + lane;
                     const bool act = i < n_items;
                     const int ii = act ? i : 0;
                     const int rep_l = ii / A, arm = ii - rep_l * A;
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
-                    const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
-                    const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
-                    const unsigned below = (1u << lane) - 1u;
-                    if (act) order[sm ? cap - 1 - (n_sm + __popc(m_sm & below)) : n_raw + __popc(m_raw & below)] = (unsigned short)i;
-                    n_raw += __popc(m_raw), n_sm += __popc(m_sm);
+                    int fam = act ? arm_family(p.sp, gid, arm) : 255;
+                    // two classes (raw, smoothed), arms in their original order within a class; debug option hb_family_sort
+                    // sorts by family instead (measured slower: 3.27 vs 3.12 ms on the six-family job)
+                    if (p.class_sort_only && act) fam = (HAS_SMOOTH && p.fam[fam].smooth != 0) ? 1 : 0;
+                    famb[slot] = (unsigned char)fam;
+#pragma unroll
+                    for (int f = 0; f < AT2_MAX_FAMILIES; ++f)
+                        if (f < F) cnt[f] += __popc(__ballot_sync(0xffffffffu, fam == f));
+                }
+                // first list position of each family: raw families in index order, then the smoothed ones
+                int off[AT2_MAX_FAMILIES], n_raw = 0, n_all = 0;
+                auto smooth_key = [&](int f) { return p.class_sort_only ? f == 1 : (HAS_SMOOTH && p.fam[f].smooth != 0); };
+#pragma unroll
+                for (int f = 0; f < AT2_MAX_FAMILIES; ++f) {
+                    off[f] = 0;
+                    if (f < F && !smooth_key(f)) off[f] = n_raw, n_raw += cnt[f];
+                }
+                n_all = n_raw;
+#pragma unroll
+                for (int f = 0; f < AT2_MAX_FAMILIES; ++f)
+                    if (f < F && smooth_key(f)) off[f] = n_all, n_all += cnt[f];
+                __syncwarp();
+                slot = lane;
+                const unsigned below = (1u << lane) - 1u;
+                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32, slot += 32) {
+                    const int fam = famb[slot];
+                    int pos = -1;
+#pragma unroll
+                    for (int f = 0; f < AT2_MAX_FAMILIES; ++f) {
+                        if (f < F) {
+                            const unsigned m = __ballot_sync(0xffffffffu, fam == f);
+                            if (fam == f) pos = off[f] + __popc(m & below);
+                            off[f] += __popc(m);
+                        }
+                    }
+                    if (pos >= 0) order[pos] = (unsigned short)(base + lane);
                 }
                 __syncwarp();
-                for (int k = 0; k < n_raw + n_sm; k += 32) {
+                for (int k = 0; k < n_all; k += 32) {
                     const int q = k + lane;
-                    const bool active = q < n_raw + n_sm;
-                    const int ii = active ? (int)order[q < n_raw ? q : cap - 1 - (q - n_raw)] : 0;
+                    const bool active = q < n_all;
+                    const int ii = active ? (int)order[q] : 0;
                     const int rep_l = ii / A, arm = ii - rep_l * A;
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
                     const ArmDraw d = draw_arm(p.sp, gid, arm);
                     const Fam<T> fam = p.fam[d.fam];
                     const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                     const float fn = f - (float)fam.s1, f1 = (f + p.sp.noise * d.z) - (float)fam.s0;
-                    if (k + 32 <= n_raw)
+                    if (!HAS_SMOOTH || k + 32 <= n_raw)
                         philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.up,
                                                                     fam.pw_off, gid, p.sp.rk, R, s_ck + ii, p.stride, C);
                     else
-                        philox_trajectory<T, true, CK, false, GTAB>(tb, active, fam.smooth != 0, f1, fn,
-                                                                    (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
-                                                                    p.stride, C);
+                        philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
+                                                                          (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
+                                                                          p.stride, C);
                 }
                 split_done = true;
             }
@@ -444,8 +482,7 @@ int launch_one(const Params<T>& p, const LaunchCfg<T>& lc, cudaStream_t st) {
     // (< teams * G + G repetitions) goes out as single repetitions.  Repetition ids do not change, results neither.
     Params<T> q = p;
     const long long teams = (long long)grid * q.n_teams, full_tiles = q.n_reps / q.G;
-    static std::atomic<unsigned> launch_seq{0};
-    q.dyn_slot = (q.team_warps == 1 && !at2_debug().hb_static_schedule) ? (int)(launch_seq.fetch_add(1) % AT2_SCHED_SLOTS) : -1;
+    q.dyn_slot = (q.team_warps == 1 && !at2_debug().hb_static_schedule) ? (int)(g_launch_seq.fetch_add(1) % AT2_SCHED_SLOTS) : -1;
     if (q.dyn_slot >= 0) {
         // dynamic: G-repetition tiles, then `singles` single repetitions per warp to even out the finish
         const int singles = opt_int(at2_debug().hb_singles, 1);
@@ -494,7 +531,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
         p->fam[f].s0 = (T)cfg->fam[f].start_shift;
         p->fam[f].s1 = (T)cfg->fam[f].end_shift;
         p->fam[f].smooth = cfg->fam[f].is_smooth;
-        p->fam[f].pw_off = f * (plan->R + 1);
+        p->fam[f].pw_off = f * at2_rec_rows(plan->R);
     }
     p->dims = at2_func_dims(cfg->func);
     p->sp.func = cfg->func, p->sp.F = cfg->n_families, p->sp.scheduler = cfg->scheduler, p->descending = cfg->descending;
@@ -511,14 +548,16 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;
     p->sort_warps = lc->team_warps < lc->G ? lc->team_warps : lc->G;
-    // raw / smoothed arms in separate warp passes when the families mix both and a warp's order list fits in the team's sort
-    // scratch, which it aliases (see the kernel); debug option hb_no_split disables it
-    int n_smooth = 0;
-    for (int f = 0; f < cfg->n_families; ++f) n_smooth += cfg->fam[f].is_smooth ? 1 : 0;
+    // raw / smoothed arms in separate warp passes when the families mix both and a warp's list and noted classes fit in the
+    // team's sort scratch, which they alias (see the kernel); debug option hb_no_split disables it
     const int cap = ((lc->stride / 32 + lc->team_warps - 1) / lc->team_warps) * 32;
     const size_t scratch = (size_t)p->sort_warps * lc->npad * (sizeof(typename KeyOf<T>::type) + 2 * sizeof(unsigned short));
-    p->split_cap = (n_smooth > 0 && n_smooth < cfg->n_families && (size_t)cap * 2 * lc->team_warps <= scratch &&
-                    lc->stride < 65536 && !at2_debug().hb_no_split) ? cap : 0;
+    int n_smooth = 0;
+    for (int f = 0; f < cfg->n_families; ++f) n_smooth += cfg->fam[f].is_smooth ? 1 : 0;
+    p->split_cap = (mode == MODE_PHILOX && n_smooth > 0 && n_smooth < cfg->n_families &&
+                    (size_t)((cap * 3 + 1) / 2) * 2 * lc->team_warps <= scratch && lc->stride < 65536 &&
+                    !at2_debug().hb_no_split) ? cap : 0;
+    p->class_sort_only = !at2_debug().hb_family_sort;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     // float path with warp-private tiles: the repetitions of a tile are halved together when their survivor-id buffers and
     // running state fit where the per-repetition path keeps its two id lists (2 * npad entries);

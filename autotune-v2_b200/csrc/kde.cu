@@ -10,6 +10,8 @@
 // streams a chunk of samples through shared memory (128-bit coalesced loads, broadcast reads), so HBM/L2 traffic is
 // N*4 B per grid tile.  Partial sums per (chunk, grid point) are reduced in a fixed order by a second kernel in
 // double -> deterministic output.
+#include <atomic>
+
 #include "at2_common.cuh"
 
 namespace {
@@ -30,11 +32,30 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
+// Completion counters of the launches in flight: the last CTA of a grid tile to finish does the fixed-order reduction of
+// that tile's partial sums itself (no second launch) and hands the counter back zeroed.  A launch owns one slot
+// (round-robin on the host; launches that overlap in time hold different slots).
+#define KDE_SLOTS 32
+#define KDE_MAX_GTILES 16
+__device__ unsigned int g_kde_done[KDE_SLOTS][KDE_MAX_GTILES];
+
+struct KdeOut {
+    float* dens;             // normalised density [G] (single-GPU form), or nullptr
+    double norm;
+    // sharded form: the UNNORMALISED float64 sums of this call's samples go to element `slot_off + j` of every target -
+    // the ranks' symmetric buffers (peer stores) or one NVSwitch multicast address (multimem.st)
+    double* target[AT2_MAX_PEERS];
+    int n_targets, is_multicast;
+    long long slot_off;
+};
+
 template <int KERNEL>
 __global__ void __launch_bounds__(KDE_BLOCK) kde_partial_kernel(const float* __restrict__ x, long long n, double start,
                                                                 double step, int G, float inv_h, float centre, int n_chunks,
-                                                                long long chunk_len, float* __restrict__ partial) {
+                                                                long long chunk_len, float* __restrict__ partial,
+                                                                int done_slot, const __grid_constant__ KdeOut out) {
     __shared__ __align__(16) float s_x[KDE_STAGE];
+    __shared__ unsigned int s_ticket;
     const int chunk = blockIdx.x, gtile = blockIdx.y;
     float gs[KDE_GPT], acc[KDE_GPT];
 #pragma unroll
@@ -48,22 +69,23 @@ __global__ void __launch_bounds__(KDE_BLOCK) kde_partial_kernel(const float* __r
     const long long hi = min(n, lo + chunk_len);
     for (long long base = lo; base < hi; base += KDE_STAGE) {
         const int cnt = (int)min((long long)KDE_STAGE, hi - base);
+        const int cnt8 = (cnt + 7) & ~7;               // the pair loop below runs in blocks of eight samples
         __syncthreads();
-        // 128-bit loads when the stage is aligned and full, scalar tail otherwise; pad with +inf-like far values
-        if ((base & 3) == 0 && cnt == KDE_STAGE) {
-            const float4* src = reinterpret_cast<const float4*>(x + base);
-            for (int i = threadIdx.x; i < KDE_STAGE / 4; i += KDE_BLOCK) {
-                float4 v = __ldg(src + i);
-                v.x = (v.x - centre) * inv_h, v.y = (v.y - centre) * inv_h, v.z = (v.z - centre) * inv_h, v.w = (v.w - centre) * inv_h;
-                reinterpret_cast<float4*>(s_x)[i] = v;
-            }
-        } else {
-            for (int i = threadIdx.x; i < KDE_STAGE; i += KDE_BLOCK)
-                s_x[i] = i < cnt ? (__ldg(x + base + i) - centre) * inv_h : 3.0e38f;   // far away: contributes exactly 0
+        // 128-bit loads when the stage's first sample is 16-byte aligned (the address, not just the index: `x` may be a
+        // view at any element offset); scalar loads otherwise and for the ragged end; pad with far-away values
+        const bool vec = ((reinterpret_cast<uintptr_t>(x + base)) & 15u) == 0;
+        const int nvec = vec ? cnt / 4 : 0;
+        const float4* src = reinterpret_cast<const float4*>(x + base);
+        for (int i = threadIdx.x; i < nvec; i += KDE_BLOCK) {
+            float4 v = __ldg(src + i);
+            v.x = (v.x - centre) * inv_h, v.y = (v.y - centre) * inv_h, v.z = (v.z - centre) * inv_h, v.w = (v.w - centre) * inv_h;
+            reinterpret_cast<float4*>(s_x)[i] = v;
         }
+        for (int i = nvec * 4 + threadIdx.x; i < cnt8; i += KDE_BLOCK)
+            s_x[i] = i < cnt ? (__ldg(x + base + i) - centre) * inv_h : 3.0e38f;   // far away: contributes exactly 0
         __syncthreads();
 #pragma unroll 8
-        for (int i = 0; i < KDE_STAGE; ++i) {
+        for (int i = 0; i < cnt8; ++i) {
             const float xs = s_x[i];
 #pragma unroll
             for (int k = 0; k < KDE_GPT; ++k) {
@@ -80,25 +102,114 @@ __global__ void __launch_bounds__(KDE_BLOCK) kde_partial_kernel(const float* __r
         const int j = gtile * KDE_TILE_G + k * KDE_BLOCK + threadIdx.x;
         if (j < G) partial[(size_t)chunk * G + j] = acc[k];
     }
+    if (done_slot < 0) return;                 // more grid tiles than counters: kde_finish_kernel reduces
+    // last CTA of this grid tile: reduce the tile's partial sums over the chunks, in chunk order, in double -> the same
+    // bits whatever the CTA schedule was
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&g_kde_done[done_slot][gtile], 1u);
+    __syncthreads();
+    if (s_ticket != (unsigned)n_chunks - 1u) return;
+    __threadfence();
+    double s[KDE_GPT];
+#pragma unroll
+    for (int k = 0; k < KDE_GPT; ++k) s[k] = 0.0;
+    const int j0 = gtile * KDE_TILE_G + threadIdx.x;
+#pragma unroll 4
+    for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+        for (int k = 0; k < KDE_GPT; ++k) {
+            const int j = j0 + k * KDE_BLOCK;
+            if (j < G) s[k] += (double)__ldcg(partial + (size_t)c * G + j);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KDE_GPT; ++k) {
+        const int j = j0 + k * KDE_BLOCK;
+        if (j >= G) continue;
+        if (out.dens != nullptr) out.dens[j] = (float)(s[k] * out.norm);
+        if (out.is_multicast)
+            multimem_st_f64(out.target[0] + out.slot_off + j, s[k]);
+        else
+            for (int r = 0; r < out.n_targets; ++r) out.target[r][out.slot_off + j] = s[k];
+    }
+    if (threadIdx.x == 0) g_kde_done[done_slot][gtile] = 0u;
 }
 
-__global__ void kde_finish_kernel(const float* __restrict__ partial, int n_chunks, int G, double norm,
-                                  float* __restrict__ dens) {
+__global__ void kde_finish_kernel(const float* __restrict__ partial, int n_chunks, int G, const __grid_constant__ KdeOut out) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= G) return;
     double s = 0.0;
     for (int c = 0; c < n_chunks; ++c) s += (double)partial[(size_t)c * G + j];
+    if (out.dens != nullptr) out.dens[j] = (float)(s * out.norm);
+    if (out.is_multicast)
+        multimem_st_f64(out.target[0] + out.slot_off + j, s);
+    else
+        for (int r = 0; r < out.n_targets; ++r) out.target[r][out.slot_off + j] = s;
+}
+
+// density = norm * (sum of the ranks' unnormalised sums, in rank order) - the same bits on every rank
+__global__ void kde_combine_kernel(const double* __restrict__ parts, int n_parts, int G, double norm, float* __restrict__ dens) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= G) return;
+    double s = 0.0;
+    for (int r = 0; r < n_parts; ++r) s += parts[(size_t)r * G + j];
     dens[j] = (float)(s * norm);
 }
 
 int kde_chunks(long long n, int G) {
-    // enough CTAs to fill 148 SMs a few times over, but at least one full stage per chunk
+    // CTAs: a multiple of the SM count (two per SM per grid tile, more for long inputs: <= 1024 samples per chunk-ish),
+    // never more chunks than blocks of 64 samples
     const int gtiles = (G + KDE_TILE_G - 1) / KDE_TILE_G;
-    long long want = (148LL * 4 + gtiles - 1) / gtiles;
-    long long max_chunks = (n + KDE_STAGE - 1) / KDE_STAGE;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long per_sm = (n + (long long)sms * 1024 - 1) / ((long long)sms * 1024);
+    if (gtiles == 1 && per_sm < 2) per_sm = 2;
+    long long want = (long long)sms * per_sm;
+    const long long max_chunks = (n + 63) / 64;
     if (want > max_chunks) want = max_chunks;
     if (want < 1) want = 1;
     return (int)want;
+}
+
+double kde_norm(int kernel, long long n_total, double bandwidth) {
+    return (kernel == AT2_KDE_EPANECHNIKOV ? 0.75 : 0.3989422804014327) / ((double)n_total * bandwidth);
+}
+
+int kde_launch(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
+               const KdeOut& out, float* d_workspace, int64_t workspace_floats, const char* who, cudaStream_t st) {
+    AT2_REQUIRE(d_x && d_workspace, "%s: NULL pointer", who);
+    AT2_REQUIRE(n > 0 && G >= 2, "%s: need n > 0 samples and G >= 2 grid points (got %lld, %d)", who, (long long)n, G);
+    AT2_REQUIRE(bandwidth > 0, "%s: bandwidth must be positive", who);
+    AT2_REQUIRE(kernel == AT2_KDE_EPANECHNIKOV || kernel == AT2_KDE_GAUSSIAN, "%s: unknown kernel %d", who, kernel);
+    const int n_chunks = kde_chunks(n, G);
+    AT2_REQUIRE(workspace_floats >= (int64_t)n_chunks * G, "%s: workspace too small (%lld < %lld floats)", who,
+                (long long)workspace_floats, (long long)n_chunks * G);
+    // chunk length: a multiple of four samples, so that every chunk starts 16-byte aligned relative to d_x
+    long long chunk_len = (n + n_chunks - 1) / n_chunks;
+    chunk_len = (chunk_len + 3) / 4 * 4;
+    const int used_chunks = (int)((n + chunk_len - 1) / chunk_len);
+    const double step = (end - start) / (double)(G - 1);
+    const int gtiles = (G + KDE_TILE_G - 1) / KDE_TILE_G;
+    const dim3 grid(used_chunks, gtiles);
+    const float inv_h = (float)(1.0 / bandwidth);
+    const float centre = (float)(0.5 * (start + end));
+    static std::atomic<unsigned> seq{0};
+    const int slot = gtiles <= KDE_MAX_GTILES ? (int)(seq.fetch_add(1) % KDE_SLOTS) : -1;
+    if (kernel == AT2_KDE_EPANECHNIKOV)
+        kde_partial_kernel<0><<<grid, KDE_BLOCK, 0, st>>>(d_x, n, start, step, G, inv_h, centre, used_chunks, chunk_len,
+                                                          d_workspace, slot, out);
+    else
+        kde_partial_kernel<1><<<grid, KDE_BLOCK, 0, st>>>(d_x, n, start, step, G, inv_h, centre, used_chunks, chunk_len,
+                                                          d_workspace, slot, out);
+    AT2_CUDA_CHECK(cudaGetLastError());
+    at2_count_launch(1);
+    if (slot < 0) {
+        kde_finish_kernel<<<(G + 127) / 128, 128, 0, st>>>(d_workspace, used_chunks, G, out);
+        AT2_CUDA_CHECK(cudaGetLastError());
+        at2_count_launch(1);
+    }
+    return AT2_OK;
 }
 
 }  // namespace
@@ -112,33 +223,40 @@ extern "C" int at2_kde_f32(const float* d_x, int64_t n, double start, double end
                            int32_t kernel, float* d_density, float* d_workspace, int64_t workspace_floats,
                            void* stream) {
     at2_reset_launch_count();
-    AT2_REQUIRE(d_x && d_density && d_workspace, "at2_kde_f32: NULL pointer");
-    AT2_REQUIRE(n > 0 && G >= 2, "at2_kde_f32: need n > 0 samples and G >= 2 grid points (got %lld, %d)", (long long)n, G);
-    AT2_REQUIRE(bandwidth > 0, "at2_kde_f32: bandwidth must be positive");
-    AT2_REQUIRE(kernel == AT2_KDE_EPANECHNIKOV || kernel == AT2_KDE_GAUSSIAN, "at2_kde_f32: unknown kernel %d", kernel);
-    const int n_chunks = kde_chunks(n, G);
-    AT2_REQUIRE(workspace_floats >= (int64_t)n_chunks * G, "at2_kde_f32: workspace too small (%lld < %lld floats)",
-                (long long)workspace_floats, (long long)n_chunks * G);
-    // chunk length: multiple of the stage so that every stage but the last is full and 16-byte aligned
-    long long chunk_len = (n + n_chunks - 1) / n_chunks;
-    chunk_len = (chunk_len + KDE_STAGE - 1) / KDE_STAGE * KDE_STAGE;
-    const int used_chunks = (int)((n + chunk_len - 1) / chunk_len);
-    const double step = (end - start) / (double)(G - 1);
-    const dim3 grid(used_chunks, (G + KDE_TILE_G - 1) / KDE_TILE_G);
-    cudaStream_t st = (cudaStream_t)stream;
-    const float inv_h = (float)(1.0 / bandwidth);
-    const float centre = (float)(0.5 * (start + end));
-    double norm;
-    if (kernel == AT2_KDE_EPANECHNIKOV) {
-        kde_partial_kernel<0><<<grid, KDE_BLOCK, 0, st>>>(d_x, n, start, step, G, inv_h, centre, used_chunks, chunk_len, d_workspace);
-        norm = 0.75 / ((double)n * bandwidth);
-    } else {
-        kde_partial_kernel<1><<<grid, KDE_BLOCK, 0, st>>>(d_x, n, start, step, G, inv_h, centre, used_chunks, chunk_len, d_workspace);
-        norm = 0.3989422804014327 / ((double)n * bandwidth);
+    AT2_REQUIRE(d_density != nullptr, "at2_kde_f32: NULL pointer");
+    KdeOut out = {};
+    out.dens = d_density;
+    out.norm = kde_norm(kernel, n, bandwidth > 0 ? bandwidth : 1.0);
+    return kde_launch(d_x, n, start, end, G, bandwidth, kernel, out, d_workspace, workspace_floats, "at2_kde_f32",
+                      (cudaStream_t)stream);
+}
+
+extern "C" int at2_kde_partial_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth,
+                                   int32_t kernel, double* const* d_targets, int32_t n_targets, int32_t is_multicast,
+                                   int64_t slot_offset, float* d_workspace, int64_t workspace_floats, void* stream) {
+    at2_reset_launch_count();
+    AT2_REQUIRE(d_targets != nullptr && n_targets >= 1 && n_targets <= AT2_MAX_PEERS, "at2_kde_partial_f32: need 1..%d targets",
+                AT2_MAX_PEERS);
+    AT2_REQUIRE(!is_multicast || n_targets == 1, "at2_kde_partial_f32: a multicast target is a single address");
+    AT2_REQUIRE(slot_offset >= 0, "at2_kde_partial_f32: slot_offset must be >= 0");
+    KdeOut out = {};
+    for (int r = 0; r < n_targets; ++r) {
+        AT2_REQUIRE(d_targets[r] != nullptr, "at2_kde_partial_f32: target %d is NULL", r);
+        out.target[r] = d_targets[r];
     }
+    out.n_targets = n_targets, out.is_multicast = is_multicast, out.slot_off = slot_offset;
+    return kde_launch(d_x, n, start, end, G, bandwidth, kernel, out, d_workspace, workspace_floats, "at2_kde_partial_f32",
+                      (cudaStream_t)stream);
+}
+
+extern "C" int at2_kde_combine_f64(const double* d_parts, int32_t n_parts, int32_t G, int64_t n_total, double bandwidth,
+                                   int32_t kernel, float* d_density, void* stream) {
+    at2_reset_launch_count();
+    AT2_REQUIRE(d_parts && d_density && n_parts >= 1 && G >= 2 && n_total > 0 && bandwidth > 0, "at2_kde_combine_f64: bad argument");
+    AT2_REQUIRE(kernel == AT2_KDE_EPANECHNIKOV || kernel == AT2_KDE_GAUSSIAN, "at2_kde_combine_f64: unknown kernel %d", kernel);
+    kde_combine_kernel<<<(G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_parts, n_parts, G, kde_norm(kernel, n_total, bandwidth),
+                                                                           d_density);
     AT2_CUDA_CHECK(cudaGetLastError());
-    kde_finish_kernel<<<(G + 127) / 128, 128, 0, st>>>(d_workspace, used_chunks, G, norm, d_density);
-    AT2_CUDA_CHECK(cudaGetLastError());
-    at2_count_launch(2);
+    at2_count_launch(1);
     return AT2_OK;
 }

@@ -184,7 +184,7 @@ __device__ __noinline__ int arm_family(const ArmSpace& sp, unsigned long long gi
 
 // Shared-memory tables of one CTA as the trajectory loop sees them.
 struct SimTables {
-    uint32_t rec_addr;     // shared-space address of rec[0][0]  (GTAB: byte offset of rec in the global table)
+    uint32_t rec_addr;     // shared-space address of rec[0]  (GTAB: byte offset of rec in the global table)
     uint32_t sg_addr;      // shared-space address of sg[0][0]   (GTAB: byte offset of sg)
     const int* ckpos;      // checkpoint positions (ckpt_time - 1), INT_MAX-terminated, in shared memory
     int R, sg_stride;
@@ -263,8 +263,8 @@ __device__ __forceinline__ float step_folded(float f, float g, float fn, float u
 // checkpoint losses to ck[c * stride] as their positions are produced and the smooth arms' Savitzky-Golay read-outs at
 // the end.  All 32 lanes must call it; lanes with active == false do nothing.
 //
-// A lane's epoch is the shared-memory address of its (family, step) record: an accepted attempt advances it by one
-// record, a rejected one leaves it, a finished (or padding) lane sits on the sentinel record whose NaN slope fails every
+// A lane's epoch is the shared-memory address of its (family, step) row: an accepted attempt advances it by one
+// row, a rejected one leaves it, a finished (or padding) lane sits on the sentinel record whose NaN slope fails every
 // acceptance test - so the attempt is branch-free and needs no bounds check.  Checkpoints are flagged in the records
 // themselves (sign bit of w, set by at2_hb_tables_build for the plan's checkpoint positions): an accepted attempt at a
 // flagged step stores the new loss through the lane's row pointer and moves that pointer one row down - two predicated
@@ -287,6 +287,10 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     uint32_t rec_base = tb.rec_addr + (uint32_t)pw_off * (AT2_REC * 4u);
     static_assert(!PARTIAL || CK == 1, "a partial run produces one checkpoint");
     uint32_t sg_base = tb.sg_addr + (PARTIAL ? (uint32_t)only_c * 4u : 0u);   // PARTIAL: column only_c of sg
+    // the Savitzky-Golay row of the step a lane stands on: sg rows have the record stride (x2 beyond 12 checkpoints), so it
+    // sits at a fixed distance from the lane's record address
+    const uint32_t sg_mul = (uint32_t)tb.sg_stride / AT2_REC;
+    const uint32_t sg_delta = sg_base - rec_base * sg_mul;
     // a partial run (stop_t < R) of a finished lane must not walk on: park inactive lanes on the sentinel record
     const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     uint32_t addr = rec_base + (uint32_t)(active ? 1 : R) * (AT2_REC * 4u);   // record of the step to produce next
@@ -333,10 +337,10 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         }
         if constexpr (HAS_SMOOTH && PARTIAL) {
             const float fs = (ok && smooth) ? ff : 0.0f;
-            acc[0] = fmaf(tab32<GTAB>(gbase, sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4)), fs, acc[0]);
+            acc[0] = fmaf(tab32<GTAB>(gbase, addr * sg_mul + sg_delta), fs, acc[0]);
         } else if constexpr (HAS_SMOOTH) {
             const float fs = (ok && smooth) ? ff : 0.0f;
-            const uint32_t a = sg_base + ((addr - rec_base) >> 5) * (uint32_t)(tb.sg_stride * 4);
+            const uint32_t a = addr * sg_mul + sg_delta;
 #pragma unroll
             for (int c4 = 0; c4 < CK; c4 += 4) {
                 const float4 w = tab128<GTAB>(gbase, a + c4 * 4u);
@@ -419,7 +423,7 @@ __device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool 
     const uint32_t end_addr = rec_base + (uint32_t)stop_t * (AT2_REC * 4u);
     uint32_t addr = active ? rec_base + AT2_REC * 4u : end_addr;         // record of the step to produce next
     const uint32_t sg_col = tb.sg_addr + (uint32_t)c * 4u;
-    const uint32_t sg_row = (uint32_t)(tb.sg_stride * 4);
+    const uint32_t sg_mul = (uint32_t)tb.sg_stride / AT2_REC;
     float A = 1.0f, Cc = 0.0f, accA = 0.0f, accC = 0.0f;
     if constexpr (HAS_SMOOTH) accA = smooth ? lds32(sg_col) : 0.0f;      // sg[0][c] * (A_0 = 1)
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
@@ -438,7 +442,7 @@ __device__ __forceinline__ float philox_affine_offset(const SimTables& tb, bool 
         const float Cn = dn ? fmaf(-k, Cc, Cc) : q * fmaf(upc, fast_rcp(g1), Cc);
         A = ok ? An : A, Cc = ok ? Cn : Cc;
         if constexpr (HAS_SMOOTH) {
-            const float w = (ok && smooth) ? lds32(sg_col + ((addr - rec_base) >> 5) * sg_row) : 0.0f;
+            const float w = (ok && smooth) ? lds32(sg_col + (addr - rec_base) * sg_mul) : 0.0f;
             accA = fmaf(w, A, accA), accC = fmaf(w, Cc, accC);
         }
         addr += ok ? (AT2_REC * 4u) : 0u;

@@ -656,7 +656,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
         p.fam[f].s0 = (float)cfg->fam[f].start_shift;
         p.fam[f].s1 = (float)cfg->fam[f].end_shift;
         p.fam[f].smooth = cfg->fam[f].is_smooth;
-        p.fam[f].pw_off = f * (plan->R + 1);
+        p.fam[f].pw_off = f * at2_rec_rows(plan->R);
     }
     p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
     p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);

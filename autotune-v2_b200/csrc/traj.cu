@@ -77,7 +77,7 @@ extern "C" int at2_sim_trajectories_f32(const at2_plan* plan, const at2_sim_conf
         fam[f].s0 = (float)cfg->fam[f].start_shift;
         fam[f].s1 = (float)cfg->fam[f].end_shift;
         fam[f].smooth = cfg->fam[f].is_smooth;
-        fam[f].pw_off = f * (plan->R + 1);
+        fam[f].pw_off = f * at2_rec_rows(plan->R);
     }
     const int has_smooth = at2_cfg_has_smooth(cfg);
     At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(plan->n_ckpts)};

@@ -104,7 +104,7 @@ const char* at2_last_error(void);
 
 /* Debug options (tests and measurements only; all zero by default = the library chooses): tile / CTA shapes and code-path
  * switches that never change a result.  Process-wide; the library never reads the environment.  Names: hb_reps_per_tile,
- * hb_team_warps, hb_warps_per_cta, hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles,
+ * hb_team_warps, hb_warps_per_cta, hb_no_split, hb_family_sort, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles,
  * force_gtab, lazy_reps_per_tile, tpe_warps_per_cta, kf_warps_per_cta, kf_reps_per_tile; "reset" clears all. */
 int at2_debug_option(const char* name, int32_t value);
 
@@ -303,6 +303,18 @@ int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain, const dou
 int64_t at2_kde_workspace_floats(int64_t n, int32_t G);
 int at2_kde_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
                 float* d_density, float* d_workspace, int64_t workspace_floats, void* stream);
+
+/* The same estimate sharded over the ranks that hold the samples (N GPUs: every rank evaluates only its own slice of the
+ * OFE vector).  at2_kde_partial_f32 writes the UNNORMALISED float64 kernel sums of this call's n samples on the G grid
+ * points to elements slot_offset .. slot_offset + G - 1 of every target - the ranks' symmetric buffers mapped into this
+ * process (peer stores), or one NVSwitch multicast address (is_multicast = 1: multimem.st) - rank r uses
+ * slot_offset = r * G.  After a barrier across the ranks, at2_kde_combine_f64 adds the n_parts slots IN SLOT ORDER and
+ * normalises by n_total samples: every rank obtains the same bits. */
+int at2_kde_partial_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
+                        double* const* d_targets, int32_t n_targets, int32_t is_multicast, int64_t slot_offset,
+                        float* d_workspace, int64_t workspace_floats, void* stream);
+int at2_kde_combine_f64(const double* d_parts, int32_t n_parts, int32_t G, int64_t n_total, double bandwidth, int32_t kernel,
+                        float* d_density, void* stream);
 
 /* Full-trajectory output (inspection / per-evaluator API, core/simulation_evaluator.py:84-116): raw trajectory
  * d_raw[a][0..R-1] of n_arms arms given their first value d_f1[a], target d_fn[a], family index and Philox stream id.

@@ -11,7 +11,10 @@ from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
 FAM6 = [(1.5, 10, 15, False, 0, 200), (0.5, 7, 10, False, 0, 200), (0.2, 4, 7, True, 0, 200),
         (1.5, 10, 15, False, 200, 400), (0.5, 7, 10, False, 200, 400), (0.2, 4, 7, True, 200, 400)]
 cases = [('branin-flat', HyperbandSimSpec('branin', [(0, 1, 0, False, 0, 0)], 81, 3, 0), 100000),
-         ('rastrigin-6fam', HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10), 100000)]
+         ('rastrigin-6fam', HyperbandSimSpec('rastrigin', FAM6, 81, 3, 10), 100000),
+         ('egg-3fam-R243', HyperbandSimSpec('egg', [(1.5, 10, 15, False, 0, 1000), (0.5, 7, 10, False, 0, 1000),
+                                                    (0.2, 4, 7, True, 0, 1000)], 243, 3, 10), 20000),
+         ('wave-6fam-R27', HyperbandSimSpec('wave', FAM6, 27, 3, 10), 200000)]
 for _ in range(60):
     run_hyperband_repetitions(cases[0][1], 100000, seed=0, early_stop=False)
 ref = {}
@@ -37,3 +40,6 @@ for setting in (sys.argv[1:] or ['']):
         except Exception as e:  # noqa: BLE001
             line += f' | {name} ERROR {str(e)[:60]}'
     print(line, flush=True)
+import subprocess
+print(subprocess.run(['nvidia-smi', '--query-gpu=clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_throttle_reasons.active',
+                      '--format=csv,noheader'], capture_output=True, text=True).stdout.strip(), flush=True)

@@ -112,7 +112,8 @@ def test_tables_f64_bit_exact_with_python_floats(R):
     buf = np.zeros(nbytes // 8, np.float64)
     nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 1, buf.ctypes.data))
     F = len(FAM6)
-    rec = buf[:8 * F * (R + 1)].reshape(F, R + 1, 8)
+    rows = (R + 1) | 1                                                # csrc/at2_common.cuh at2_rec_rows
+    rec = buf[:12 * F * rows].reshape(F, rows, 12)                    # 12-real records (csrc/at2_common.cuh AT2_REC)
     for f, fam in enumerate(FAM6):
         for t in range(1, R):
             assert rec[f, t, 4] == (t / (R - 1)) ** fam[1]            # python float pow, simulation_evaluator.py:105
@@ -123,8 +124,8 @@ def test_tables_f64_bit_exact_with_python_floats(R):
         assert np.isnan(rec[f, R, 1])                                 # sentinel row: acceptance can never pass
     # Savitzky-Golay rows at the checkpoints agree with scipy's operator to rounding
     W = gp.savgol_operator(R)
-    sgw = 8 if plan.n_ckpts > 4 else 4
-    sg = buf[8 * F * (R + 1):8 * F * (R + 1) + sgw * (R + 1)].reshape(R + 1, sgw)
+    sgw = 12 if plan.n_ckpts <= 12 else 24
+    sg = buf[12 * F * rows:12 * F * rows + sgw * (R + 1)].reshape(R + 1, sgw)
     for c in range(plan.n_ckpts):
         row = plan.ckpt_time[c] - 1
         assert np.max(np.abs(sg[:R, c] - W[row])) < 1e-12
@@ -133,17 +134,20 @@ def test_tables_f64_bit_exact_with_python_floats(R):
 
 @pytest.mark.parametrize('R', [27, 81])
 def test_tables_f32_folded_records(R):
-    """Float tables (Philox paths): {d, c, d log2e, d log2e + 32, +-w, K1w, K0, P11}; the sign of w flags the plan's
-    checkpoint positions; pw[f][t] = {K1, K0, P11, 0} follows the Savitzky-Golay rows (include/at2.h)."""
+    """Float tables (Philox paths): 12-real records {d, c, d log2e, d log2e + 32 | +-w, K1w, K0, P11 | spare}, row =
+    f * rows + t with rows = (R + 1) | 1; the sign of w flags the plan's checkpoint positions; the folded-step table of the
+    pre-drawn path {K1, K0, P11, 0} follows the Savitzky-Golay rows (csrc/at2_common.cuh)."""
     plan = nat.bracket_plan(R, 3)
     cfg = _cfg(FAM6)
     nbytes = nat.lib.at2_hb_tables_bytes(C.byref(plan), C.byref(cfg), 0)
     buf = np.zeros(nbytes // 4, np.float32)
     nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 0, buf.ctypes.data))
     F = len(FAM6)
-    sgw = 8 if plan.n_ckpts > 4 else 4
-    rec = buf[:8 * F * (R + 1)].reshape(F, R + 1, 8)
-    pw = buf[8 * F * (R + 1) + sgw * (R + 1):].reshape(F, R + 1, 4)
+    sgw = 12 if plan.n_ckpts <= 12 else 24
+    rows = (R + 1) | 1
+    rec = buf[:12 * F * rows].reshape(F, rows, 12)
+    assert np.all(rec[:, :, 8:] == 0)
+    pw = buf[12 * F * rows + sgw * (R + 1):].reshape(F, rows, 4)
     ckpos = {plan.ckpt_time[c] - 1 for c in range(plan.n_ckpts)}
     f32 = np.float32
     for f, fam in enumerate(FAM6):
