@@ -244,18 +244,33 @@ class KnownFnSpec:
         self.db = torch.from_numpy(db).to(device)
         self.curves = torch.from_numpy(curves).to(device)
 
-    def lookup(self, queries, times=None):
-        """Nearest recorded arm of each query row (raw values in domain order); with `times` also the loss read-out."""
+    def _domain_bytes_for(self, order):
+        """Domain descriptor with another summation order (the squared error is summed in the attribute order of the
+        PROPOSED arm, known_loss_fn_problem.py:36-48: any order a caller's Arm happens to have)."""
+        if order is None or list(order) == [self.desc.order[k] for k in range(len(self.names))]:
+            return self.domain_bytes
+        if sorted(order) != list(range(len(self.names))):
+            raise ValueError(f'order must be a permutation of range({len(self.names)})')
+        desc = nat.DomainDesc.from_buffer_copy(bytes(self.desc))
+        for k, i in enumerate(order):
+            desc.order[k] = int(i)
+        return ops.struct_tensor(desc)
+
+    def lookup(self, queries, times=None, order=None):
+        """Nearest recorded arm of each query row (raw values in domain order); with `times` also the loss read-out.
+        `order`: summation order of the squared-error terms as indices into the domain's hyperparameters (default: the
+        attribute order of a drawn arm)."""
+        domain_bytes = self._domain_bytes_for(order)
         if torch.is_tensor(queries):
             q = queries.to(self.device, torch.float64).contiguous()
         else:
             q = torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float64)).to(self.device)
         if times is None:
-            idx, dist, _ = torch.ops.at2.nn_lookup(self.domain_bytes, self.db, q, self.db.new_empty((0, 0)),
+            idx, dist, _ = torch.ops.at2.nn_lookup(domain_bytes, self.db, q, self.db.new_empty((0, 0)),
                                                    torch.empty(0, device=self.device, dtype=torch.int32))
             return idx, dist
         t = torch.as_tensor(np.asarray(times, np.int32)).to(self.device)
-        return tuple(torch.ops.at2.nn_lookup(self.domain_bytes, self.db, q, self.curves, t))
+        return tuple(torch.ops.at2.nn_lookup(domain_bytes, self.db, q, self.curves, t))
 
 
 def run_knownfn_hyperband(kspec, max_iter, eta, n_reps, seed=0, rep_offset=0, min_or_max='min', predrawn=None,

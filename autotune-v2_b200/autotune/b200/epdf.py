@@ -123,22 +123,33 @@ class FusedGather:
         hdl.barrier(channel=0)          # on the current stream: every rank's stores are in every buffer after it
         return buf
 
-    def run_epdf(self, spec, seed, start, end, bandwidth, grid_points=1000, kernel='epanechnikov', early_stop=True):
+    def run_epdf(self, spec, seed, start, end, bandwidth, grid_points=1000, kernel='epanechnikov', early_stop=True,
+                 sim_events=None):
         """The whole EPDF-OFE step with the KDE sharded as well: this rank's repetitions (OFEs scattered into every rank's
         buffer by the kernel) -> kernel sums of its OWN slice on the grid (float64, scattered into every rank's slot array the
         same way) -> ONE barrier across the ranks -> the ranks' sums added in rank order and normalised.  Every rank ends up
         with the same gathered vector and the same density bits, and evaluates only 1/world of the N x G pair terms.
-        Returns (ofes [n_total], density [grid_points])."""
+        Returns (ofes [n_total], density [grid_points]).  sim_events: an optional pair of CUDA events recorded around the
+        simulation launch alone (measurements)."""
+        stream = torch.cuda.current_stream(self.device)
         if self.ktargets is None or grid_points > self.MAX_GRID:
+            if sim_events is not None:
+                sim_events[0].record(stream)
             ofes = self.run(spec, seed, early_stop)
+            if sim_events is not None:
+                sim_events[1].record(stream)
             return ofes, density(ofes, start, end, bandwidth, grid_points, kernel)
         lo, hi = shard_range(self.n_total, self.rank, self.world)
         turn = self.turn
         buf, hdl, targets = self.bufs[turn], self.handles[turn], self.targets[turn]
         kbuf, ktargets = self.kbufs[turn], self.ktargets[turn]
         self.turn ^= 1
+        if sim_events is not None:
+            sim_events[0].record(stream)
         local = torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo,
                                             lo, int(seed), buf, targets, lo, self.multicast, bool(early_stop))[0]
+        if sim_events is not None:
+            sim_events[1].record(stream)
         # the kernel sums are taken over the launch's own (locally written) OFE output, not over the symmetric buffer
         torch.ops.at2.kde_partial(local, float(start), float(end), int(grid_points), float(bandwidth), KERNEL_IDS[kernel], kbuf,
                                   ktargets, self.multicast, self.rank * int(grid_points))

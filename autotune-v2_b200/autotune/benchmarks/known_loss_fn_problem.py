@@ -30,9 +30,8 @@ class KnownFnEvaluator(SimulationEvaluator):
         names = list(self.proposed_arm.__dict__.keys())
         if set(names) != set(db.names):
             raise KeyError(f'the proposed arm must define exactly the domain hyperparameters {db.names}')
-        if names != [db.names[i] for i in db.desc.order[:len(names)]]:
-            raise NotImplementedError('the device path sums the squared error in the attribute order of a drawn arm')
-        idx, _ = db.lookup([[float(self.proposed_arm[n]) for n in db.names]])
+        # the reference sums the squared-error terms in the attribute order of the proposed arm (:36-48), whatever it is
+        idx, _ = db.lookup([[float(self.proposed_arm[n]) for n in db.names]], order=[db.names.index(n) for n in names])
         nearest = db.arms[int(idx[0])]
         curve = self.known_fs[nearest]
         return OptimisationGoals(fval=curve[time - 1], test_error=-1, validation_error=-1, fvals=curve)

@@ -34,7 +34,7 @@ void at2_reset_launch_count();
 // measurements.  Process-wide, all zero by default (= the library decides); never read from the environment.
 struct At2Debug {
     int hb_reps_per_tile, hb_team_warps, hb_warps_per_cta;   // > 0: override choose_launch (hb_sim.cu)
-    int hb_no_split, hb_family_sort, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
+    int hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
     int force_gtab;                                           // constant tables from global memory on any plan
     int lazy_reps_per_tile;                                   // hb_lazy.cu tile width
     int tpe_warps_per_cta;                                    // tpe_sim.cu

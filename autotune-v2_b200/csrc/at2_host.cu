@@ -28,7 +28,7 @@ extern "C" int at2_debug_option(const char* name, int32_t value) {
     }
     const struct { const char* name; int* field; } table[] = {
         {"hb_reps_per_tile", &g_debug.hb_reps_per_tile}, {"hb_team_warps", &g_debug.hb_team_warps},
-        {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split}, {"hb_family_sort", &g_debug.hb_family_sort},
+        {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split},
         {"hb_equal_tiles", &g_debug.hb_equal_tiles}, {"hb_no_tile_halving", &g_debug.hb_no_tile_halving},
         {"hb_static_schedule", &g_debug.hb_static_schedule}, {"hb_singles", &g_debug.hb_singles},
         {"force_gtab", &g_debug.force_gtab}, {"lazy_reps_per_tile", &g_debug.lazy_reps_per_tile},

@@ -48,7 +48,6 @@ struct Params {
     int dyn_slot;     // >= 0: warp-private tiles are handed out through the device counter pair g_sched[dyn_slot]
     int tile_halving; // float path, warp-private tiles: the tile's repetitions are halved together (halving.cuh tile_halving_f32)
     int km_a, km_b;   // entries of a repetition's two survivor-id buffers in that mode
-    int class_sort_only;   // debug: sort the tile's arms into raw / smoothed only, not by family
     int split_cap;    // > 0: raw and smooth arms of a tile run in separate warp passes; entries of a warp's order list
     int sort_warps;   // warps of a team that ever run halving = min(team_warps, G); only they own sort scratch
     int n_teams;      // teams per CTA
@@ -151,105 +150,68 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
         const int n_items = g_eff * A;
 
         // ---------------- phase 1: trajectories -> checkpoint losses in shared memory ----------------
-        bool split_done = false;
         if constexpr (MODE == MODE_PHILOX) {
-            if (p.split_cap > 0) {
-                // Families mix raw and Savitzky-Golay-smoothed arms.  A smoothed arm accumulates C dot products along its
-                // trajectory and in a mixed warp pass every lane pays for them.  So this warp first lists its items with the raw
-                // arms in front and the smoothed ones at the back (the family of an arm is one Philox block away; a counting
-                // sort over classes - or, debug option hb_family_sort, over families), then runs the passes that hold only raw
-                // arms through the lean loop.  The list and the classes noted by the counting sweep alias the halving sort
-                // scratch.  Every arm is simulated by the same arithmetic either way: outputs do not change by a bit.
-                const int cap = p.split_cap;
-                unsigned short* order = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride)) +
-                                        (size_t)wteam * ((cap * 3 + 1) / 2);
-                unsigned char* famb = reinterpret_cast<unsigned char*>(order + cap);
-                int cnt[AT2_MAX_FAMILIES];
-#pragma unroll
-                for (int f = 0; f < AT2_MAX_FAMILIES; ++f) cnt[f] = 0;
-                int slot = lane;
-                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32, slot += 32) {
+            // Families that mix raw and Savitzky-Golay-smoothed arms: a smoothed arm accumulates C dot products along its
+            // trajectory and in a mixed warp pass every lane pays for them.  So this warp first lists its items with the raw
+            // arms in front and the smoothed ones at the back (the family of an arm is one Philox block away), then runs the
+            // passes that hold only raw arms through the lean loop.  The list aliases the halving sort scratch.  Every arm is
+            // simulated by the same arithmetic either way: outputs do not change by a bit.  Without the list the warp's items
+            // run in their natural order.  Either way there is ONE call site per loop variant (lean / smoothed): the
+            // trajectory loops are most of the kernel's code and instruction fetch is a measured limiter (sim_core.cuh).
+            const bool listed = HAS_SMOOTH && p.split_cap > 0;
+            const int cap = p.split_cap;
+            unsigned short* order = reinterpret_cast<unsigned short*>(reinterpret_cast<K*>(s_ck + (size_t)C * p.stride)) +
+                                    (size_t)wteam * cap;
+            int n_raw = 0, n_sm = 0;
+            if (listed) {
+                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
                     const int i = base + lane;
                     const bool act = i < n_items;
                     const int ii = act ? i : 0;
                     const int rep_l = ii / A, arm = ii - rep_l * A;
                     const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
-                    int fam = act ? arm_family(p.sp, gid, arm) : 255;
-                    // two classes (raw, smoothed), arms in their original order within a class; debug option hb_family_sort
-                    // sorts by family instead (measured slower: 3.27 vs 3.12 ms on the six-family job)
-                    if (p.class_sort_only && act) fam = (HAS_SMOOTH && p.fam[fam].smooth != 0) ? 1 : 0;
-                    famb[slot] = (unsigned char)fam;
-#pragma unroll
-                    for (int f = 0; f < AT2_MAX_FAMILIES; ++f)
-                        if (f < F) cnt[f] += __popc(__ballot_sync(0xffffffffu, fam == f));
-                }
-                // first list position of each family: raw families in index order, then the smoothed ones
-                int off[AT2_MAX_FAMILIES], n_raw = 0, n_all = 0;
-                auto smooth_key = [&](int f) { return p.class_sort_only ? f == 1 : (HAS_SMOOTH && p.fam[f].smooth != 0); };
-#pragma unroll
-                for (int f = 0; f < AT2_MAX_FAMILIES; ++f) {
-                    off[f] = 0;
-                    if (f < F && !smooth_key(f)) off[f] = n_raw, n_raw += cnt[f];
-                }
-                n_all = n_raw;
-#pragma unroll
-                for (int f = 0; f < AT2_MAX_FAMILIES; ++f)
-                    if (f < F && smooth_key(f)) off[f] = n_all, n_all += cnt[f];
-                __syncwarp();
-                slot = lane;
-                const unsigned below = (1u << lane) - 1u;
-                for (int base = wteam * 32; base < n_items; base += p.team_warps * 32, slot += 32) {
-                    const int fam = famb[slot];
-                    int pos = -1;
-#pragma unroll
-                    for (int f = 0; f < AT2_MAX_FAMILIES; ++f) {
-                        if (f < F) {
-                            const unsigned m = __ballot_sync(0xffffffffu, fam == f);
-                            if (fam == f) pos = off[f] + __popc(m & below);
-                            off[f] += __popc(m);
-                        }
-                    }
-                    if (pos >= 0) order[pos] = (unsigned short)(base + lane);
+                    const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
+                    const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
+                    const unsigned below = (1u << lane) - 1u;
+                    if (act) order[sm ? cap - 1 - (n_sm + __popc(m_sm & below)) : n_raw + __popc(m_raw & below)] = (unsigned short)i;
+                    n_raw += __popc(m_raw), n_sm += __popc(m_sm);
                 }
                 __syncwarp();
-                for (int k = 0; k < n_all; k += 32) {
-                    const int q = k + lane;
-                    const bool active = q < n_all;
-                    const int ii = active ? (int)order[q] : 0;
-                    const int rep_l = ii / A, arm = ii - rep_l * A;
-                    const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
-                    const ArmDraw d = draw_arm(p.sp, gid, arm);
-                    const Fam<T> fam = p.fam[d.fam];
-                    const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
-                    const float fn = f - (float)fam.s1, f1 = (f + p.sp.noise * d.z) - (float)fam.s0;
-                    if (!HAS_SMOOTH || k + 32 <= n_raw)
-                        philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.up,
-                                                                    fam.pw_off, gid, p.sp.rk, R, s_ck + ii, p.stride, C);
-                    else
-                        philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
-                                                                          (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
-                                                                          p.stride, C);
-                }
-                split_done = true;
             }
-        }
-        for (int base = wteam * 32; base < n_items && !split_done; base += p.team_warps * 32) {
-            const int i = base + lane;
-            const bool active = i < n_items;
-            const int ii = active ? i : 0;
-            const int rep_l = ii / A, arm = ii - rep_l * A;
-            const long long rep_g = rep0 + rep_l;                   // index into per-call arrays
-            const unsigned long long gid = (unsigned long long)(p.rep_offset + rep_g) * (unsigned long long)A + arm;
-            if constexpr (MODE == MODE_PHILOX) {
+            // this warp's share of the tile: `n_mine` items, the q-th of which is item_of(q)
+            const int my_groups = n_items > wteam * 32 ? (n_items - wteam * 32 + p.team_warps * 32 - 1) / (p.team_warps * 32) : 0;
+            const int n_mine = listed ? n_raw + n_sm : my_groups * 32;
+            for (int k = 0; k < n_mine; k += 32) {
+                const int q = k + lane;
+                int i;
+                if (listed)
+                    i = q < n_mine ? (int)order[q < n_raw ? q : cap - 1 - (q - n_raw)] : n_items;
+                else
+                    i = (k / 32) * p.team_warps * 32 + wteam * 32 + lane;
+                const bool active = i < n_items;
+                const int ii = active ? i : 0;
+                const int rep_l = ii / A, arm = ii - rep_l * A;
+                const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + rep_l) * (unsigned long long)A + arm;
                 const ArmDraw d = draw_arm(p.sp, gid, arm);
                 const Fam<T> fam = p.fam[d.fam];
                 const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
-                philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
-                                                                  (float)fam.up, fam.pw_off, gid, p.sp.rk, R,
-                                                                  s_ck + ii, p.stride, C);
-            } else {
+                if (!HAS_SMOOTH || (listed && k + 32 <= n_raw))
+                    philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.up, fam.pw_off, gid,
+                                                                p.sp.rk, R, s_ck + ii, p.stride, C);
+                else
+                    philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
+                                                                      (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
+                                                                      p.stride, C);
+            }
+        } else {
+            for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {
+                const int i = base + lane;
+                const bool active = i < n_items;
+                const int ii = active ? i : 0;
+                const int rep_l = ii / A, arm = ii - rep_l * A;
+                const long long rep_g = rep0 + rep_l;                   // index into per-call arrays
                 const long long a_g = rep_g * A + arm;
                 const T f1 = active ? p.f1[a_g] : (T)0;
                 const T fn = active ? p.fn[a_g] : (T)0;
@@ -555,9 +517,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     int n_smooth = 0;
     for (int f = 0; f < cfg->n_families; ++f) n_smooth += cfg->fam[f].is_smooth ? 1 : 0;
     p->split_cap = (mode == MODE_PHILOX && n_smooth > 0 && n_smooth < cfg->n_families &&
-                    (size_t)((cap * 3 + 1) / 2) * 2 * lc->team_warps <= scratch && lc->stride < 65536 &&
-                    !at2_debug().hb_no_split) ? cap : 0;
-    p->class_sort_only = !at2_debug().hb_family_sort;
+                    (size_t)cap * 2 * lc->team_warps <= scratch && lc->stride < 65536 && !at2_debug().hb_no_split) ? cap : 0;
     p->n_tiles = (n_reps + lc->G - 1) / lc->G;
     // float path with warp-private tiles: the repetitions of a tile are halved together when their survivor-id buffers and
     // running state fit where the per-repetition path keeps its two id lists (2 * npad entries);

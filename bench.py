@@ -312,18 +312,17 @@ def main():
 
     def make_step(spec_, n_loc, n_tot, fg, early_stop, kde=(KDE_START, KDE_END, KDE_H, KDE_G)):
         def step(seed, sim_events=None):
+            if fg is not None:
+                # this rank's repetitions with the OFEs scattered to every rank by the kernel, the KDE of its own slice,
+                # one barrier, the ranks' kernel sums added in rank order
+                return fg.run_epdf(spec_, seed, kde[0], kde[1], kde[2], kde[3], 'epanechnikov', early_stop, sim_events)
             if sim_events is not None:
                 sim_events[0].record(stream)
-            if fg is not None:
-                full = fg.run(spec_, seed, early_stop)      # this rank's repetitions, every rank's OFEs
-                if sim_events is not None:
-                    sim_events[1].record(stream)            # (includes the barrier across the ranks)
-            else:
-                ofe = run_hyperband_repetitions(spec_, n_loc, seed=seed, rep_offset=rank * n_loc, device=dev,
-                                                early_stop=early_stop)['ofe']
-                if sim_events is not None:
-                    sim_events[1].record(stream)
-                full = gather_slices(ofe, n_tot) if world > 1 else ofe
+            ofe = run_hyperband_repetitions(spec_, n_loc, seed=seed, rep_offset=rank * n_loc, device=dev,
+                                            early_stop=early_stop)['ofe']
+            if sim_events is not None:
+                sim_events[1].record(stream)
+            full = gather_slices(ofe, n_tot) if world > 1 else ofe
             return full, density(full, *kde[:3], kde[3])
         return step
 
@@ -358,7 +357,8 @@ def main():
     value, ms_per_step, sim_ms = time_steps(step_full, n_total, K, warm=max(args.warmup, 3), with_sim_events=True)
     t1 = time.perf_counter()
     sampler.stop()
-    launches = 3 * K   # per step: fused simulation+halving, KDE partial sums, KDE finish
+    # per step: fused simulation + halving, KDE (one launch: the last CTA reduces); N > 1: + the combine of the ranks' sums
+    launches = (3 if fused is not None else 2) * K
     value_default, ms_default, sim_ms_default = time_steps(step_default, n_total, K, warm=3, with_sim_events=True)
 
     # ---- end to end through the public API with host buffers (H2D of the step's constant tables from pinned memory, D2H of

@@ -104,7 +104,7 @@ const char* at2_last_error(void);
 
 /* Debug options (tests and measurements only; all zero by default = the library chooses): tile / CTA shapes and code-path
  * switches that never change a result.  Process-wide; the library never reads the environment.  Names: hb_reps_per_tile,
- * hb_team_warps, hb_warps_per_cta, hb_no_split, hb_family_sort, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles,
+ * hb_team_warps, hb_warps_per_cta, hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles,
  * force_gtab, lazy_reps_per_tile, tpe_warps_per_cta, kf_warps_per_cta, kf_reps_per_tile; "reset" clears all. */
 int at2_debug_option(const char* name, int32_t value);
 

@@ -156,3 +156,26 @@ def test_problem_api_evaluate_matches_reference_semantics():
         assert goals.fvals == list(curves[g['mnist_query_idx'][k]])
     ev = problem.get_evaluator()          # random arm from the domain
     assert 0 < ev.evaluate(27).fval < 1.1
+
+
+def test_evaluator_accepts_any_attribute_order_of_the_proposed_arm():
+    """The reference sums the squared-error terms in the attribute order of the PROPOSED arm (known_loss_fn_problem.py:36-48)
+    and accepts whatever order a caller's Arm has.  A user-built Arm with the hyperparameters in another order must be
+    looked up with that summation order, not refused: same nearest arm as the oracle run with the permuted order."""
+    from autotune.benchmarks.known_loss_fn_problem import KnownFnEvaluator
+    from autotune.core import Arm
+    spec, arms, curves, odom, known_fs, dom, to_opt = _spec('mnist')
+    rng = np.random.default_rng(11)
+    db = spec.db.cpu().numpy()
+    names = list(spec.names)
+    for trial in range(12):
+        row = db[rng.integers(0, len(db))] * (1 + 0.05 * rng.normal(size=db.shape[1]))
+        row = np.clip(row, [np.exp(p['min_val']) if p['scale'] == 'log' else p['min_val'] for p in odom],
+                      [np.exp(p['max_val']) if p['scale'] == 'log' else p['max_val'] for p in odom])
+        perm = list(rng.permutation(len(names)))
+        arm = Arm(**{names[i]: float(row[i]) for i in perm})
+        assert list(arm.__dict__.keys()) == [names[i] for i in perm]
+        ev = KnownFnEvaluator(known_fs, arm, dom, _device_db=spec)
+        got = ev.evaluate(9)
+        want_idx, _ = okf.nearest({names[i]: float(row[i]) for i in perm}, arms, odom)
+        assert got.fvals == list(curves[want_idx]) and got.fval == curves[want_idx][8]
