@@ -25,7 +25,8 @@ class Plan(C.Structure):
                 ('bracket_first_round', C.c_int32 * (MAX_BRACKETS + 1)),
                 ('round_n_eval', C.c_int32 * MAX_ROUNDS), ('round_keep', C.c_int32 * MAX_ROUNDS),
                 ('round_time', C.c_int32 * MAX_ROUNDS), ('round_ckpt', C.c_int32 * MAX_ROUNDS),
-                ('ckpt_time', C.c_int32 * MAX_CKPTS), ('bracket_r0', C.c_double * MAX_BRACKETS)]
+                ('ckpt_time', C.c_int32 * MAX_CKPTS), ('bracket_r0', C.c_double * MAX_BRACKETS),
+                ('round_res', C.c_int32 * MAX_ROUNDS)]
 
 
 class Family(C.Structure):

@@ -101,6 +101,7 @@ extern "C" int at2_bracket_plan(int32_t R, int32_t eta, at2_plan* plan) {
             // just below 1, e.g. R = 729, eta = 3 -> r = 0.9999999999999999): keep that quirk.
             const int time_i = (int)r_i;
             plan->round_time[nr] = time_i >= 1 ? time_i : R + time_i;
+            plan->round_res[nr] = time_i;
             alive = keep < alive ? keep : alive;
             surv += (int)alive;
             ++nr;

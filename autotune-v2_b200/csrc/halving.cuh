@@ -256,7 +256,8 @@ struct HalvingState {
 // ck[c * stride + arm]; writes the requested per-round outputs for repetition `rep_g` and folds the round-bests into
 // `st`.  keys: npad sort keys, ids_a/ids_b: npad arm ids each (warp-private scratch).  When `latest_ck` is given,
 // latest_ck[arm] ends up holding the checkpoint index of the last round the arm was evaluated in (what the hybrids'
-// history transfer keys on, hybrid_hyperband_tpe_with_transfer.py:96-98).  All 32 lanes must call it.
+// history transfer keys on, hybrid_hyperband_tpe_with_transfer.py:96-98), with bit 7 set when that round's int(r_i) was 0
+// and the read wrapped to the last point (the reference records the 0, not R).  All 32 lanes must call it.
 template <typename T>
 __device__ void warp_halving_bracket(const at2_plan& plan, int b, const T* ck, int stride, typename KeyOf<T>::type* keys,
                                      unsigned short* ids_a, unsigned short* ids_b, bool desc, int lane, long long rep_g,
@@ -274,7 +275,8 @@ __device__ void warp_halving_bracket(const at2_plan& plan, int b, const T* ck, i
         T rb_loss;
         int rb_arm;
         if (latest_ck != nullptr)
-            for (int j = lane; j < n_cur; j += 32) latest_ck[first_round ? first + j : (int)ids[j]] = (unsigned char)c;
+            for (int j = lane; j < n_cur; j += 32)
+                latest_ck[first_round ? first + j : (int)ids[j]] = (unsigned char)(c | (plan.round_res[rd] < 1 ? 0x80 : 0));
         if constexpr (sizeof(T) == 4) {
             warp_halving_round_f32(n_cur, keep, first_round, first, ids, ids_next, keys, desc, lane,
                                    [&](int, int id) { return col[id]; }, rb_loss, rb_arm);

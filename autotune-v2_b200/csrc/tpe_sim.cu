@@ -449,8 +449,11 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                 float ix = 0.0f, iy = 0.0f, il = 0.0f;
                 if (step < 0) {                                      // (1) candidate for injection
                     const int a = first + step;
-                    const int lc = w.latest[a];
-                    if (transferable(p.tpe.transfer, p.plan.ckpt_time[lc], r0, R, p.tpe.threshold))
+                    const int lc = w.latest[a] & 0x7f;
+                    // the resource count the reference recorded for the arm: int(r_i), which is 0 (not R) where the read
+                    // wrapped to the last point (R = 729, eta = 3)
+                    const int r_arm = (w.latest[a] & 0x80) ? 0 : p.plan.ckpt_time[lc];
+                    if (transferable(p.tpe.transfer, r_arm, r0, R, p.tpe.threshold))
                         do_insert = true, ix = w.ax[a], iy = w.ay[a], il = sign * w.ck[lc * cap + a];
                 } else {                                             // (2) next arm of the bracket
                     if (step == 0) n_startup += w.n_obs;
@@ -626,6 +629,7 @@ extern "C" int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resou
     plan->bracket_n[0] = n_evals, plan->bracket_first_arm[0] = 0, plan->bracket_first_round[0] = 0;
     plan->bracket_first_round[1] = 1;
     plan->round_n_eval[0] = n_evals, plan->round_keep[0] = 0, plan->round_time[0] = t, plan->round_ckpt[0] = 0;
+    plan->round_res[0] = n_resources;
     plan->ckpt_time[0] = t;
     plan->bracket_r0[0] = (double)n_resources;
     return AT2_OK;

@@ -74,6 +74,9 @@ typedef struct at2_plan {
     int32_t ckpt_time[AT2_MAX_CKPTS];           /* ascending */
     double bracket_r0[AT2_MAX_BRACKETS];        /* r = R*eta**(-s) as the float the reference computes (transfer
                                                    predicates compare against it un-truncated) */
+    int32_t round_res[AT2_MAX_ROUNDS];          /* int(r_i) itself, NOT wrapped (0 where round_time wrapped to R): what
+                                                   the hybrids record per evaluator for their transfer predicates
+                                                   (hybrid_hyperband_tpe_with_transfer.py:96-98,161-209) */
 } at2_plan;
 
 /* One shape family, core/shape_family_scheduler.py:10-17. */
