@@ -107,7 +107,7 @@ def _load():
         'at2_sim_trajectories_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), vp, i64, vp, vp, vp, vp, u64, vp, vp]),
         'at2_single_round_plan': (C.c_int, [i32, i32, i32, C.POINTER(Plan)]),
         'at2_tpe_sim_f32': (C.c_int, [C.POINTER(Plan), C.POINTER(SimConfig), C.POINTER(TpeConfig), vp, i64, i64, u64,
-                                      C.POINTER(HbOutputs), vp, vp, vp]),
+                                      C.POINTER(HbOutputs), vp, vp, vp, vp]),
         'at2_tpe_score_f32': (C.c_int, [vp, vp, i32, i32, C.c_double, C.c_double, C.POINTER(TpeConfig), vp, i32, vp, vp, vp,
                                         vp, vp]),
         'at2_nn_workspace_bytes': (i64, [i64, i32, i32]),
@@ -121,6 +121,8 @@ def _load():
         'at2_kde_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, vp, vp, i64, vp]),
         'at2_kde_partial_f32': (C.c_int, [vp, i64, C.c_double, C.c_double, i32, C.c_double, i32, C.POINTER(C.c_void_p), i32, i32,
                                           i64, vp, i64, vp]),
+        'at2_segmented_topk_f32': (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
+        'at2_segmented_topk_f64': (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
         'at2_kde_combine_f64': (C.c_int, [vp, i32, i32, i64, C.c_double, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():

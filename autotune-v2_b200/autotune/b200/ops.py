@@ -285,8 +285,9 @@ def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.T
 def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, tpe_bytes: torch.Tensor, n_reps: int,
             rep_offset: int, seed: int, details: bool) -> List[torch.Tensor]:
     """Hyperband-TPE hybrids / stand-alone TPE / random search on the simulation problem (at2_tpe_sim_f32).
-    Returns the at2::hb_sim_f32 outputs followed, when `details`, by arm_xy [n_reps, n_arms, 2] and obs_loss [n_reps, n_arms]
-    (the loss the TPE phase observed for an arm; NaN for arms that were not observed)."""
+    Returns the at2::hb_sim_f32 outputs followed, when `details`, by arm_xy [n_reps, n_arms, 2], obs_loss [n_reps, n_arms]
+    (the loss the TPE phase observed for an arm; NaN for arms that were not observed) and n_injected [n_reps, n_brackets]
+    (evaluations of earlier brackets transferred into each bracket's TPE run)."""
     _require_cuda(tables, 'tables')
     plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     tpe = _struct(nat.TpeConfig, tpe_bytes)
@@ -294,12 +295,13 @@ def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Ten
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
         arm_xy = torch.empty(n_reps, plan.n_arms, 2, device=tables.device, dtype=torch.float32) if details else None
         obs = torch.full((n_reps, plan.n_arms), float('nan'), device=tables.device, dtype=torch.float32) if details else None
+        inj = torch.zeros(n_reps, plan.n_brackets, device=tables.device, dtype=torch.int32) if details else None
         if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
             nat.check(nat.lib.at2_tpe_sim_f32(C.byref(plan), C.byref(cfg), C.byref(tpe), tables.data_ptr(), n_reps, rep_offset,
                                               seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs),
                                               arm_xy.data_ptr() if details else None, obs.data_ptr() if details else None,
-                                              _stream_ptr(tables.device)))
-    return tensors + ([arm_xy, obs] if details else [])
+                                              inj.data_ptr() if details else None, _stream_ptr(tables.device)))
+    return tensors + ([arm_xy, obs, inj] if details else [])
 
 
 @torch.library.custom_op('at2::tpe_score', mutates_args=(), device_types='cuda')
@@ -399,3 +401,26 @@ def ks_statistic(a_sorted: torch.Tensor, b_sorted: torch.Tensor) -> torch.Tensor
         nat.check(nat.lib.at2_ks_statistic_f32(a_sorted.data_ptr(), a_sorted.numel(), b_sorted.data_ptr(),
                                                b_sorted.numel(), d.data_ptr(), _stream_ptr(a_sorted.device)))
     return d
+
+
+@torch.library.custom_op('at2::segmented_topk', mutates_args=(), device_types='cuda')
+def segmented_topk(losses: torch.Tensor, seg_offsets: torch.Tensor, keep: torch.Tensor, max_seg_len: int,
+                   descending: bool) -> torch.Tensor:
+    """The successive-halving selection alone (at2_segmented_topk_f32 / _f64): per segment of `losses` (float32 or
+    float64, 1-D; segment s = [seg_offsets[s], seg_offsets[s+1]), int64) the positions of its keep[s] (int32) best losses,
+    best first, in python's stable sorted() order (hyperband_optimiser.py:46-57); -1 past keep.  int32, laid out like `losses`."""
+    _require_cuda(losses, 'losses')
+    for name, t, dt in (('seg_offsets', seg_offsets, torch.int64), ('keep', keep, torch.int32)):
+        _require_cuda(t, name)
+        if t.dtype != dt or t.dim() != 1 or not t.is_contiguous():
+            raise RuntimeError(f'{name} must be a contiguous 1-D {dt} tensor')
+    if losses.dtype not in (torch.float32, torch.float64) or losses.dim() != 1 or not losses.is_contiguous():
+        raise RuntimeError('losses must be a contiguous 1-D float32 or float64 tensor')
+    if seg_offsets.numel() != keep.numel() + 1:
+        raise RuntimeError('seg_offsets must have one more entry than keep')
+    fn = nat.lib.at2_segmented_topk_f32 if losses.dtype == torch.float32 else nat.lib.at2_segmented_topk_f64
+    with torch.cuda.device(losses.device):
+        idx = torch.full((losses.numel(),), -1, device=losses.device, dtype=torch.int32)
+        nat.check(fn(losses.data_ptr(), seg_offsets.data_ptr(), keep.data_ptr(), keep.numel(), int(max_seg_len),
+                     int(bool(descending)), idx.data_ptr(), _stream_ptr(losses.device)))
+    return idx

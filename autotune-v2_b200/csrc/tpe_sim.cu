@@ -51,6 +51,7 @@ struct TpeParams {
     float* ckpt_loss;
     float* arm_xy;      // optional [n_reps][n_arms][2]
     float* obs_loss;    // optional [n_reps][n_arms]: the loss TPE observed (only written for observed arms)
+    int* n_injected;    // optional [n_reps][n_brackets]: observations transferred into the bracket's TPE run
 };
 
 // warp-private working set
@@ -427,6 +428,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
             const bool inject = use_tpe && b > 0 && p.tpe.transfer != AT2_TRANSFER_NONE;
             const int n_prev = inject ? first : 0;
             int n_startup = p.tpe.n_startup;                          // + injected, tpe_optimiser.py:52
+            int n_inj = 0;
 #pragma unroll 1
             for (int base = 0; base < n_b; base += 32) {
                 const bool act = base + lane < n_b;
@@ -454,7 +456,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                     // wrapped to the last point (R = 729, eta = 3)
                     const int r_arm = (w.latest[a] & 0x80) ? 0 : p.plan.ckpt_time[lc];
                     if (transferable(p.tpe.transfer, r_arm, r0, R, p.tpe.threshold))
-                        do_insert = true, ix = w.ax[a], iy = w.ay[a], il = sign * w.ck[lc * cap + a];
+                        do_insert = true, ++n_inj, ix = w.ax[a], iy = w.ay[a], il = sign * w.ck[lc * cap + a];
                 } else {                                             // (2) next arm of the bracket
                     if (step == 0) n_startup += w.n_obs;
                     const int arm = first + step;
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(cons
                 if (do_insert) tpe_insert(w, ix, iy, il, lane);
             }
             __syncwarp();
+            if (lane == 0 && p.n_injected != nullptr) p.n_injected[rep * p.plan.n_brackets + b] = n_inj;
 #pragma unroll 1
             for (int base = 0; base < n_b; base += 32) {              // (3) full trajectories
                 const bool act = base + lane < n_b;
@@ -637,7 +640,8 @@ extern "C" int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resou
 
 extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe,
                                const void* d_tables, int64_t n_reps, int64_t rep_offset, uint64_t seed,
-                               const at2_hb_outputs* out, float* d_arm_xy, float* d_obs_loss, void* stream) {
+                               const at2_hb_outputs* out, float* d_arm_xy, float* d_obs_loss, int32_t* d_n_injected,
+                               void* stream) {
     at2_reset_launch_count();
     AT2_REQUIRE(plan && cfg && d_tables && out, "at2_tpe_sim_f32: NULL plan/config/tables/outputs");
     AT2_REQUIRE(n_reps > 0 && rep_offset >= 0, "at2_tpe_sim_f32: n_reps must be positive and rep_offset >= 0");
@@ -673,6 +677,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     p.ofe = (float*)out->d_ofe, p.ofe_arm = out->d_ofe_arm, p.best_xy = (float*)out->d_best_xy;
     p.round_best = (float*)out->d_round_best, p.round_best_arm = out->d_round_best_arm;
     p.survivors = out->d_survivors, p.ckpt_loss = (float*)out->d_ckpt_loss, p.arm_xy = d_arm_xy, p.obs_loss = d_obs_loss;
+    p.n_injected = d_n_injected;
     p.npad = halving_npad(plan);
     p.cap = (plan->n_arms + 31) & ~31;
     const int C = plan->n_ckpts;

@@ -220,6 +220,18 @@ typedef struct at2_tpe_config {
     double prior_weight;   /* 1.0 */
 } at2_tpe_config;
 
+/* The successive-halving selection alone (parity of survivor indices): for each of n_segments segments
+ * d_losses[d_seg_offsets[s] .. d_seg_offsets[s+1]) write the positions (0-based within the segment) of its d_keep[s] best
+ * losses, best first, to d_idx_out at the segment's own offsets; entries past keep are set to -1.  Order and tie-breaks are
+ * python's stable sorted(evaluators, key=loss, reverse=descending)[:keep] (optimisers/sequential/hyperband_optimiser.py:
+ * 46-57); keep is clamped to [0, segment length].  max_seg_len: an upper bound on the segment lengths (<= 65536; sizes the
+ * per-warp sort scratch) - a longer segment is an error.  Runs the same warp primitives as the fused kernels (ranking by
+ * counting, register / shared-memory bitonic networks).  Synchronises `stream` before returning. */
+int at2_segmented_topk_f32(const float* d_losses, const int64_t* d_seg_offsets, const int32_t* d_keep, int64_t n_segments,
+                           int32_t max_seg_len, int32_t descending, int32_t* d_idx_out, void* stream);
+int at2_segmented_topk_f64(const double* d_losses, const int64_t* d_seg_offsets, const int32_t* d_keep, int64_t n_segments,
+                           int32_t max_seg_len, int32_t descending, int32_t* d_idx_out, void* stream);
+
 /* Plan of a stand-alone optimiser that evaluates n_evals arms once at n_resources: TpeOptimiser
  * (tpe_optimiser.py:40-60) with tpe.enabled = 1, RandomOptimiser (random_optimiser.py:39-58) with enabled = 0. */
 int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resources, at2_plan* plan);
@@ -229,10 +241,12 @@ int at2_single_round_plan(int32_t R, int32_t n_evals, int32_t n_resources, at2_p
  * sim(tpe), sim(random).  Same tables/outputs as at2_hb_sim_f32; with tpe->enabled == 0 and a Hyperband plan the results
  * are bit-identical to at2_hb_sim_f32.  d_arm_xy (optional): float[n_reps][n_arms][2] hyperparameters of every arm.
  * d_obs_loss (optional): float[n_reps][n_arms], the loss the TPE phase observed for an arm (its read-out at the bracket's
- * first resource level, tpe_optimiser.py:62-89) - written only for arms that were observed, so pre-fill with NaN. */
+ * first resource level, tpe_optimiser.py:62-89) - written only for arms that were observed, so pre-fill with NaN.
+ * d_n_injected (optional): int32[n_reps][n_brackets], how many evaluations of earlier brackets were transferred into the
+ * bracket's TPE run (_get_trials, hybrid_hyperband_tpe_with_transfer.py:116-158). */
 int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, const at2_tpe_config* tpe, const void* d_tables,
                     int64_t n_reps, int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, float* d_arm_xy,
-                    float* d_obs_loss, void* stream);
+                    float* d_obs_loss, int32_t* d_n_injected, void* stream);
 
 /* Parzen-estimator scoring alone (parity of the estimator arithmetic): for each of n_problems independent 1-D
  * hp.uniform(low, high) problems with n_obs observations (d_obs, d_loss: float[n_problems][n_obs], trial order), build the

@@ -21,5 +21,15 @@ smsp__sass_thread_inst_executed_op_fadd_pred_on.sum,smsp__sass_thread_inst_execu
 python scripts/tpe_timing.py 8000 > $out/${tag}_plain_tpe.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:tpe_sim_kernel -s 9 -c 1 -f -o $out/${tag}_prof_tpe \
     python scripts/tpe_timing.py 8000 > $out/${tag}_ncu_tpe.log 2>&1
+# early-stopping kernel (the product default), closest-known-function kernels, and the three simulation variants
+python scripts/lazy_timing.py 100000 fam6 > $out/${tag}_plain_lazy.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:hb_lazy_kernel -s 60 -c 1 -f -o $out/${tag}_prof_lazy \
+    python scripts/lazy_timing.py 100000 fam6 > $out/${tag}_ncu_lazy.log 2>&1
+python scripts/knownfn_timing.py 10000 > $out/${tag}_plain_knownfn.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'hb_knownfn_kernel|nn_lookup_kernel' -s 4 -c 3 -f -o $out/${tag}_prof_knownfn \
+    python scripts/knownfn_timing.py 10000 > $out/${tag}_ncu_knownfn.log 2>&1
+python scripts/quick_timing.py > $out/${tag}_plain_quick.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:hb_sim_kernel -s 35 -c 1 -f -o $out/${tag}_prof_hb_flat \
+    python scripts/quick_timing.py > $out/${tag}_ncu_quick.log 2>&1
 tail -2 $out/${tag}_plain_bench.log | cut -c1-400
 ls -la $out | grep ${tag}_

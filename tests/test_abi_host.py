@@ -58,6 +58,10 @@ def test_bracket_plan_matches_oracle(R, eta):
     assert list(plan.ckpt_time[:plan.n_ckpts]) == sorted({(t - 1) % R + 1 for t in ohb.plan_checkpoints(ohb.bracket_plan(R, eta))})
     for r in range(plan.n_rounds):
         assert plan.ckpt_time[plan.round_ckpt[r]] == plan.round_time[r]
+    # the resource count the hybrids record per evaluator is int(r_i) itself - 0, not R, where the read wraps (R = 729)
+    assert list(plan.round_res[:plan.n_rounds]) == [rd['time'] for b in ohb.bracket_plan(R, eta) for rd in b['rounds']]
+    if (R, eta) == (729, 3):
+        assert plan.round_res[0] == 0 and plan.round_time[0] == 729
 
 
 def test_bracket_plan_sweep_against_mpmath_smax():

@@ -40,9 +40,9 @@ def test_parzen_models_and_scores_match_oracle(n_obs):
     # inside a suggestion the simulation kernel skips the weight normalisation and the truncation mass: a per-problem
     # constant shift of the scores, the same arg-max
     shift = lean - scores
-    assert np.all(np.abs(shift - shift.mean(axis=1, keepdims=True)) < 2e-3), np.abs(shift - shift.mean(axis=1, keepdims=True)).max()
+    assert np.all(np.abs(shift - shift.mean(axis=1, keepdims=True)) < 2e-5), np.abs(shift - shift.mean(axis=1, keepdims=True)).max()
     top2 = np.sort(scores, axis=1)[:, -2:]
-    clear = top2[:, 1] - top2[:, 0] > 5e-3
+    clear = top2[:, 1] - top2[:, 0] > 5e-5
     assert np.array_equal(np.argmax(lean, axis=1)[clear], np.argmax(scores, axis=1)[clear]) and clear.sum() >= 4
     for k in range(n_prob):
         below, above = otpe.split_trials(obs[k].astype(np.float64), loss[k].astype(np.float64))
@@ -56,8 +56,8 @@ def test_parzen_models_and_scores_match_oracle(n_obs):
         wa, ma, sa = otpe.adaptive_parzen_normal(above, 1.0, 0.5 * (hi + lo), hi - lo)
         want = otpe.gmm1_lpdf(cand[k].astype(np.float64), wb, mb, sb, lo, hi) - \
             otpe.gmm1_lpdf(cand[k].astype(np.float64), wa, ma, sa, lo, hi)
-        assert np.max(np.abs(scores[k] - want)) < 2e-3, (k, np.max(np.abs(scores[k] - want)))
-        assert np.argmax(scores[k]) == np.argmax(want) or np.sort(want)[-1] - np.sort(want)[-2] < 5e-3
+        assert np.max(np.abs(scores[k] - want)) < 2e-5, (k, np.max(np.abs(scores[k] - want)))
+        assert np.argmax(scores[k]) == np.argmax(want) or np.sort(want)[-1] - np.sort(want)[-2] < 5e-5
 
 
 def _spec(func, fams, R=81, noise=10, mom='min'):
@@ -101,21 +101,28 @@ def test_hybrid_structure_and_invariants():
         assert torch.equal(again['ofe'], out['ofe'][300:800])
 
 
-HYBRID_PICKLES = [
-    ('simulation-rastrigin-families-2/hist-sim-rastrigin-sim(hb+tpe+transfer+none)-7000-1', 'rastrigin', FAM6, 10, 'none'),
-    ('simulation-rastrigin-families-2/hist-sim-rastrigin-sim(hb+tpe+transfer+all)-7000-1', 'rastrigin', FAM6, 10, 'all'),
-    ('simulation-rastrigin-families-2/hist-sim-rastrigin-sim(hb+tpe+transfer+same)-7000-1', 'rastrigin', FAM6, 10, 'same'),
-    ('simulation-rastrigin-families-2/hist-sim-rastrigin-sim(hb+tpe+transfer+longest)-7000-1', 'rastrigin', FAM6, 10, 'longest'),
-    ('simulation-rastrigin-families-1/hist-sim-rastrigin-sim(hb+tpe+transfer+all)-7000-1', 'rastrigin', FAM6[:3], 10, 'all'),
-    ('simulation-flat-branin/hist-sim(hb+tpe+transfer+none)-7000-1', 'branin', FLAT, 0, 'none'),
-    ('simulation-flat-drop-wave/hist-sim-wave-sim(hb+tpe+transfer+all)-7000-1', 'wave', FLAT, 0, 'all'),
-]
+# every hybrid OFE vector the reference stores (epdf_ofes/simulation-*/...sim(hb+tpe+transfer+*)...): five problem
+# directories x four transfer modes
+_SIM_DIRS = [('simulation-rastrigin-families-2/hist-sim-rastrigin-', 'rastrigin', FAM6, 10),
+             ('simulation-rastrigin-families-1/hist-sim-rastrigin-', 'rastrigin', FAM6[:3], 10),
+             ('simulation-flat-rastrigin/hist-sim-rastrigin-', 'rastrigin', FLAT, 0),
+             ('simulation-flat-branin/hist-', 'branin', FLAT, 0),
+             ('simulation-flat-drop-wave/hist-sim-wave-', 'wave', FLAT, 0)]
+HYBRID_PICKLES = [(f'{pre}sim(hb+tpe+transfer+{mode})-7000-1', func, fams, noise, mode)
+                  for pre, func, fams, noise in _SIM_DIRS for mode in ('none', 'all', 'same', 'longest')]
+# Stand-alone TPE vectors of the flat problems (a flat trajectory is constant, so n_resources does not matter and the OFE
+# is the best f(x, y) among the evaluations).  The pickles do NOT record max_iter; scanning it (scripts/tpe_budget_scan.py,
+# device and oracle alike) leaves 13 evaluations for sim(tpe) and 25 for sim(tpe2xbudget) as the closest counts on all three
+# problems (12 / 14 and 24 / 26 are each rejected on at least two of them) - i.e. ten random start-up trials plus 3 / 15
+# suggestions.  An inferred configuration: a consistency check of the early TPE phase, not a pin.
+TPE_PICKLES = [(f'{pre}sim({m})-7000-1', func, n_eval) for pre, func, fams, _ in _SIM_DIRS if fams is FLAT
+               for m, n_eval in (('tpe', 13), ('tpe2xbudget', 25))]
 
 
 @pytest.mark.parametrize('key,func,fams,noise,transfer', HYBRID_PICKLES)
 def test_hybrid_ofe_distribution_matches_reference_pickles(key, func, fams, noise, transfer):
     """The only pins on TPE behaviour the reference offers: its stored 7000-repetition OFE vectors of the hybrids
-    (two-sample KS p > 0.01, fixed seed).  Plain Hyperband is distinguishable from these vectors (the reference's own
+    (two-sample KS at a family-wise 0.01 level over the twenty vectors and D < 0.03, fixed seed).  Plain Hyperband is distinguishable from these vectors (the reference's own
     HB-vs-hybrid KS is D = 0.07, p = 2e-14), so passing is not vacuous - see test_hybrid_differs_from_hyperband."""
     from scipy.stats import ks_2samp
 
@@ -123,7 +130,24 @@ def test_hybrid_ofe_distribution_matches_reference_pickles(key, func, fams, nois
     want = np.load(f'{GOLDEN}/epdf_ofes.npz')[key]
     got = run_hybrid_repetitions(_spec(func, fams, 81, noise), 20000, transfer, seed=21)['ofe'].cpu().numpy().astype(np.float64)
     res = ks_2samp(got, want)
-    assert res.pvalue > 0.01, (res, got.mean(), want.mean(), got.std(), want.std())
+    # twenty vectors are tested: 0.01 family-wise (Bonferroni) is 5e-4 per vector; measured: 19 of 20 above 0.01, one at 0.003
+    assert res.pvalue > 0.01 / len(HYBRID_PICKLES), (res, got.mean(), want.mean(), got.std(), want.std())
+    assert res.statistic < 0.03
+
+
+@pytest.mark.parametrize('key,func,n_eval', TPE_PICKLES)
+def test_standalone_tpe_ofe_distribution_close_to_reference_pickles(key, func, n_eval):
+    """Stand-alone TpeOptimiser against the reference's stored sim(tpe) / sim(tpe2xbudget) OFE vectors of the flat problems at
+    the inferred evaluation counts (see TPE_PICKLES): the two CDFs stay within 0.05 of each other (one evaluation more or
+    fewer moves them apart by 0.03-0.05, so this bounds the count and the behaviour of the first suggestions together)."""
+    from scipy.stats import ks_2samp
+
+    from autotune.b200.engine import run_tpe_repetitions
+    want = np.load(f'{GOLDEN}/epdf_ofes.npz')[key]
+    got = run_tpe_repetitions(_spec(func, FLAT, 81, 0), 20000, 24, n_eval, seed=23)['ofe'].cpu().numpy().astype(np.float64)
+    res = ks_2samp(got, want)
+    assert res.statistic < 0.05, (res, got.mean(), want.mean())
+    assert abs(got.mean() - want.mean()) < 0.04 * abs(want.mean()), (got.mean(), want.mean())
 
 
 def test_hybrid_differs_from_hyperband():
@@ -214,3 +238,71 @@ def test_truncated_mixture_sampler_matches_hyperopts_rejection_sampler(case):
     want = otpe.gmm1_sample(w, mu, sg, lo, hi, 20000, np.random.RandomState(11))
     res = ks_2samp(samples, want)
     assert res.pvalue > 0.01, (case, res)
+
+
+@pytest.mark.parametrize('R,eta,n_reps', [(81, 3, 200), (729, 9, 12)])
+def test_transfer_bookkeeping_follows_the_reference_predicates(R, eta, n_reps):
+    """How many earlier evaluations each bracket's TPE run receives (details output n_injected) equals the count the
+    reference's predicates give (hybrid_hyperband_tpe_with_transfer.py:96-98,128-130,161-209) on the resource count it
+    records per evaluator: int(r_i) of the arm's latest round - which is 0, not R, in the round whose read wraps to the last
+    point (R = 729 with eta = 3 or 9: r = 0.9999999999999999), so those arms are NOT transferable in any mode.  (R = 729, eta = 9:
+    two brackets of 729 + 81 arms, the largest such plan whose tables fit the TPE kernel's shared memory.)"""
+    from oracle import hyperband as ohb
+    from oracle.hybrid import is_transferable
+
+    from autotune.b200.engine import run_hybrid_repetitions
+    from autotune.b200.engine import HyperbandSimSpec
+    spec = HyperbandSimSpec('rastrigin', FAM6[:2], R, eta, 10, 'uniform', 'min')
+    plan = ohb.bracket_plan(R, eta)
+    if R == 729:
+        assert plan[0]['rounds'][0]['time'] == 0
+    for mode in ('all', 'longest', 'same', 'threshold'):
+        out = run_hybrid_repetitions(spec, n_reps, mode, threshold=9, seed=4, details=True)
+        surv, inj = out['survivors'].cpu().numpy(), out['n_injected'].cpu().numpy()
+        assert inj.shape == (n_reps, len(plan))
+        for rep in range(n_reps):
+            latest, first, pos = {}, 0, 0
+            for bi, b in enumerate(plan):
+                r0 = b['rounds'][0]['resource']
+                if bi > 0 and b['n'] > 10:      # a bracket of <= 10 arms never leaves hyperopt's start-up: nothing to inject
+                    want = sum(is_transferable(mode, r, r0, R, 9) for r in latest.values())
+                    assert inj[rep, bi] == want, (mode, rep, bi, inj[rep], want)
+                alive = list(range(first, first + b['n']))
+                for rd in b['rounds']:
+                    for a in alive:
+                        latest[a] = rd['time']
+                    k = min(rd['keep'], len(alive))
+                    alive = surv[rep, pos:pos + k].tolist()
+                    pos += k
+                first += b['n']
+
+
+@pytest.mark.parametrize('n_obs', [12, 40, 117])
+def test_suggestion_argmax_never_differs_from_float64_over_many_problems(n_obs):
+    """A suggestion is the arg-max of the score over 24 candidates.  Over 2048 random suggestion problems per history length
+    the device scores - the full form and the lean one used inside tpe_sim - stay within 2e-5 of the float64 restatement
+    (measured 1e-6, scripts/tpe_score_stats.py) and pick the same candidate every time."""
+    n_prob, n_cand, lo, hi = 2048, 24, -5.12, 5.12
+    rng = np.random.default_rng(1000 + n_obs)
+    obs = rng.uniform(lo, hi, (n_prob, n_obs)).astype(np.float32)
+    loss = rng.normal(size=(n_prob, n_obs)).astype(np.float32)
+    cand = rng.uniform(lo, hi, (n_prob, n_cand)).astype(np.float32)
+    scores, _, lean, _ = torch.ops.at2.tpe_score(torch.from_numpy(obs).cuda(), torch.from_numpy(loss).cuda(), lo, hi,
+                                                 _tpe_bytes(), torch.from_numpy(cand).cuda())
+    scores, lean = scores.cpu().numpy().astype(np.float64), lean.cpu().numpy().astype(np.float64)
+    flips = 0
+    for k in range(n_prob):
+        if len(np.unique(obs[k])) < n_obs:
+            # two equal observations: hyperopt orders the components with np.argsort(mus), which is not stable, so which of
+            # the two gets which age weight is implementation-defined there (seen once in 6144 problems, score off by 1e-3)
+            continue
+        below, above = otpe.split_trials(obs[k].astype(np.float64), loss[k].astype(np.float64))
+        wb, mb, sb = otpe.adaptive_parzen_normal(below, 1.0, 0.5 * (hi + lo), hi - lo)
+        wa, ma, sa = otpe.adaptive_parzen_normal(above, 1.0, 0.5 * (hi + lo), hi - lo)
+        want = otpe.gmm1_lpdf(cand[k].astype(np.float64), wb, mb, sb, lo, hi) - \
+            otpe.gmm1_lpdf(cand[k].astype(np.float64), wa, ma, sa, lo, hi)
+        assert np.abs(scores[k] - want).max() < 2e-5
+        d = lean[k] - want
+        assert np.abs(d - d.mean()).max() < 2e-5
+        flips += int(np.argmax(lean[k]) != np.argmax(want)) + int(np.argmax(scores[k]) != np.argmax(want))
+    assert flips == 0
