@@ -94,6 +94,13 @@ static std::atomic<unsigned> g_launch_seq{0};   // one sequence for every kernel
 // Register cap 80 (65536 / 768): shared memory (a 3-repetition tile per warp) holds about 24 warps per SM anyway - three
 // 8-warp CTAs when the constant tables are small, ONE 24-warp CTA when they are large (six families: 18 KB per CTA), see
 // choose_launch.  Measured -4 % against a 64-register cap on the configurations with smoothed families.
+// capture-free second half of the trajectory loop (sim_core.cuh philox_trajectory SPLIT) per loop variant
+#ifndef AT2_SPLIT_LEAN
+#define AT2_SPLIT_LEAN true
+#endif
+#ifndef AT2_SPLIT_SMOOTH
+#define AT2_SPLIT_SMOOTH false
+#endif
 #ifndef AT2_HB_MAX_WARPS
 #define AT2_HB_MAX_WARPS 24
 #endif
@@ -122,7 +129,9 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
     const T* s_pw = (GTAB ? p.tables : s_tab) + L.off_pw();
     const SimTables tb{GTAB ? (uint32_t)(L.off_rec() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_rec),
                        GTAB ? (uint32_t)(L.off_sg() * sizeof(T)) : (uint32_t)__cvta_generic_to_shared(s_sg), s_ckpos, R,
-                       L.sg_stride, reinterpret_cast<const unsigned char*>(p.tables)};
+                       L.sg_stride, reinterpret_cast<const unsigned char*>(p.tables),
+                       // the end value is the last checkpoint: everything after the second-to-last one runs capture-free
+                       p.plan.ckpt_time[C - 1] == R ? (C >= 2 ? p.plan.ckpt_time[C - 2] : 1) : INT_MAX};
 
     unsigned char* my_team = team_base + (size_t)team * p.team_bytes;
     T* s_ck = reinterpret_cast<T*>(my_team);                                          // [C][stride]
@@ -198,12 +207,13 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
                 const float fn = f - (float)fam.s1;                          // opt_function_simulation_problem.py:63
                 const float f1 = (f + p.sp.noise * d.z) - (float)fam.s0;     // :62,:64
                 if (!HAS_SMOOTH || (listed && k + 32 <= n_raw))
-                    philox_trajectory<T, false, 1, false, GTAB>(tb, active, false, f1, fn, (float)fam.up, fam.pw_off, gid,
-                                                                p.sp.rk, R, s_ck + ii, p.stride, C);
+                    philox_trajectory<T, false, 1, false, GTAB, AT2_SPLIT_LEAN>(tb, active, false, f1, fn, (float)fam.up,
+                                                                                fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
+                                                                                p.stride, C);
                 else
-                    philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB>(tb, active, HAS_SMOOTH && fam.smooth != 0, f1, fn,
-                                                                      (float)fam.up, fam.pw_off, gid, p.sp.rk, R, s_ck + ii,
-                                                                      p.stride, C);
+                    philox_trajectory<T, HAS_SMOOTH, CK, false, GTAB, AT2_SPLIT_SMOOTH>(tb, active, HAS_SMOOTH && fam.smooth != 0,
+                                                                                        f1, fn, (float)fam.up, fam.pw_off, gid,
+                                                                                        p.sp.rk, R, s_ck + ii, p.stride, C);
             }
         } else {
             for (int base = wteam * 32; base < n_items; base += p.team_warps * 32) {

@@ -4,8 +4,7 @@
 // core/shape_family_scheduler.py:50-77 (family choice).
 #pragma once
 #include <climits>
-
-
+#include <type_traits>
 
 #include "at2_common.cuh"
 
@@ -191,6 +190,8 @@ struct SimTables {
     const int* ckpos;      // checkpoint positions (ckpt_time - 1), INT_MAX-terminated, in shared memory
     int R, sg_stride;
     const unsigned char* gbase = nullptr;   // GTAB only: the table in global memory
+    int lean_from = INT_MAX;   // first step (1-based record row) from which no checkpoint but the end value follows, see
+                               // philox_trajectory SPLIT; INT_MAX: the plan's last checkpoint is not the last position
 };
 
 // ---- the Philox word stream of a trajectory ---------------------------------------------------------------------------
@@ -279,7 +280,13 @@ __device__ __forceinline__ float step_folded(float f, float g, float fn, float u
 // `only_c` is produced, into ck[0] (instantiate with CK = 1: a smoothed arm then accumulates that one Savitzky-Golay
 // read-out - one scalar table fetch and one FMA per step instead of all C of them).  The stream and the arithmetic are
 // the same as in the full run, so the value equals the one the full run reads at that checkpoint, bit for bit.
-template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false>
+//
+// SPLIT = true (full runs): the loop exists twice.  Hyperband's checkpoints are geometric (R eta^-k), so all but the last
+// sit in the first 1/eta of the trajectory and the last is the end value: once every lane of the warp has passed the
+// second-to-last checkpoint (tb.lean_from) the rest of the run goes through a copy of the loop without the capture
+// instructions (4 of ~49 per attempt), and the end value is stored after the loop.  Plans whose last checkpoint is not the
+// last position keep the capturing loop throughout (lean_from = INT_MAX).
+template <typename T, bool HAS_SMOOTH, int CK, bool PARTIAL = false, bool GTAB = false, bool SPLIT = false>
 __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool active, bool smooth, float f1, float fnf,
                                                   float upc, int pw_off, unsigned long long gid,
                                                   const uint32_t* __restrict__ rk, int stop_t, T* ck, int stride, int C,
@@ -324,14 +331,15 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         }
     }
     const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-    auto attempt = [&](float x, float ku) {
+    auto attempt = [&](float x, float ku, auto cap_tag) {
+        constexpr bool CAPTURE = decltype(cap_tag)::value;
         const float4 gm = tab128<GTAB>(gbase, addr);                               // d, c, d log2e, d log2e + 32
         const float4 pw = tab128<GTAB>(gbase, addr + 16u);                         // +-w, K1w, K0, P11
         const AttemptOut o = mt_attempt(gm, pw, x, ku, ff, fnf, upc);
         bool ok = o.ok;
         if constexpr (PARTIAL) ok = ok && addr < end_addr;
         ff = ok ? o.fnew : ff;
-        if constexpr (!PARTIAL) {
+        if constexpr (CAPTURE) {
             // smooth lanes store too (into rows the read-outs below overwrite): no test of their own
             const bool cap = ok && __float_as_int(pw.x) < 0;
             sts32_if(ckp, ff, cap);                  // predicated store: no branch in the attempt
@@ -354,11 +362,11 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         }
         if (ok) addr += AT2_REC * 4u;
     };
-    auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu) {
+    auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu, auto cap_tag) {
         float x0, x1, ku0, ku1;
         box_muller_pair(wa, wb, wu, x0, x1, ku0, ku1);
-        attempt(x0, ku0);
-        attempt(x1, ku1);
+        attempt(x0, ku0, cap_tag);
+        attempt(x1, ku1, cap_tag);
     };
     auto block = [&](uint32_t ctr) { return at2_philox10_rk(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, rk); };
     auto unfinished = [&]() { return __any_sync(0xffffffffu, addr < end_addr); };
@@ -374,27 +382,46 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         // separate tail loop each (ncu, six families: no_instruction 1.1 cycles per instruction; merged: 3.13 -> 2.89 ms).
         // Full runs test for completion every eight attempts (a mid-body test costs more in scheduling freedom than the
         // ~2 attempts per pass it saves: measured +1.5 %); partial runs - often only a few steps long - every four.
+        // run(cap_tag, n_counted, until): superblocks while fewer than n_counted have run or some lane is below `until`
+        int it = 0;
+        auto run = [&](auto cap_tag, int n_counted, uint32_t until) {
 #pragma unroll 1
-        for (int it = 0;; ++it) {
-            if (it >= n_main && !unfinished()) break;
-            B = block(ctr + 1);
-            At2U4 An;
-            if constexpr (PARTIAL) {
-                pair(A.x, A.y, A.z);
-                pair(A.w, B.x, B.y);
-                if (it >= n_main && !unfinished()) break;
-                Cb = block(ctr + 2);
-                An = block(ctr + 3);
-            } else {
-                Cb = block(ctr + 2);
-                An = block(ctr + 3);
-                pair(A.x, A.y, A.z);
-                pair(A.w, B.x, B.y);
+            for (;; ++it) {
+                if (it >= n_counted && !__any_sync(0xffffffffu, addr < until)) break;
+                B = block(ctr + 1);
+                At2U4 An;
+                if constexpr (PARTIAL) {
+                    pair(A.x, A.y, A.z, cap_tag);
+                    pair(A.w, B.x, B.y, cap_tag);
+                    if (it >= n_counted && !__any_sync(0xffffffffu, addr < until)) break;
+                    Cb = block(ctr + 2);
+                    An = block(ctr + 3);
+                } else {
+                    Cb = block(ctr + 2);
+                    An = block(ctr + 3);
+                    pair(A.x, A.y, A.z, cap_tag);
+                    pair(A.w, B.x, B.y, cap_tag);
+                }
+                ctr += 3;
+                pair(B.z, B.w, Cb.x, cap_tag);
+                pair(Cb.y, Cb.z, Cb.w, cap_tag);
+                A = An;
             }
-            ctr += 3;
-            pair(B.z, B.w, Cb.x);
-            pair(Cb.y, Cb.z, Cb.w);
-            A = An;
+        };
+        if constexpr (PARTIAL) {
+            run(std::false_type{}, n_main, end_addr);
+        } else if constexpr (!SPLIT) {
+            run(std::true_type{}, n_main, end_addr);
+        } else {
+            // capturing superblocks until every lane stands at or beyond step lean_from (inactive lanes sit on the sentinel,
+            // beyond any step), then the capture-free copy to the end; the end value is the last checkpoint
+            const bool split = tb.lean_from < R;
+            const uint32_t lean_addr = rec_base + (uint32_t)(split ? tb.lean_from : R) * (AT2_REC * 4u);
+            run(std::true_type{}, split ? ((tb.lean_from - 1) >> 3) : n_main, split ? lean_addr : end_addr);
+            if (split) {
+                run(std::false_type{}, n_main, end_addr);
+                sts32_if(ckp, ff, active);
+            }
         }
     }
     if constexpr (PARTIAL) {
