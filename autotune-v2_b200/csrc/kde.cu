@@ -8,8 +8,10 @@
 // Shape of the work at the reference sizes: N = 1e5..1e6 samples (0.4-4 MB, L2 resident), G = 1000 grid points,
 // N*G pair terms of 3 FP32 instructions each -> compute bound.  Each thread keeps GPT grid points in registers and
 // streams a chunk of samples through shared memory (128-bit coalesced loads, broadcast reads), so HBM/L2 traffic is
-// N*4 B per grid tile.  Partial sums per (chunk, grid point) are reduced in a fixed order by a second kernel in
-// double -> deterministic output.
+// N*4 B per grid tile.  The CTAs' partial sums are added as 64-bit FIXED-POINT integers (2^-20 units) with L2 atomics:
+// integer addition is associative, so the result does not depend on the order in which CTAs finish - deterministic
+// output without a serial reduction pass; the last CTA of a grid tile converts, normalises and hands the accumulators
+// back zeroed.  (Grids wider than the accumulator array fall back to per-chunk partial rows + a fixed-order second kernel.)
 #include <atomic>
 
 #include "at2_common.cuh"
@@ -38,6 +40,11 @@ __device__ __forceinline__ float fast_ex2(float x) {
 #define KDE_SLOTS 32
 #define KDE_MAX_GTILES 16
 __device__ unsigned int g_kde_done[KDE_SLOTS][KDE_MAX_GTILES];
+// fixed-point accumulators of the launches in flight: a CTA's float partial sum (<= its chunk length, terms in [0, 1]) times
+// 2^20 is an exact integer below 2^63 for any chunk; the total stays below 2^53 for n < 2^33 samples, so the double it
+// converts to is exact as well.  Zero whenever a slot is handed out (module load; the last CTA re-zeroes what it read).
+#define KDE_FIX_SCALE 1048576.0f
+__device__ unsigned long long g_kde_acc[KDE_SLOTS][KDE_MAX_GTILES * KDE_TILE_G];
 
 struct KdeOut {
     float* dens;             // normalised density [G] (single-GPU form), or nullptr
@@ -97,41 +104,38 @@ __global__ void __launch_bounds__(KDE_BLOCK) kde_partial_kernel(const float* __r
             }
         }
     }
+    if (done_slot < 0) {                       // more grid tiles than accumulators: partial rows, kde_finish_kernel reduces
+#pragma unroll
+        for (int k = 0; k < KDE_GPT; ++k) {
+            const int j = gtile * KDE_TILE_G + k * KDE_BLOCK + threadIdx.x;
+            if (j < G) partial[(size_t)chunk * G + j] = acc[k];
+        }
+        return;
+    }
+    unsigned long long* fix = g_kde_acc[done_slot];
 #pragma unroll
     for (int k = 0; k < KDE_GPT; ++k) {
         const int j = gtile * KDE_TILE_G + k * KDE_BLOCK + threadIdx.x;
-        if (j < G) partial[(size_t)chunk * G + j] = acc[k];
+        if (j < G) atomicAdd(fix + j, (unsigned long long)__float2ll_rn(acc[k] * KDE_FIX_SCALE));
     }
-    if (done_slot < 0) return;                 // more grid tiles than counters: kde_finish_kernel reduces
-    // last CTA of this grid tile: reduce the tile's partial sums over the chunks, in chunk order, in double -> the same
-    // bits whatever the CTA schedule was
+    // last CTA of this grid tile: convert the tile's sums (the same integers whatever the CTA schedule was), write the
+    // outputs and zero the accumulators for the slot's next launch
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_ticket = atomicAdd(&g_kde_done[done_slot][gtile], 1u);
     __syncthreads();
     if (s_ticket != (unsigned)n_chunks - 1u) return;
     __threadfence();
-    double s[KDE_GPT];
-#pragma unroll
-    for (int k = 0; k < KDE_GPT; ++k) s[k] = 0.0;
-    const int j0 = gtile * KDE_TILE_G + threadIdx.x;
-#pragma unroll 4
-    for (int c = 0; c < n_chunks; ++c) {
-#pragma unroll
-        for (int k = 0; k < KDE_GPT; ++k) {
-            const int j = j0 + k * KDE_BLOCK;
-            if (j < G) s[k] += (double)__ldcg(partial + (size_t)c * G + j);
-        }
-    }
 #pragma unroll
     for (int k = 0; k < KDE_GPT; ++k) {
-        const int j = j0 + k * KDE_BLOCK;
+        const int j = gtile * KDE_TILE_G + k * KDE_BLOCK + threadIdx.x;
         if (j >= G) continue;
-        if (out.dens != nullptr) out.dens[j] = (float)(s[k] * out.norm);
+        const double sum = (double)(long long)atomicExch(fix + j, 0ull) * (1.0 / (double)KDE_FIX_SCALE);
+        if (out.dens != nullptr) out.dens[j] = (float)(sum * out.norm);
         if (out.is_multicast)
-            multimem_st_f64(out.target[0] + out.slot_off + j, s[k]);
+            multimem_st_f64(out.target[0] + out.slot_off + j, sum);
         else
-            for (int r = 0; r < out.n_targets; ++r) out.target[r][out.slot_off + j] = s[k];
+            for (int r = 0; r < out.n_targets; ++r) out.target[r][out.slot_off + j] = sum;
     }
     if (threadIdx.x == 0) g_kde_done[done_slot][gtile] = 0u;
 }

@@ -169,7 +169,9 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
     // the second block feeds the initial noise and the extra coordinates only: nothing reads it on a noise-free 2-D problem
     if (sp.noise != 0.0f || sp.func == AT2_FUNC_EGG4) {
         const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
-        d.z = sqrtf(-2.0f * logf(u1)) * cospif((float)(r2.x >> 8) * 1.1920928955078125e-7f);
+        // Box-Muller with the approximate MUFU forms (relative error ~1e-6, far below the FP32 tolerance tier; the full and
+        // the early-stopping kernels share this function, so they stay bit-identical to each other)
+        d.z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) * fast_cos((float)(r2.x >> 8) * 3.7450703e-7f);   // 2 pi / 2^24
         d.x2 = fmaf((float)(r2.y >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
         d.y2 = fmaf((float)(r2.z >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
     }
@@ -420,7 +422,9 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
             run(std::true_type{}, split ? ((tb.lean_from - 1) >> 3) : n_main, split ? lean_addr : end_addr);
             if (split) {
                 run(std::false_type{}, n_main, end_addr);
-                sts32_if(ckp, ff, active);
+                // to the last row by its own address, not through ckp: on a short plan a lane may already have captured the
+                // end value in the capturing copy (same value - the store is idempotent - but ckp has moved past the row)
+                sts32_if((uint32_t)__cvta_generic_to_shared(ck) + (uint32_t)(C - 1) * row_bytes, ff, active);
             }
         }
     }
