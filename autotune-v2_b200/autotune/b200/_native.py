@@ -123,6 +123,7 @@ def _load():
                                           i64, vp, i64, vp]),
         'at2_segmented_topk_f32': (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
         'at2_segmented_topk_f64': (C.c_int, [vp, vp, vp, i64, i32, i32, vp, vp]),
+        'at2_family_slots': (i32, [C.POINTER(SimConfig), C.POINTER(i32)]),
         'at2_kde_combine_f64': (C.c_int, [vp, i32, i32, i64, C.c_double, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():

@@ -58,7 +58,8 @@ static int at2_resident_by_regs(Kern kern, int block, int* out) {
 }
 
 // ---- constant-table layout shared by host builder and kernels (units: reals) --------------------------------------
-// rec: one 12-real record per (family, step): row r = f * rows + t with t in [0,R] and rows = at2_rec_rows(R) (R + 1
+// rec: one 12-real record per (family block, step) - families with equal (ml_agg, nec_agg) share a block, see
+//      at2_family_slot_map; F below counts blocks: row r = f * rows + t with t in [0,R] and rows = at2_rec_rows(R) (R + 1
 //      made odd, see below).  Row t = 0 of a family is unused; row R is a sentinel whose c is NaN, so the acceptance test
 //      of a finished lane can never pass and no bounds check is needed in the inner loop.
 //   float tables (Philox paths): two 128-bit loads from one address (+0, +16 bytes), 16 bytes spare:
@@ -99,6 +100,24 @@ static inline int at2_check_gather(const at2_gather* g, const char* who) {
     AT2_REQUIRE(!g->is_multicast || g->n_targets == 1, "%s: a multicast gather has exactly one target address", who);
     for (int r = 0; r < g->n_targets; ++r) AT2_REQUIRE(g->d_target[r] != nullptr, "%s: gather target %d is NULL", who, r);
     return AT2_OK;
+}
+
+// Families that share (ml_agg, nec_agg) have identical per-step records (the other family attributes - up_spik, the shifts,
+// is_smooth - are per-arm scalars, not table entries): they share one block of the table.  slot[f] = index of family f's
+// block; returns the number of blocks.  (The reference's six general families are two copies of three shapes with
+// different shifts, run_simulation.py:41-47: 3 blocks, 12 KB less shared memory per CTA.)
+static inline int at2_family_slot_map(const at2_sim_config* cfg, int* slot) {
+    int n = 0;
+    for (int f = 0; f < cfg->n_families; ++f) {
+        slot[f] = -1;
+        for (int g = 0; g < f; ++g)
+            if (cfg->fam[g].ml_agg == cfg->fam[f].ml_agg && cfg->fam[g].nec_agg == cfg->fam[f].nec_agg) {
+                slot[f] = slot[g];
+                break;
+            }
+        if (slot[f] < 0) slot[f] = n++;
+    }
+    return n;
 }
 
 static inline int at2_cfg_has_smooth(const at2_sim_config* cfg) {

@@ -243,14 +243,18 @@ static int check_cfg(const at2_plan* plan, const at2_sim_config* cfg) {
 
 extern "C" int64_t at2_hb_tables_bytes(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64) {
     if (check_cfg(plan, cfg) != AT2_OK) return AT2_EINVAL;
-    At2TableLayout L{plan->R, cfg->n_families, at2_cfg_has_smooth(cfg), at2_sg_stride(plan->n_ckpts)};
+    int slot[AT2_MAX_FAMILIES];
+    At2TableLayout L{plan->R, at2_family_slot_map(cfg, slot), at2_cfg_has_smooth(cfg), at2_sg_stride(plan->n_ckpts)};
     return (int64_t)L.total() * (is_f64 ? 8 : 4);
 }
 
 template <typename T>
 static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out) {
-    const int R = plan->R, F = cfg->n_families;
+    const int R = plan->R;
     const bool f32 = sizeof(T) == 4;
+    int slot[AT2_MAX_FAMILIES], first_of[AT2_MAX_FAMILIES];     // first_of[block] = a family that owns the block
+    const int F = at2_family_slot_map(cfg, slot);              // blocks of records, one per distinct (ml_agg, nec_agg)
+    for (int f = cfg->n_families - 1; f >= 0; --f) first_of[slot[f]] = f;
     At2TableLayout L{R, F, at2_cfg_has_smooth(cfg), at2_sg_stride(plan->n_ckpts)};
     for (int i = 0; i < L.total(); ++i) out[i] = (T)0;
     const double k = 2.0;  // simulation_evaluator.py:94
@@ -272,9 +276,10 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
         for (int f = 0; f < F; ++f) {
             T* row = rec + (size_t)AT2_REC * (f * rows + t);
             T* rpw = row + 4;
-            const double P = pow(frac, cfg->fam[f].nec_agg);          // :105
-            const double P11 = pow(frac, 1.1 * cfg->fam[f].nec_agg);  // :112
-            const double ml = cfg->fam[f].ml_agg / 100.0, w = d * scale;
+            const at2_family& fam = cfg->fam[first_of[f]];
+            const double P = pow(frac, fam.nec_agg);          // :105
+            const double P11 = pow(frac, 1.1 * fam.nec_agg);  // :112
+            const double ml = fam.ml_agg / 100.0, w = d * scale;
             const double K1 = ml * (1.0 - P), K0 = P - 2.0 * ml * (1.0 - P);   // a (1-P) + P with a = (g-2) ml
             row[0] = (T)d;
             row[1] = (T)c;
@@ -315,6 +320,14 @@ static int build_tables(const at2_plan* plan, const at2_sim_config* cfg, T* out)
             for (int c = 0; c < plan->n_ckpts; ++c) sg[t * L.sg_stride + c] = (T)W[(size_t)c * R + t];
     }
     return AT2_OK;
+}
+
+extern "C" int32_t at2_family_slots(const at2_sim_config* cfg, int32_t* slots) {
+    if (cfg == nullptr || slots == nullptr || cfg->n_families < 1 || cfg->n_families > AT2_MAX_FAMILIES) return AT2_EINVAL;
+    int slot[AT2_MAX_FAMILIES];
+    const int n = at2_family_slot_map(cfg, slot);
+    for (int f = 0; f < cfg->n_families; ++f) slots[f] = slot[f];
+    return n;
 }
 
 extern "C" int at2_hb_tables_build(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64, void* host_out) {

@@ -52,7 +52,7 @@ template <bool HAS_SMOOTH, bool GTAB>
 __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
-    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    const At2TableLayout L{R, p.sp.n_slots, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
     const int tab_elems = GTAB ? 0 : (L.total_philox() + 3) & ~3;   // GTAB: tables stay in global memory (sim_core.cuh tab128)
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);
@@ -299,13 +299,15 @@ static int early_stop_impl(const at2_plan* plan, const at2_sim_config* cfg, cons
         p.n_gather = gather->n_targets, p.gather_multicast = gather->is_multicast, p.gather_base = gather->base;
     }
     p.plan = *plan;
+    int slot[AT2_MAX_FAMILIES];
+    p.sp.n_slots = at2_family_slot_map(cfg, slot);
     for (int f = 0; f < cfg->n_families; ++f) {
         p.fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
         p.fam[f].up = (float)cfg->fam[f].up_spik;
         p.fam[f].s0 = (float)cfg->fam[f].start_shift;
         p.fam[f].s1 = (float)cfg->fam[f].end_shift;
         p.fam[f].smooth = cfg->fam[f].is_smooth;
-        p.fam[f].pw_off = f * at2_rec_rows(plan->R);
+        p.fam[f].pw_off = slot[f] * at2_rec_rows(plan->R);
     }
     p.dims = at2_func_dims(cfg->func);
     {
@@ -342,7 +344,7 @@ static int early_stop_impl(const at2_plan* plan, const at2_sim_config* cfg, cons
     p.cur_cap = widest > 512 ? widest : 512;
     if (p.cur_cap > 4 * p.npad) p.cur_cap = 4 * p.npad;
     const int C = plan->n_ckpts;
-    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    At2TableLayout L{plan->R, p.sp.n_slots, has_smooth, at2_sg_stride(C)};
     const size_t tab_bytes = (size_t)((L.total_philox() + 3) & ~3) * 4, fixed_small = 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     const bool force_gtab = at2_debug().force_gtab != 0;
     // launch geometry of tile width g: a warp's tile state (loss buffer, per-repetition state, sort scratch, survivor ids),

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(AT2_HB_MAX_WARPS * 32, 1) hb_sim_kernel(const 
     typedef typename KeyOf<T>::type K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F;
-    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    const At2TableLayout L{R, p.sp.n_slots, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
     // GTAB: the tables stay in global memory (plans too large for shared memory), see sim_core.cuh tab128
     // the Philox kernels stage records + Savitzky-Golay rows; the pre-drawn paths also the folded-step table (pw)
     const int tab_total = MODE == MODE_PHILOX ? L.total_philox() : L.total();
@@ -352,7 +352,7 @@ struct LaunchCfg {
 static int opt_int(int v, int dflt) { return v > 0 ? v : dflt; }   // a debug option, or the library's own choice
 
 template <typename T>
-int choose_launch(const at2_plan* plan, int has_smooth, int F, long long n_reps, int mode, LaunchCfg<T>* out) {
+int choose_launch(const at2_plan* plan, int has_smooth, int F /* record blocks */, long long n_reps, int mode, LaunchCfg<T>* out) {
     typedef typename KeyOf<T>::type K;
     const int A = plan->n_arms, C = plan->n_ckpts, R = plan->R;
     int widest = 0;
@@ -477,6 +477,7 @@ int launch_dispatch(const Params<T>& p, const LaunchCfg<T>& lc, int has_smooth, 
     if (!has_smooth) return launch_one<T, MODE, false, 1>(p, lc, st);
     const int C = p.plan.n_ckpts;
     if (C <= 4) return launch_one<T, MODE, true, 4>(p, lc, st);
+    if (C == 5) return launch_one<T, MODE, true, 5>(p, lc, st);
     if (C <= 6) return launch_one<T, MODE, true, 6>(p, lc, st);
     if (C <= 8) return launch_one<T, MODE, true, 8>(p, lc, st);
     return launch_one<T, MODE, true, 16>(p, lc, st);
@@ -497,13 +498,15 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     AT2_REQUIRE(!has_smooth || at2_savgol_window(plan->R) <= plan->R,
                 "If mode is 'interp', window_length must be less than or equal to the size of x.");
     p->plan = *plan;
+    int slot[AT2_MAX_FAMILIES];
+    p->sp.n_slots = at2_family_slot_map(cfg, slot);
     for (int f = 0; f < cfg->n_families; ++f) {
         p->fam[f].ml = sizeof(T) == 8 ? (T)cfg->fam[f].ml_agg : (T)(cfg->fam[f].ml_agg / 100.0);
         p->fam[f].up = (T)cfg->fam[f].up_spik;
         p->fam[f].s0 = (T)cfg->fam[f].start_shift;
         p->fam[f].s1 = (T)cfg->fam[f].end_shift;
         p->fam[f].smooth = cfg->fam[f].is_smooth;
-        p->fam[f].pw_off = f * at2_rec_rows(plan->R);
+        p->fam[f].pw_off = slot[f] * at2_rec_rows(plan->R);
     }
     p->dims = at2_func_dims(cfg->func);
     p->sp.func = cfg->func, p->sp.F = cfg->n_families, p->sp.scheduler = cfg->scheduler, p->descending = cfg->descending;
@@ -515,7 +518,7 @@ int fill_params(const at2_plan* plan, const at2_sim_config* cfg, const void* d_t
     p->ofe = (T*)out->d_ofe, p->ofe_arm = out->d_ofe_arm, p->best_xy = (T*)out->d_best_xy;
     p->round_best = (T*)out->d_round_best, p->round_best_arm = out->d_round_best_arm;
     p->survivors = out->d_survivors, p->ckpt_loss = (T*)out->d_ckpt_loss;
-    const int rc = choose_launch<T>(plan, has_smooth, cfg->n_families, n_reps, mode, lc);
+    const int rc = choose_launch<T>(plan, has_smooth, p->sp.n_slots, n_reps, mode, lc);
     if (rc != AT2_OK) return rc;
     p->G = lc->G, p->npad = lc->npad, p->stride = lc->stride;
     p->team_warps = lc->team_warps, p->n_teams = lc->n_teams, p->team_bytes = lc->team_bytes;

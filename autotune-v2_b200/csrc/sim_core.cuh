@@ -146,6 +146,7 @@ __device__ __forceinline__ void team_barrier(int team, int team_warps) {
 // Where arms live and how they are drawn (Philox path).
 struct ArmSpace {
     int func, F, scheduler;
+    int n_slots;       // blocks of per-step records in the table (families with equal shapes share one, at2_family_slot_map)
     float x_min, x_rng, y_min, y_rng, noise;
     uint32_t key0, key1;
     uint32_t rk[20];   // Philox key schedule of (key0, key1), at2_round_keys
@@ -319,11 +320,15 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         const float f0 = (active && smooth) ? ff : 0.0f;
 #pragma unroll
         for (int c4 = 0; c4 < CK; c4 += 4) {                                  // sg[0][c] * fs[0]
-            const float4 w = tab128<GTAB>(gbase, sg_base + c4 * 4u);
-            acc[c4] = w.x * f0;
-            if (c4 + 1 < CK) acc[c4 + 1] = w.y * f0;
-            if (c4 + 2 < CK) acc[c4 + 2] = w.z * f0;
-            if (c4 + 3 < CK) acc[c4 + 3] = w.w * f0;
+            if (CK - c4 == 1) {
+                acc[c4] = tab32<GTAB>(gbase, sg_base + c4 * 4u) * f0;
+            } else {
+                const float4 w = tab128<GTAB>(gbase, sg_base + c4 * 4u);
+                acc[c4] = w.x * f0;
+                if (c4 + 1 < CK) acc[c4 + 1] = w.y * f0;
+                if (c4 + 2 < CK) acc[c4 + 2] = w.z * f0;
+                if (c4 + 3 < CK) acc[c4 + 3] = w.w * f0;
+            }
         }
     }
     if constexpr (!PARTIAL) {
@@ -353,13 +358,20 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         } else if constexpr (HAS_SMOOTH) {
             const float fs = (ok && smooth) ? ff : 0.0f;
             const uint32_t a = addr * sg_mul + sg_delta;
+            // The smoothed passes are bound by shared-memory wavefronts (a 128-bit load is four of them whatever the lanes'
+            // addresses; a 32-bit load of lanes standing on up to eight consecutive steps is one: the 48-byte row stride puts
+            // them in distinct banks) - so a lone last weight (CK = 5: R = 81, eta = 3) is fetched as a scalar.
 #pragma unroll
             for (int c4 = 0; c4 < CK; c4 += 4) {
-                const float4 w = tab128<GTAB>(gbase, a + c4 * 4u);
-                acc[c4] = fmaf(w.x, fs, acc[c4]);
-                if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
-                if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
-                if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
+                if (CK - c4 == 1) {
+                    acc[c4] = fmaf(tab32<GTAB>(gbase, a + c4 * 4u), fs, acc[c4]);
+                } else {
+                    const float4 w = tab128<GTAB>(gbase, a + c4 * 4u);
+                    acc[c4] = fmaf(w.x, fs, acc[c4]);
+                    if (c4 + 1 < CK) acc[c4 + 1] = fmaf(w.y, fs, acc[c4 + 1]);
+                    if (c4 + 2 < CK) acc[c4 + 2] = fmaf(w.z, fs, acc[c4 + 2]);
+                    if (c4 + 3 < CK) acc[c4 + 3] = fmaf(w.w, fs, acc[c4 + 3]);
+                }
             }
         }
         if (ok) addr += AT2_REC * 4u;

@@ -352,7 +352,7 @@ template <bool HAS_SMOOTH, int CK>
 __global__ void __launch_bounds__(AT2_TPE_MAX_WARPS * 32, 1) tpe_sim_kernel(const __grid_constant__ TpeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, cap = p.cap;
-    const At2TableLayout L{R, F, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
+    const At2TableLayout L{R, p.sp.n_slots, HAS_SMOOTH ? 1 : 0, at2_sg_stride(C)};
     const int tab_elems = (L.total_philox() + 3) & ~3;
     float* s_tab = reinterpret_cast<float*>(smem_raw);
     int* s_ckpos = reinterpret_cast<int*>(s_tab + tab_elems);       // [AT2_MAX_CKPTS + 4]
@@ -658,13 +658,15 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     int rc = fill_tpe(tpe, &p.tpe);
     if (rc != AT2_OK) return rc;
     p.plan = *plan;
+    int slot[AT2_MAX_FAMILIES];
+    p.sp.n_slots = at2_family_slot_map(cfg, slot);
     for (int f = 0; f < cfg->n_families; ++f) {
         p.fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
         p.fam[f].up = (float)cfg->fam[f].up_spik;
         p.fam[f].s0 = (float)cfg->fam[f].start_shift;
         p.fam[f].s1 = (float)cfg->fam[f].end_shift;
         p.fam[f].smooth = cfg->fam[f].is_smooth;
-        p.fam[f].pw_off = f * at2_rec_rows(plan->R);
+        p.fam[f].pw_off = slot[f] * at2_rec_rows(plan->R);
     }
     p.sp.func = cfg->func, p.sp.F = cfg->n_families, p.sp.scheduler = cfg->scheduler, p.descending = cfg->descending;
     p.sp.x_min = (float)cfg->x_min, p.sp.x_rng = (float)(cfg->x_max - cfg->x_min);
@@ -688,7 +690,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     p.scratch_floats = (int)(scratch / 4);
     size_t wb = (size_t)p.cap * ((C + 5) * 4 + 3 * 2 + 2) + 32 * 2 + scratch;
     p.warp_bytes = (int)((wb + 15) & ~(size_t)15);
-    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(C)};
+    At2TableLayout L{plan->R, p.sp.n_slots, has_smooth, at2_sg_stride(C)};
     const size_t fixed = (size_t)((L.total_philox() + 3) & ~3) * 4 + 2 * (AT2_MAX_CKPTS + 4) * sizeof(int);
     int dev = 0, max_smem = 0, sms = 0;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));

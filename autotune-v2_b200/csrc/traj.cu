@@ -71,21 +71,23 @@ extern "C" int at2_sim_trajectories_f32(const at2_plan* plan, const at2_sim_conf
     AT2_REQUIRE(cfg->n_families >= 1 && cfg->n_families <= AT2_MAX_FAMILIES, "at2_sim_trajectories_f32: n_families %d outside [1,%d]",
                 cfg->n_families, AT2_MAX_FAMILIES);
     Fam<float> fam[8] = {};
+    int slot[AT2_MAX_FAMILIES];
+    const int n_slots = at2_family_slot_map(cfg, slot);
     for (int f = 0; f < cfg->n_families; ++f) {
         fam[f].ml = (float)(cfg->fam[f].ml_agg / 100.0);
         fam[f].up = (float)cfg->fam[f].up_spik;
         fam[f].s0 = (float)cfg->fam[f].start_shift;
         fam[f].s1 = (float)cfg->fam[f].end_shift;
         fam[f].smooth = cfg->fam[f].is_smooth;
-        fam[f].pw_off = f * at2_rec_rows(plan->R);
+        fam[f].pw_off = slot[f] * at2_rec_rows(plan->R);
     }
     const int has_smooth = at2_cfg_has_smooth(cfg);
-    At2TableLayout L{plan->R, cfg->n_families, has_smooth, at2_sg_stride(plan->n_ckpts)};
+    At2TableLayout L{plan->R, n_slots, has_smooth, at2_sg_stride(plan->n_ckpts)};
     const size_t smem = (size_t)L.off_sg() * sizeof(float);
     AT2_CUDA_CHECK(cudaFuncSetAttribute(traj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long grid = (n_arms + 127) / 128;
     if (grid > 148 * 16) grid = 148 * 16;
-    traj_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>((const float*)d_tables, plan->R, cfg->n_families, plan->n_ckpts,
+    traj_kernel<<<(unsigned)grid, 128, smem, (cudaStream_t)stream>>>((const float*)d_tables, plan->R, n_slots, plan->n_ckpts,
                                                                       has_smooth, fam[0], fam[1], fam[2], fam[3], fam[4], fam[5],
                                                                       fam[6], fam[7], n_arms, d_f1, d_fn, d_family,
                                                                       (const unsigned long long*)d_stream_id, (uint32_t)seed,

@@ -131,6 +131,9 @@ int at2_savgol_rows(int32_t R, int32_t n_rows, const int32_t* rows, double* out)
  * checkpoint positions (the trajectory loop stores a loss where a record is flagged) and the Savitzky-Golay columns are
  * the plan's checkpoints - pass the same plan to the build and to the launch.  The caller copies `host_out` to the device
  * and passes it as `d_tables`. */
+/* Families with equal (ml_agg, nec_agg) share one block of per-step records in the tables (their other attributes are
+ * per-arm scalars): slots[f] = block of family f; returns the number of blocks (<= n_families), negative on bad input. */
+int32_t at2_family_slots(const at2_sim_config* cfg, int32_t* slots);
 int64_t at2_hb_tables_bytes(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64);
 int at2_hb_tables_build(const at2_plan* plan, const at2_sim_config* cfg, int32_t is_f64, void* host_out);
 

@@ -104,6 +104,12 @@ def _cfg(families, func='rastrigin', noise=10.0):
     return cfg
 
 
+def _slots(cfg):
+    slots = (C.c_int32 * 8)()
+    n = nat.lib.at2_family_slots(C.byref(cfg), slots)
+    return n, list(slots[:cfg.n_families])
+
+
 FAM6 = [(1.5, 10, 15, False, 0, 200), (0.5, 7, 10, False, 0, 200), (0.2, 4, 7, True, 0, 200),
         (1.5, 10, 15, False, 200, 400), (0.5, 7, 10, False, 200, 400), (0.2, 4, 7, True, 200, 400)]
 
@@ -115,10 +121,11 @@ def test_tables_f64_bit_exact_with_python_floats(R):
     nbytes = nat.lib.at2_hb_tables_bytes(C.byref(plan), C.byref(cfg), 1)
     buf = np.zeros(nbytes // 8, np.float64)
     nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 1, buf.ctypes.data))
-    F = len(FAM6)
+    F, slot = _slots(cfg)                                             # record blocks: equal shapes share one
+    assert (F, slot) == (3, [0, 1, 2, 0, 1, 2])
     rows = (R + 1) | 1                                                # csrc/at2_common.cuh at2_rec_rows
     rec = buf[:12 * F * rows].reshape(F, rows, 12)                    # 12-real records (csrc/at2_common.cuh AT2_REC)
-    for f, fam in enumerate(FAM6):
+    for f, fam in zip(slot, FAM6):
         for t in range(1, R):
             assert rec[f, t, 4] == (t / (R - 1)) ** fam[1]            # python float pow, simulation_evaluator.py:105
             assert rec[f, t, 5] == (t / (R - 1)) ** (1.1 * fam[1])    # :112
@@ -146,7 +153,7 @@ def test_tables_f32_folded_records(R):
     nbytes = nat.lib.at2_hb_tables_bytes(C.byref(plan), C.byref(cfg), 0)
     buf = np.zeros(nbytes // 4, np.float32)
     nat.check(nat.lib.at2_hb_tables_build(C.byref(plan), C.byref(cfg), 0, buf.ctypes.data))
-    F = len(FAM6)
+    F, slot = _slots(cfg)
     sgw = 12 if plan.n_ckpts <= 12 else 24
     rows = (R + 1) | 1
     rec = buf[:12 * F * rows].reshape(F, rows, 12)
@@ -154,7 +161,7 @@ def test_tables_f32_folded_records(R):
     pw = buf[12 * F * rows + sgw * (R + 1):].reshape(F, rows, 4)
     ckpos = {plan.ckpt_time[c] - 1 for c in range(plan.n_ckpts)}
     f32 = np.float32
-    for f, fam in enumerate(FAM6):
+    for f, fam in zip(slot, FAM6):
         for t in range(1, R):
             a, s = gp.gamma_shape_scale(t, R)
             d = a - 1.0 / 3.0
