@@ -219,7 +219,7 @@ def measured_traffic(key='dram_bytes_per_launch_avg'):
             with open(os.path.join(ROOT, 'profiles', f'{tag}_dram_traffic.json')) as f:
                 d = json.load(f)
             for k, v in d.items():
-                if k.startswith('hb_sim_kernel<float, 0, 1, 6') or (tag == 'r01' and k.startswith('hb_sim_kernel<float, 0, 0, 1')):
+                if k.startswith('hb_sim_kernel<float, 0, 1, 5') or k.startswith('hb_sim_kernel<float, 0, 1, 6') or (tag == 'r01' and k.startswith('hb_sim_kernel<float, 0, 0, 1')):
                     if v.get(key) is not None:
                         return v[key], f'profiles/{tag}_dram_traffic.json [{k}]'
         except Exception:  # noqa: BLE001
@@ -545,7 +545,7 @@ def main():
                     'note': 'full-simulation path; per step every rank uploads the constant tables from pinned memory and reads '
                             'its own OFE slice back, rank 0 also the density'},
             'gpu_launches': launches,
-            'roofline': {'kernel': 'hb_sim_kernel<float,PHILOX,HAS_SMOOTH,CK=6> (fused simulation + successive halving)',
+            'roofline': {'kernel': 'hb_sim_kernel<float,PHILOX,HAS_SMOOTH,CK=5> (fused simulation + successive halving)',
                          'bound': 'fp32', 'achieved': achieved_tflops, 'peak': fma_peak_tflops, 'unit': 'TFLOP/s',
                          'frac': achieved_tflops / fma_peak_tflops, 'traffic': traffic,
                          'traffic_note': f'DRAM bytes per launch from the committed ncu capture ({traffic_src}); the kernel has '

@@ -61,7 +61,7 @@ if os.path.exists(lcsv):
     lines.append('')
 # ---- full captures ----
 traffic = {}
-for rep in (f'{tag}_prof_bench.ncu-rep', f'{tag}_prof_hb_flat.ncu-rep', f'{tag}_prof_lazy.ncu-rep', f'{tag}_prof_knownfn.ncu-rep',
+for rep in (f'{tag}_prof_bench.ncu-rep', f'{tag}_prof_hb_flat.ncu-rep', f'{tag}_prof_lazy.ncu-rep', f'{tag}_prof_knownfn.ncu-rep', f'{tag}_prof_nnlookup.ncu-rep',
             f'{tag}_prof_tpe.ncu-rep'):
     path = os.path.join(out, rep)
     if not os.path.exists(path):
