@@ -127,14 +127,13 @@ def run_hyperband_repetitions(spec, n_reps, seed=0, rep_offset=0, device=None, d
     device = _cuda_device(device)
     if early_stop is None:
         early_stop = not details
-    if early_stop:
-        # arms are simulated only as far as the round that reads them needs; same streams, bit-identical outputs
-        outs = torch.ops.at2.hb_sim_early_stop(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes,
-                                               int(n_reps), int(rep_offset), int(seed), bool(details))
-        return dict(zip([k for k in ops.HB_OUTPUT_NAMES if k != 'ckpt_loss'], outs))
-    outs = torch.ops.at2.hb_sim_f32(spec.tables(device, torch.float32), spec.plan_bytes, spec.cfg_bytes, int(n_reps),
-                                    int(rep_offset), int(seed), bool(details))
-    return dict(zip(ops.HB_OUTPUT_NAMES, outs))
+    # straight to the library (ops.hb_sim_direct: the body of torch.ops.at2.hb_sim_f32 / hb_sim_early_stop without the
+    # dispatcher round trip); early stopping simulates arms only as far as the round that reads them needs - same streams,
+    # bit-identical outputs
+    outs = ops.hb_sim_direct(spec.tables(device, torch.float32), spec.plan, spec.cfg, int(n_reps), int(rep_offset), int(seed),
+                             bool(details), bool(early_stop))
+    names = [k for k in ops.HB_OUTPUT_NAMES if k != 'ckpt_loss'] if early_stop else ops.HB_OUTPUT_NAMES
+    return dict(zip(names, outs))
 
 
 def arm_families(spec, seed, rep_ids, arm_ids):

@@ -5,9 +5,13 @@ One process per GPU (torch.distributed, NCCL over NVLink); repetitions are indep
 all-gather of each rank's OFE slice.  RNG streams are keyed by the *global* repetition id, so the gathered vector is
 bit-identical for every world size.
 """
+import functools
+
 import numpy as np
 import torch
 import torch.distributed as dist
+
+from . import ops
 
 KERNEL_IDS = {'epanechnikov': 0, 'gaussian': 1}
 
@@ -41,6 +45,13 @@ def gather_slices(local, n_total, group=None):
         a, b = shard_range(n_total, r, world)
         parts.append(recv[r * width:r * width + (b - a)])
     return torch.cat(parts)
+
+
+@functools.lru_cache(maxsize=64)
+def _grid(start, end, grid_points):
+    g = np.linspace(start, end, grid_points)
+    g.setflags(write=False)
+    return g
 
 
 class FusedGather:
@@ -118,8 +129,8 @@ class FusedGather:
         lo, hi = shard_range(self.n_total, self.rank, self.world)
         buf, hdl, targets = self.bufs[self.turn], self.handles[self.turn], self.targets[self.turn]
         self.turn ^= 1
-        torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo, lo,
-                                    int(seed), buf, targets, lo, self.multicast, bool(early_stop))
+        ops.hb_sim_gather_direct(spec.tables(self.device, torch.float32), spec.plan, spec.cfg, hi - lo, lo, int(seed), buf,
+                                 targets, lo, self.multicast, bool(early_stop))
         hdl.barrier(channel=0)          # on the current stream: every rank's stores are in every buffer after it
         return buf
 
@@ -146,22 +157,21 @@ class FusedGather:
         self.turn ^= 1
         if sim_events is not None:
             sim_events[0].record(stream)
-        local = torch.ops.at2.hb_sim_gather(spec.tables(self.device, torch.float32), spec.plan_bytes, spec.cfg_bytes, hi - lo,
-                                            lo, int(seed), buf, targets, lo, self.multicast, bool(early_stop))[0]
+        local = ops.hb_sim_gather_direct(spec.tables(self.device, torch.float32), spec.plan, spec.cfg, hi - lo, lo, int(seed),
+                                         buf, targets, lo, self.multicast, bool(early_stop))[0]
         if sim_events is not None:
             sim_events[1].record(stream)
         # the kernel sums are taken over the launch's own (locally written) OFE output, not over the symmetric buffer
-        torch.ops.at2.kde_partial(local, float(start), float(end), int(grid_points), float(bandwidth), KERNEL_IDS[kernel], kbuf,
-                                  ktargets, self.multicast, self.rank * int(grid_points))
+        ops.kde_partial_direct(local, float(start), float(end), int(grid_points), float(bandwidth), KERNEL_IDS[kernel], kbuf,
+                               ktargets, self.multicast, self.rank * int(grid_points))
         hdl.barrier(channel=0)          # covers both scatters: they precede it in stream order on every rank
-        dens = torch.ops.at2.kde_combine(kbuf, self.world, int(grid_points), self.n_total, float(bandwidth), KERNEL_IDS[kernel])
+        dens = ops.kde_combine_direct(kbuf, self.world, int(grid_points), self.n_total, float(bandwidth), KERNEL_IDS[kernel])
         return buf, dens
 
 
 def density(ofes, start, end, bandwidth, grid_points=1000, kernel='epanechnikov'):
     """EPDF of a float32 CUDA vector on linspace(start, end, grid_points)."""
-    return torch.ops.at2.kde(ofes.contiguous(), float(start), float(end), int(grid_points), float(bandwidth),
-                             KERNEL_IDS[kernel])
+    return ops.kde_direct(ofes.contiguous(), float(start), float(end), int(grid_points), float(bandwidth), KERNEL_IDS[kernel])
 
 
 def summary_stats(ofes):
@@ -192,7 +202,7 @@ def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=100
         if fused.n_total != int(n_reps):
             raise ValueError(f'FusedGather was built for {fused.n_total} repetitions, not {n_reps}')
         ofes, dens = fused.run_epdf(spec, seed, start, end, bandwidth, grid_points, kernel, early_stop)
-        return {'ofes': ofes, 'density': dens, 'grid': np.linspace(start, end, grid_points)}
+        return {'ofes': ofes, 'density': dens, 'grid': _grid(start, end, grid_points)}
     lo, hi = shard_range(n_reps, rank, world)
     if runner is None:
         def runner(spec_, n, seed_, off, dev):
@@ -200,4 +210,4 @@ def run_epdf_ofe(spec, n_reps, seed=0, *, start, end, bandwidth, grid_points=100
     local = runner(spec, hi - lo, seed, lo, device) if hi > lo else torch.empty(0, device=device)
     ofes = gather_slices(local, n_reps, group)
     dens = density(ofes, start, end, bandwidth, grid_points, kernel)
-    return {'ofes': ofes, 'density': dens, 'grid': np.linspace(start, end, grid_points)}
+    return {'ofes': ofes, 'density': dens, 'grid': _grid(start, end, grid_points)}

@@ -51,22 +51,31 @@ def _outputs(plan, n_reps, device, dtype, details, ckpt_loss=True, dims=2):
 HB_OUTPUT_NAMES = ['ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors', 'ckpt_loss']
 
 
+def hb_sim_direct(tables: torch.Tensor, plan, cfg, n_reps: int, rep_offset: int, seed: int, details: bool,
+                  early_stop: bool) -> List[torch.Tensor]:
+    """The body of at2::hb_sim_f32 / at2::hb_sim_early_stop on the ctypes structs themselves: what the batched entry points
+    (autotune.b200.engine) call - no dispatcher round trip and no struct (de)serialisation, which is most of the host time
+    of a reference-sized job (7 000 repetitions are ~0.1 ms of kernel)."""
+    _require_cuda(tables, 'tables')
+    with torch.cuda.device(tables.device):
+        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=not early_stop,
+                                 dims=nat.lib.at2_func_dims(cfg.func))
+        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
+            fn = nat.lib.at2_hb_sim_early_stop_f32 if early_stop else nat.lib.at2_hb_sim_f32
+            nat.check(fn(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset, seed & 0xFFFFFFFFFFFFFFFF,
+                         C.byref(outs), _stream_ptr(tables.device)))
+    return tensors
+
+
 @torch.library.custom_op('at2::hb_sim_f32', mutates_args=(), device_types='cuda')
 def hb_sim_f32(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
                seed: int, details: bool) -> List[torch.Tensor]:
     """Fused Philox/Gamma simulation + successive halving for `n_reps` Hyperband repetitions (at2_hb_sim_f32)."""
-    _require_cuda(tables, 'tables')
-    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
-    with torch.cuda.device(tables.device):
-        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, dims=nat.lib.at2_func_dims(cfg.func))
-        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
-            nat.check(nat.lib.at2_hb_sim_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
-                                             seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
-    return tensors
+    return hb_sim_direct(tables, _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes), n_reps, rep_offset, seed,
+                         details, False)
 
 
-@torch.library.custom_op('at2::hb_sim_gather', mutates_args=('gathered',), device_types='cuda')
-def hb_sim_gather(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
+def hb_sim_gather_direct(tables: torch.Tensor, plan, cfg, n_reps: int, rep_offset: int,
                   seed: int, gathered: torch.Tensor, gather_ptrs: List[int], gather_base: int, multicast: bool = False,
                   early_stop: bool = False) -> List[torch.Tensor]:
     """at2::hb_sim_f32 (or, with early_stop, at2::hb_sim_early_stop) fused with the all-gather of the OFEs
@@ -75,7 +84,6 @@ def hb_sim_gather(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: tor
     multicast=True - through the one NVSwitch multicast address in `gather_ptrs` (multimem.st).  `gathered` is this rank's
     own buffer (declared mutated; it must be among the targets)."""
     _require_cuda(tables, 'tables')
-    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
     if not 1 <= len(gather_ptrs) <= nat.MAX_PEERS or (multicast and len(gather_ptrs) != 1):
         raise RuntimeError(f'between 1 and {nat.MAX_PEERS} gather buffers (exactly one multicast address)')
     if gathered.dtype != torch.float32 or gather_base < 0 or gather_base + n_reps > gathered.numel():
@@ -93,20 +101,22 @@ def hb_sim_gather(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: tor
     return tensors
 
 
+@torch.library.custom_op('at2::hb_sim_gather', mutates_args=('gathered',), device_types='cuda')
+def hb_sim_gather(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
+                  seed: int, gathered: torch.Tensor, gather_ptrs: List[int], gather_base: int, multicast: bool = False,
+                  early_stop: bool = False) -> List[torch.Tensor]:
+    """hb_sim_gather_direct as a custom op (struct arguments as CPU uint8 tensors)."""
+    return hb_sim_gather_direct(tables, _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes), n_reps, rep_offset,
+                                seed, gathered, gather_ptrs, gather_base, multicast, early_stop)
+
+
 @torch.library.custom_op('at2::hb_sim_early_stop', mutates_args=(), device_types='cuda')
 def hb_sim_early_stop(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, n_reps: int, rep_offset: int,
                       seed: int, details: bool) -> List[torch.Tensor]:
     """at2::hb_sim_f32 with early stopping (at2_hb_sim_early_stop_f32): identical outputs (minus ckpt_loss) at a fraction
     of the simulated epochs."""
-    _require_cuda(tables, 'tables')
-    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
-    with torch.cuda.device(tables.device):
-        outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details, ckpt_loss=False,
-                                 dims=nat.lib.at2_func_dims(cfg.func))
-        if n_reps > 0:   # an empty job is an empty result, as the reference's loop over range(0) would give
-            nat.check(nat.lib.at2_hb_sim_early_stop_f32(C.byref(plan), C.byref(cfg), tables.data_ptr(), n_reps, rep_offset,
-                                                        seed & 0xFFFFFFFFFFFFFFFF, C.byref(outs), _stream_ptr(tables.device)))
-    return tensors
+    return hb_sim_direct(tables, _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes), n_reps, rep_offset, seed,
+                         details, True)
 
 
 @hb_sim_f32.register_fake
@@ -150,25 +160,29 @@ def fma_peak_probe(sink: torch.Tensor, blocks: int, threads: int, iters: int, va
         nat.check(nat.lib.at2_fma_peak_probe(blocks, threads, iters, variant, sink.data_ptr(), _stream_ptr(sink.device)))
 
 
-@torch.library.custom_op('at2::kde', mutates_args=(), device_types='cuda')
-def kde(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int) -> torch.Tensor:
-    """Kernel density of the float32 samples `x` on linspace(start, end, grid_points) (at2_kde_f32);
-    kernel 0 = Epanechnikov (the reference's), 1 = Gaussian."""
+def kde_direct(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int) -> torch.Tensor:
+    """The body of at2::kde, called directly by autotune.b200.epdf.density (see hb_sim_direct)."""
     _require_cuda(x, 'x')
     if x.dtype != torch.float32 or x.dim() != 1 or not x.is_contiguous():
         raise RuntimeError('x must be a contiguous 1-D float32 tensor')
     n = x.numel()
     with torch.cuda.device(x.device):
-        ws_n = nat.lib.at2_kde_workspace_floats(n, grid_points)
-        ws = torch.empty(max(ws_n, 1), device=x.device, dtype=torch.float32)
+        ws_n = nat.lib.at2_kde_workspace_floats(n, grid_points)     # 0 unless the grid is wider than the accumulator array
+        ws = torch.empty(ws_n, device=x.device, dtype=torch.float32) if ws_n > 0 else None
         dens = torch.empty(grid_points, device=x.device, dtype=torch.float32)
         nat.check(nat.lib.at2_kde_f32(x.data_ptr(), n, start, end, grid_points, bandwidth, kernel, dens.data_ptr(),
-                                      ws.data_ptr(), ws_n, _stream_ptr(x.device)))
+                                      ws.data_ptr() if ws is not None else None, ws_n, _stream_ptr(x.device)))
     return dens
 
 
-@torch.library.custom_op('at2::kde_partial', mutates_args=('parts',), device_types='cuda')
-def kde_partial(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int,
+@torch.library.custom_op('at2::kde', mutates_args=(), device_types='cuda')
+def kde(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int) -> torch.Tensor:
+    """Kernel density of the float32 samples `x` on linspace(start, end, grid_points) (at2_kde_f32);
+    kernel 0 = Epanechnikov (the reference's), 1 = Gaussian."""
+    return kde_direct(x, start, end, grid_points, bandwidth, kernel)
+
+
+def kde_partial_direct(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int,
                 parts: torch.Tensor, target_ptrs: List[int], multicast: bool, slot_offset: int) -> None:
     """The sharded form of at2::kde (at2_kde_partial_f32): the UNNORMALISED float64 kernel sums of the samples `x` go to
     elements slot_offset .. slot_offset + grid_points - 1 of every buffer in `target_ptrs` (device addresses of the ranks'
@@ -184,14 +198,21 @@ def kde_partial(x: torch.Tensor, start: float, end: float, grid_points: int, ban
     n = x.numel()
     with torch.cuda.device(x.device):
         ws_n = nat.lib.at2_kde_workspace_floats(n, grid_points)
-        ws = torch.empty(max(ws_n, 1), device=x.device, dtype=torch.float32)
+        ws = torch.empty(ws_n, device=x.device, dtype=torch.float32) if ws_n > 0 else None
         ptrs = (C.c_void_p * len(target_ptrs))(*target_ptrs)
         nat.check(nat.lib.at2_kde_partial_f32(x.data_ptr(), n, start, end, grid_points, bandwidth, kernel, ptrs, len(target_ptrs),
-                                              int(multicast), slot_offset, ws.data_ptr(), ws_n, _stream_ptr(x.device)))
+                                              int(multicast), slot_offset, ws.data_ptr() if ws is not None else None, ws_n,
+                                              _stream_ptr(x.device)))
 
 
-@torch.library.custom_op('at2::kde_combine', mutates_args=(), device_types='cuda')
-def kde_combine(parts: torch.Tensor, n_parts: int, grid_points: int, n_total: int, bandwidth: float, kernel: int) -> torch.Tensor:
+@torch.library.custom_op('at2::kde_partial', mutates_args=('parts',), device_types='cuda')
+def kde_partial(x: torch.Tensor, start: float, end: float, grid_points: int, bandwidth: float, kernel: int,
+                parts: torch.Tensor, target_ptrs: List[int], multicast: bool, slot_offset: int) -> None:
+    """kde_partial_direct as a custom op."""
+    kde_partial_direct(x, start, end, grid_points, bandwidth, kernel, parts, target_ptrs, multicast, slot_offset)
+
+
+def kde_combine_direct(parts: torch.Tensor, n_parts: int, grid_points: int, n_total: int, bandwidth: float, kernel: int) -> torch.Tensor:
     """density = norm * (sum of the first n_parts slots of `parts`, in slot order) (at2_kde_combine_f64)."""
     _require_cuda(parts, 'parts')
     if parts.dtype != torch.float64 or not parts.is_contiguous() or parts.numel() < n_parts * grid_points:
@@ -201,6 +222,12 @@ def kde_combine(parts: torch.Tensor, n_parts: int, grid_points: int, n_total: in
         nat.check(nat.lib.at2_kde_combine_f64(parts.data_ptr(), n_parts, grid_points, n_total, bandwidth, kernel,
                                               dens.data_ptr(), _stream_ptr(parts.device)))
     return dens
+
+
+@torch.library.custom_op('at2::kde_combine', mutates_args=(), device_types='cuda')
+def kde_combine(parts: torch.Tensor, n_parts: int, grid_points: int, n_total: int, bandwidth: float, kernel: int) -> torch.Tensor:
+    """kde_combine_direct as a custom op."""
+    return kde_combine_direct(parts, n_parts, grid_points, n_total, bandwidth, kernel)
 
 
 def _opt_ptr(t):

@@ -182,13 +182,15 @@ double kde_norm(int kernel, long long n_total, double bandwidth) {
 
 int kde_launch(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
                const KdeOut& out, float* d_workspace, int64_t workspace_floats, const char* who, cudaStream_t st) {
-    AT2_REQUIRE(d_x && d_workspace, "%s: NULL pointer", who);
+    AT2_REQUIRE(d_x != nullptr, "%s: NULL pointer", who);
     AT2_REQUIRE(n > 0 && G >= 2, "%s: need n > 0 samples and G >= 2 grid points (got %lld, %d)", who, (long long)n, G);
     AT2_REQUIRE(bandwidth > 0, "%s: bandwidth must be positive", who);
     AT2_REQUIRE(kernel == AT2_KDE_EPANECHNIKOV || kernel == AT2_KDE_GAUSSIAN, "%s: unknown kernel %d", who, kernel);
     const int n_chunks = kde_chunks(n, G);
-    AT2_REQUIRE(workspace_floats >= (int64_t)n_chunks * G, "%s: workspace too small (%lld < %lld floats)", who,
-                (long long)workspace_floats, (long long)n_chunks * G);
+    // the per-chunk partial rows are only written by grids wider than the accumulator array (see kde_partial_kernel)
+    const bool needs_rows = (G + KDE_TILE_G - 1) / KDE_TILE_G > KDE_MAX_GTILES;
+    AT2_REQUIRE(!needs_rows || (d_workspace != nullptr && workspace_floats >= (int64_t)n_chunks * G),
+                "%s: workspace too small (%lld < %lld floats)", who, (long long)workspace_floats, (long long)n_chunks * G);
     // chunk length: a multiple of four samples, so that every chunk starts 16-byte aligned relative to d_x
     long long chunk_len = (n + n_chunks - 1) / n_chunks;
     chunk_len = (chunk_len + 3) / 4 * 4;
@@ -220,6 +222,7 @@ int kde_launch(const float* d_x, int64_t n, double start, double end, int32_t G,
 
 extern "C" int64_t at2_kde_workspace_floats(int64_t n, int32_t G) {
     if (n <= 0 || G <= 0) return 0;
+    if ((G + KDE_TILE_G - 1) / KDE_TILE_G <= KDE_MAX_GTILES) return 0;   // fixed-point accumulators inside the library
     return (int64_t)kde_chunks(n, G) * G;
 }
 

@@ -319,7 +319,9 @@ int at2_hb_knownfn_f64(const at2_plan* plan, const at2_domain* domain, const dou
 
 /* Density of the n samples d_x on the G-point grid linspace(start, end, G) with the given bandwidth:
  * replaces sklearn's KernelDensity(kernel='epanechnikov', bandwidth).fit(x) + exp(score_samples(grid))
- * (experiments/simulation_evaluation/plot_results.py:11-17).  d_workspace: at2_kde_workspace_floats(n, G) floats. */
+ * (experiments/simulation_evaluation/plot_results.py:11-17).  d_workspace: at2_kde_workspace_floats(n, G) floats - 0, and
+ * d_workspace may then be NULL, for grids of up to 16 384 points: the CTAs' partial sums are accumulated as 64-bit
+ * fixed-point integers in library-owned device memory (order-independent, so the density is deterministic). */
 int64_t at2_kde_workspace_floats(int64_t n, int32_t G);
 int at2_kde_f32(const float* d_x, int64_t n, double start, double end, int32_t G, double bandwidth, int32_t kernel,
                 float* d_density, float* d_workspace, int64_t workspace_floats, void* stream);
