@@ -1,7 +1,8 @@
 // (a)+(b) fused: Gamma-process trajectory simulation + Hyperband successive halving, one launch for all repetitions.
 //
-// Work decomposition (B200: 148 SMs, 4 SMSPs each, no HBM traffic to speak of - the kernel is issue/XU bound):
-//   * a CTA owns a *tile* of G consecutive repetitions; its G*A arm trajectories are spread flat over the CTA's lanes
+// Work decomposition (B200: 148 SMs, 4 SMSPs each, no HBM traffic to speak of - the kernel is bound by instruction issue,
+// its smoothed passes by shared-memory wavefronts):
+//   * a warp (or a team of warps) owns a *tile* of G consecutive repetitions; its G*A arm trajectories are spread flat over the lanes
 //     (one lane = one arm at a time) so lane occupancy does not depend on A being a multiple of 32;
 //   * every lane runs its own Philox4x32-10 stream -> Box-Muller -> Marsaglia-Tsang attempt loop.  A rejected attempt
 //     simply does not advance that lane's epoch, so lanes drift apart by a few epochs instead of the whole warp

@@ -34,8 +34,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
-// Completion counters of the launches in flight: the last CTA of a grid tile to finish does the fixed-order reduction of
-// that tile's partial sums itself (no second launch) and hands the counter back zeroed.  A launch owns one slot
+// Completion counters of the launches in flight: the last CTA of a grid tile to finish converts that tile's accumulated
+// sums itself (no second launch) and hands the counter back zeroed.  A launch owns one slot
 // (round-robin on the host; launches that overlap in time hold different slots).
 #define KDE_SLOTS 32
 #define KDE_MAX_GTILES 16

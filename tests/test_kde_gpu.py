@@ -55,5 +55,5 @@ def test_grid_shapes_and_errors():
         torch.ops.at2.kde(x, -4.0, 4.0, 1000, 0.0, 0)        # bandwidth must be positive
     with pytest.raises(RuntimeError):
         torch.ops.at2.kde(x.cpu(), -4.0, 4.0, 1000, 0.5, 0)  # no CPU fallback
-    # determinism: fixed-order reduction
+    # determinism: the partial sums are added as fixed-point integers (order-independent)
     assert torch.equal(torch.ops.at2.kde(x, -4.0, 4.0, 1000, 0.5, 0), torch.ops.at2.kde(x, -4.0, 4.0, 1000, 0.5, 0))
