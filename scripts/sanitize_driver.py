@@ -46,5 +46,11 @@ for mk, n_arms in ((mnist_domain_problem, 425), (cifar_domain_problem, 300)):
 print('ok knownfn', flush=True)
 density(torch.randn(5000, device='cuda'), -3.0, 3.0, 0.3, 1000)
 density(torch.randn(5000, device='cuda'), -3.0, 3.0, 0.3, 1000, kernel='gaussian')
+from autotune.b200 import ops  # noqa: E402
+for dt in (torch.float32, torch.float64):      # stand-alone halving step: every width class
+    lens = [1, 9, 32, 33, 128, 129, 256, 257, 700]
+    offs = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), device='cuda')
+    ops.segmented_topk(torch.randn(int(offs[-1]), device='cuda', dtype=dt), offs,
+                       torch.tensor([max(1, k // 3) for k in lens], dtype=torch.int32, device='cuda'), 700, False)
 torch.cuda.synchronize()
 print('sanitize driver done', flush=True)
