@@ -37,6 +37,7 @@ struct At2Debug {
     int hb_no_split, hb_equal_tiles, hb_no_tile_halving, hb_static_schedule, hb_singles;
     int force_gtab;                                           // constant tables from global memory on any plan
     int lazy_reps_per_tile;                                   // hb_lazy.cu tile width
+    int lazy_no_cache;                                        // hb_lazy.cu: redraw the arms every round (no set-up cache)
     int tpe_warps_per_cta;                                    // tpe_sim.cu
     int kf_warps_per_cta, kf_reps_per_tile;                   // nn_lookup.cu hb_knownfn_kernel
 };

@@ -31,7 +31,7 @@ extern "C" int at2_debug_option(const char* name, int32_t value) {
         {"hb_warps_per_cta", &g_debug.hb_warps_per_cta}, {"hb_no_split", &g_debug.hb_no_split},
         {"hb_equal_tiles", &g_debug.hb_equal_tiles}, {"hb_no_tile_halving", &g_debug.hb_no_tile_halving},
         {"hb_static_schedule", &g_debug.hb_static_schedule}, {"hb_singles", &g_debug.hb_singles},
-        {"force_gtab", &g_debug.force_gtab}, {"lazy_reps_per_tile", &g_debug.lazy_reps_per_tile},
+        {"force_gtab", &g_debug.force_gtab}, {"lazy_reps_per_tile", &g_debug.lazy_reps_per_tile}, {"lazy_no_cache", &g_debug.lazy_no_cache},
         {"tpe_warps_per_cta", &g_debug.tpe_warps_per_cta}, {"kf_warps_per_cta", &g_debug.kf_warps_per_cta},
         {"kf_reps_per_tile", &g_debug.kf_reps_per_tile}};
     for (const auto& e : table)

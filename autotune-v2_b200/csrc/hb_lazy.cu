@@ -16,6 +16,7 @@
 #include <cmath>
 #include <climits>
 #include <cstdlib>
+#include <mutex>
 
 #include "at2_common.cuh"
 #include "halving.cuh"
@@ -34,6 +35,12 @@ struct LazyParams {
     int km_a, km_b;   // entries of the two survivor-id buffers of a repetition (see the kernel)
     int cur_cap;      // floats in a warp's loss buffer (>= widest bracket)
     int mixed;        // the families hold both raw and smoothed ones
+    // set-up cache (global scratch, one slab per warp of the grid): start value, target and family of every arm of the tile
+    // at hand, written when a bracket's first round draws the arm, read by the later rounds that simulate it again
+    float* ws_f1;
+    float* ws_fn;
+    unsigned char* ws_fam;
+    long long ws_stride;   // entries per warp (>= G * n_arms)
     float* ofe;
     int* ofe_arm;
     float* best_xy;
@@ -48,7 +55,9 @@ struct LazyParams {
 
 __host__ __device__ inline size_t lazy_keys_offset(int cur_cap, int G) { return ((size_t)cur_cap * 4 + (size_t)G * 12 + 7) & ~(size_t)7; }
 
-template <bool HAS_SMOOTH, bool GTAB>
+// CACHE: the launch has a slab of the set-up cache per warp (see LazyParams); without one (allocation refused, or the
+// debug option lazy_no_cache) every round redraws its arms - same results, ~10 % more work on the six-family job.
+template <bool HAS_SMOOTH, bool GTAB, bool CACHE>
 __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__ LazyParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = p.plan.R, A = p.plan.n_arms, C = p.plan.n_ckpts, F = p.sp.F, G = p.G;
@@ -90,6 +99,26 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     const int kms = p.km_a + p.km_b;
     auto idbuf = [&](int g, int fl) { return ids + g * kms + (fl ? 0 : p.km_a); };   // fl = 1: buffer A
     const bool desc = p.descending != 0;
+    constexpr bool cache = CACHE;
+    const size_t wbase = (size_t)((long long)blockIdx.x * nwarps + warp) * (size_t)p.ws_stride;
+    // an arm's start value (before the read-at-R shortcut), target and family: drawn from its stream + base function, or -
+    // in the rounds after the one that drew it - read back from the warp's slab of the set-up cache
+    auto draw_item = [&](bool active, int g, int arm, unsigned long long gid, bool store, float& f1, float& fn, int& fam_idx) {
+        const ArmDraw d = draw_arm(p.sp, gid, arm);
+        const Fam<float> fam = p.fam[d.fam];
+        const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
+        fn = f - fam.s1;
+        f1 = (f + p.sp.noise * d.z) - fam.s0;
+        fam_idx = d.fam;
+        if (store && active) {
+            const size_t o = wbase + (size_t)g * A + arm;
+            __stcg(p.ws_f1 + o, f1), __stcg(p.ws_fn + o, fn), p.ws_fam[o] = (unsigned char)d.fam;
+        }
+    };
+    auto load_item = [&](bool active, int g, int arm, float& f1, float& fn, int& fam_idx) {
+        const size_t o = wbase + (size_t)(active ? g : 0) * A + (active ? arm : 0);
+        f1 = __ldcg(p.ws_f1 + o), fn = __ldcg(p.ws_fn + o), fam_idx = active ? (int)__ldcg(p.ws_fam + o) : 0;
+    };
 
     for (long long tile = (long long)blockIdx.x * nwarps + warp; tile < p.n_tiles; tile += (long long)gridDim.x * nwarps) {
         const long long rep0 = tile * G;
@@ -138,7 +167,17 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                             const int gl = act ? div_n(q) : 0, j = act ? q - gl * n_cur : 0, g = g0 + gl;
                             const int arm = first_round ? first + j : (int)idbuf(g, flip)[j];
                             const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
-                            const bool sm = act && p.fam[arm_family(p.sp, gid, arm)].smooth != 0;
+                            int fam_idx;
+                            if (cache) {        // the whole set-up happens here (first round) or comes from the cache
+                                float f1c, fnc;
+                                if (first_round)
+                                    draw_item(act, g, arm, gid, true, f1c, fnc, fam_idx);
+                                else
+                                    load_item(act, g, arm, f1c, fnc, fam_idx);
+                            } else {
+                                fam_idx = arm_family(p.sp, gid, arm);
+                            }
+                            const bool sm = act && p.fam[fam_idx].smooth != 0;
                             const unsigned m_raw = __ballot_sync(0xffffffffu, act && !sm), m_sm = __ballot_sync(0xffffffffu, sm);
                             const unsigned below = (1u << lane) - 1u;
                             if (act) order[sm ? cap - 1 - (n_sm + __popc(m_sm & below)) : n_raw + __popc(m_raw & below)] = (unsigned short)q;
@@ -154,12 +193,16 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                         const int gl = div_n(q), j = q - gl * n_cur, g = g0 + gl;
                         const int arm = first_round ? first + j : (int)idbuf(g, flip)[j];
                         const unsigned long long gid = (unsigned long long)(p.rep_offset + rep0 + g) * (unsigned long long)A + arm;
-                        const ArmDraw d = draw_arm(p.sp, gid, arm);
-                        const Fam<float> fam = p.fam[d.fam];
-                        const float f = base_function(p.sp.func, d.x, d.y, d.x2, d.y2);
-                        const float fn = f - fam.s1;
+                        float f1d, fn;
+                        int fam_idx;
+                        if (cache && (split || !first_round)) {     // first round + split: the listing pass above wrote the slab
+                            load_item(active, g, arm, f1d, fn, fam_idx);
+                        } else {
+                            draw_item(active, g, arm, gid, cache, f1d, fn, fam_idx);
+                        }
+                        const Fam<float> fam = p.fam[fam_idx];
                         const bool smooth = HAS_SMOOTH && fam.smooth != 0;
-                        const float f1 = (raw_at_target && !smooth) ? fn : (f + p.sp.noise * d.z) - fam.s0;
+                        const float f1 = (raw_at_target && !smooth) ? fn : f1d;
                         float* dst = cur + q;
                         if (!HAS_SMOOTH || (split && base + 32 <= n_raw))
                             philox_trajectory<float, false, 1, true, GTAB>(tb, active, false, f1, fn, fam.up, fam.pw_off, gid,
@@ -257,19 +300,77 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
     }
 }
 
+// Stream-ordered scratch for the set-up cache: a pool of the library's own per device that keeps what it has handed out
+// (release threshold = everything), so a launch's cudaMallocFromPoolAsync / cudaFreeAsync pair costs microseconds after the
+// first call and launches on different streams never share a slab.
+static void* lazy_scratch_alloc(size_t bytes, cudaStream_t st) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (pools[dev] == nullptr) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pools[dev] = pool;
+        }
+    }
+    void* ptr = nullptr;
+    if (cudaMallocFromPoolAsync(&ptr, bytes, pools[dev], st) != cudaSuccess) {
+        cudaGetLastError();      // no scratch: the kernel redraws the arms instead (same results)
+        return nullptr;
+    }
+    return ptr;
+}
+
 template <bool HS, bool GTAB = false>
 int launch_lazy(const LazyParams& p, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = hb_lazy_kernel<HS, GTAB>;
+    auto kern = hb_lazy_kernel<HS, GTAB, true>;
+    auto kern_nc = hb_lazy_kernel<HS, GTAB, false>;
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AT2_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern_nc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AT2_CUDA_CHECK(cudaFuncSetAttribute(kern_nc, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // persistent grid: never more CTAs than are resident at once (registers can bind before shared memory does)
     int by_regs = 0, dev = 0, sms = 0;
     if (at2_resident_by_regs(kern, block, &by_regs) != AT2_OK) return AT2_ECUDA;
     AT2_CUDA_CHECK(cudaGetDevice(&dev));
     AT2_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if ((long long)by_regs * sms < grid) grid = by_regs * sms;
-    kern<<<grid, block, smem, st>>>(p);
-    AT2_CUDA_CHECK(cudaGetLastError());
+    // set-up cache: {f1, fn} as floats + the family as a byte per (repetition of the tile, arm), one slab per warp of the grid
+    LazyParams q = p;
+    void* ws = nullptr;
+    int rounds_max = 0;
+    for (int b = 0; b < p.plan.n_brackets; ++b)
+        rounds_max = max(rounds_max, p.plan.bracket_first_round[b + 1] - p.plan.bracket_first_round[b]);
+    if (rounds_max > 1 && !at2_debug().lazy_no_cache) {
+        const long long warps = (long long)grid * (block / 32);
+        const long long stride = (((long long)p.G * p.plan.n_arms) + 15) & ~15ll;
+        ws = lazy_scratch_alloc((size_t)(warps * stride) * 9, st);
+        if (ws != nullptr) {
+            q.ws_stride = stride;
+            q.ws_f1 = reinterpret_cast<float*>(ws);
+            q.ws_fn = q.ws_f1 + warps * stride;
+            q.ws_fam = reinterpret_cast<unsigned char*>(q.ws_fn + warps * stride);
+        }
+    }
+    if (ws != nullptr)
+        kern<<<grid, block, smem, st>>>(q);
+    else
+        kern_nc<<<grid, block, smem, st>>>(q);
+    const cudaError_t launch_rc = cudaGetLastError();
+    if (ws != nullptr) cudaFreeAsync(ws, st);     // stream-ordered: after the kernel
+    AT2_CUDA_CHECK(launch_rc);
     at2_count_launch(1);
     return AT2_OK;
 }

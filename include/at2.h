@@ -181,7 +181,10 @@ int at2_hb_sim_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const
  * its first evaluate(), benchmarks/opt_function_simulation_problem.py:67-76, but only ever reads the checkpoints - SURVEY
  * D5), and a raw arm read at R is its target f_n without any simulation (core/simulation_evaluator.py:105-107,113-115).
  * Streams and arithmetic are those of at2_hb_sim_f32, so every output is bit-identical to it; out->d_ckpt_loss must be NULL
- * (the losses of unread checkpoints are never computed).  The _gather variant adds the fused all-gather of the OFEs. */
+ * (the losses of unread checkpoints are never computed).  The _gather variant adds the fused all-gather of the OFEs.
+ * The launch takes a few MB to ~120 MB of stream-ordered scratch (9 bytes per arm of the tiles in flight: the arms' start
+ * value, target and family, read back by later rounds) from a pool the library keeps; if the allocation is refused the
+ * kernel redraws the arms every round instead - the same results, a few percent slower. */
 int at2_hb_sim_early_stop_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
                               int64_t rep_offset, uint64_t seed, const at2_hb_outputs* out, void* stream);
 int at2_hb_sim_early_stop_gather_f32(const at2_plan* plan, const at2_sim_config* cfg, const void* d_tables, int64_t n_reps,
