@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(256, 3) hb_lazy_kernel(const __grid_constant__
                                 float f1c, fnc;
                                 if (first_round)
                                     draw_item(act, g, arm, gid, true, f1c, fnc, fam_idx);
-                                else
-                                    load_item(act, g, arm, f1c, fnc, fam_idx);
+                                else      // the list only needs the family
+                                    fam_idx = act ? (int)__ldcg(p.ws_fam + wbase + (size_t)g * A + arm) : 0;
                             } else {
                                 fam_idx = arm_family(p.sp, gid, arm);
                             }
