@@ -717,6 +717,7 @@ extern "C" int at2_tpe_sim_f32(const at2_plan* plan, const at2_sim_config* cfg, 
     cudaStream_t st = (cudaStream_t)stream;
     if (!has_smooth) return launch_tpe<false, 1>(p, (int)grid, nwarps * 32, smem, st);
     if (C <= 4) return launch_tpe<true, 4>(p, (int)grid, nwarps * 32, smem, st);
+    if (C == 5) return launch_tpe<true, 5>(p, (int)grid, nwarps * 32, smem, st);   // R = 81, eta = 3: scalar fifth weight (sim_core.cuh)
     if (C <= 8) return launch_tpe<true, 8>(p, (int)grid, nwarps * 32, smem, st);
     return launch_tpe<true, 16>(p, (int)grid, nwarps * 32, smem, st);
 }
