@@ -132,12 +132,13 @@ int segmented_topk(const T* d_losses, const int64_t* d_seg_offsets, const int32_
     const long long cap = (long long)sms * 8;
     if (grid > cap) grid = cap;
     kern<<<(int)grid, warps * 32, smem, st>>>(p);
-    AT2_CUDA_CHECK(cudaGetLastError());
-    at2_count_launch(1);
+    cudaError_t rc = cudaGetLastError();
     int flag = 0;
-    AT2_CUDA_CHECK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    AT2_CUDA_CHECK(cudaStreamSynchronize(st));
-    AT2_CUDA_CHECK(cudaFreeAsync(d_flag, st));
+    if (rc == cudaSuccess) rc = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (rc == cudaSuccess) rc = cudaStreamSynchronize(st);
+    cudaFreeAsync(d_flag, st);                 // on every path: the flag is this call's own allocation
+    AT2_CUDA_CHECK(rc);
+    at2_count_launch(1);
     AT2_REQUIRE(flag == 0, "%s: a segment is longer than max_seg_len = %d", who, max_seg_len);
     return AT2_OK;
 }

@@ -12,7 +12,7 @@ mkdir -p $out
 cmd="python bench.py --steps 6 --warmup 3 --no-cpu-baseline"
 $cmd > $out/${tag}_plain_bench.log 2>&1 || { echo "plain bench failed"; tail -5 $out/${tag}_plain_bench.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'hb_sim_kernel|kde_partial_kernel|kde_finish_kernel' -s 6 -c 6 -f \
+ncu --set full --clock-control none --import-source on -k regex:'hb_sim_kernel|kde_partial_kernel|kde_finish_kernel' -s 6 -c 2 -f \
     -o $out/${tag}_prof_bench $cmd > $out/${tag}_ncu_full.log 2>&1
 # SASS-counted FP32 work of one simulation launch (not part of --set full)
 ncu --clock-control none -k regex:hb_sim_kernel -s 6 -c 1 --csv --log-file $out/${tag}_sass_flops.csv --metrics \
@@ -26,10 +26,14 @@ python scripts/lazy_timing.py 100000 fam6 > $out/${tag}_plain_lazy.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:hb_lazy_kernel -s 60 -c 1 -f -o $out/${tag}_prof_lazy \
     python scripts/lazy_timing.py 100000 fam6 > $out/${tag}_ncu_lazy.log 2>&1
 python scripts/knownfn_timing.py 10000 > $out/${tag}_plain_knownfn.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'hb_knownfn_kernel|nn_lookup_kernel' -s 4 -c 3 -f -o $out/${tag}_prof_knownfn \
+ncu --set full --clock-control none --import-source on -k regex:'hb_knownfn_kernel' -s 4 -c 1 -f -o $out/${tag}_prof_knownfn \
     python scripts/knownfn_timing.py 10000 > $out/${tag}_ncu_knownfn.log 2>&1
 python scripts/quick_timing.py > $out/${tag}_plain_quick.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:hb_sim_kernel -s 35 -c 1 -f -o $out/${tag}_prof_hb_flat \
     python scripts/quick_timing.py > $out/${tag}_ncu_quick.log 2>&1
 tail -2 $out/${tag}_plain_bench.log | cut -c1-400
 ls -la $out | grep ${tag}_
+# the stand-alone nearest-recorded-arm scan (its launches come after the Hyperband ones in the same script)
+ncu --set full --clock-control none --import-source on -k regex:nn_lookup_kernel -s 2 -c 1 -f -o $out/${tag}_prof_nnlookup \
+    python scripts/knownfn_timing.py 10000 > $out/${tag}_ncu_nnlookup.log 2>&1
+du -sh $out
