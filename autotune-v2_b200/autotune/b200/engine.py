@@ -315,8 +315,8 @@ def run_optimiser_repetitions(spec, n_reps, tpe, seed=0, rep_offset=0, device=No
     `spec` (stand-alone TPE / random search use single_round_plan)."""
     device = _cuda_device(device)
     plan = spec.plan if plan is None else plan
-    outs = torch.ops.at2.tpe_sim(spec.tables(device, torch.float32, plan), ops.struct_tensor(plan), spec.cfg_bytes,
-                                 ops.struct_tensor(tpe), int(n_reps), int(rep_offset), int(seed), bool(details))
+    outs = ops.tpe_sim_direct(spec.tables(device, torch.float32, plan), plan, spec.cfg, tpe, int(n_reps), int(rep_offset),
+                              int(seed), bool(details))
     return dict(zip(ops.HB_OUTPUT_NAMES + ['arm_xy', 'obs_loss', 'n_injected'] if details else ops.HB_OUTPUT_NAMES, outs))
 
 

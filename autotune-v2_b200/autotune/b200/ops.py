@@ -308,16 +308,13 @@ def hb_knownfn(plan_bytes: torch.Tensor, domain_bytes: torch.Tensor, db: torch.T
     return [o[k] for k in KF_OUTPUT_NAMES if k in o]
 
 
-@torch.library.custom_op('at2::tpe_sim', mutates_args=(), device_types='cuda')
-def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, tpe_bytes: torch.Tensor, n_reps: int,
-            rep_offset: int, seed: int, details: bool) -> List[torch.Tensor]:
+def tpe_sim_direct(tables: torch.Tensor, plan, cfg, tpe, n_reps: int, rep_offset: int, seed: int,
+                   details: bool) -> List[torch.Tensor]:
     """Hyperband-TPE hybrids / stand-alone TPE / random search on the simulation problem (at2_tpe_sim_f32).
     Returns the at2::hb_sim_f32 outputs followed, when `details`, by arm_xy [n_reps, n_arms, 2], obs_loss [n_reps, n_arms]
     (the loss the TPE phase observed for an arm; NaN for arms that were not observed) and n_injected [n_reps, n_brackets]
     (evaluations of earlier brackets transferred into each bracket's TPE run)."""
     _require_cuda(tables, 'tables')
-    plan, cfg = _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes)
-    tpe = _struct(nat.TpeConfig, tpe_bytes)
     with torch.cuda.device(tables.device):
         outs, tensors = _outputs(plan, n_reps, tables.device, torch.float32, details)
         arm_xy = torch.empty(n_reps, plan.n_arms, 2, device=tables.device, dtype=torch.float32) if details else None
@@ -329,6 +326,14 @@ def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Ten
                                               arm_xy.data_ptr() if details else None, obs.data_ptr() if details else None,
                                               inj.data_ptr() if details else None, _stream_ptr(tables.device)))
     return tensors + ([arm_xy, obs, inj] if details else [])
+
+
+@torch.library.custom_op('at2::tpe_sim', mutates_args=(), device_types='cuda')
+def tpe_sim(tables: torch.Tensor, plan_bytes: torch.Tensor, cfg_bytes: torch.Tensor, tpe_bytes: torch.Tensor, n_reps: int,
+            rep_offset: int, seed: int, details: bool) -> List[torch.Tensor]:
+    """tpe_sim_direct as a custom op (struct arguments as CPU uint8 tensors)."""
+    return tpe_sim_direct(tables, _struct(nat.Plan, plan_bytes), _struct(nat.SimConfig, cfg_bytes),
+                          _struct(nat.TpeConfig, tpe_bytes), n_reps, rep_offset, seed, details)
 
 
 @torch.library.custom_op('at2::tpe_score', mutates_args=(), device_types='cuda')
