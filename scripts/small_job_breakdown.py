@@ -1,6 +1,5 @@
 """Development aid: where the host time of a reference-sized EPDF-OFE job (7 000 repetitions) goes.
 usage: python scripts/small_job_breakdown.py"""
-import ctypes as C
 import os
 import sys
 import time
@@ -8,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'autotune-v2_b200'))
 import torch  # noqa: E402
 
-from autotune.b200 import _native as nat, ops  # noqa: E402
+from autotune.b200 import ops  # noqa: E402
 from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions  # noqa: E402
 from autotune.b200.epdf import density, run_epdf_ofe  # noqa: E402
 
