@@ -269,6 +269,28 @@ def test_early_stopping_tile_widths_do_not_change_outputs(tile):
             assert torch.equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize('tile', [0, 5, 32])
+def test_early_stopping_setup_cache_does_not_change_outputs(tile):
+    """The early-stopping kernel draws an arm (hyperparameters, family, initial noise, base function) once per bracket and
+    reads its start value, target and family back from a per-warp slab of scratch in the later rounds; without the slab
+    (debug option lazy_no_cache, or a refused allocation) it redraws them every round.  Same streams, same bits - with the
+    raw-first lists (mixed families), without them, and on the 4-D extension whose draw has two more coordinates."""
+    from autotune.b200._native import debug_options
+    from autotune.b200.engine import HyperbandSimSpec, run_hyperband_repetitions
+    for func, fams, R, eta, noise, sched, n in (('rastrigin', FAM6, 81, 3, 10, 'uniform', 1500), ('branin', FLAT, 81, 3, 0, 'uniform', 700),
+                                                ('egg', FAM6[:3], 243, 3, 10, 'round-robin', 90), ('egg4', FAM6[:2], 27, 3, 5, 'uniform', 400),
+                                                ('rastrigin', FAM6, 729, 3, 10, 'uniform', 6)):
+        spec = HyperbandSimSpec(func, fams, R, eta, noise, sched, 'min')
+        with debug_options(lazy_reps_per_tile=tile):
+            cached = run_hyperband_repetitions(spec, n, seed=31, rep_offset=7, details=True, early_stop=True)
+        with debug_options(lazy_reps_per_tile=tile, lazy_no_cache=1):
+            redrawn = run_hyperband_repetitions(spec, n, seed=31, rep_offset=7, details=True, early_stop=True)
+        for k in ('ofe', 'ofe_arm', 'best_xy', 'round_best', 'round_best_arm', 'survivors'):
+            assert torch.equal(cached[k], redrawn[k]), (func, R, k)
+    full = run_hyperband_repetitions(spec, n, seed=31, rep_offset=7, details=True, early_stop=False)
+    assert torch.equal(full['ofe'], cached['ofe']) and torch.equal(full['survivors'], cached['survivors'])
+
+
 def test_egg4_extension_flat_family_ofe_is_the_function_value():
     """4-D Egg-holder of BASELINE.json config 5 - an EXTENSION with no reference equivalent, defined in
     include/at2.h and oracle/opt_functions.egg4.  With the flat family (no noise, no shifts) every loss of an arm equals
