@@ -205,3 +205,29 @@ def test_history_evaluators_carry_the_arms_real_family():
                 assert abs(gap - ev.end_shift) < 1e-2, (i, gap, ev.end_shift)
         if isinstance(opt, TpeOptimiser):
             assert len(distinct) > 1          # 30 random arms: several families
+
+
+@pytest.mark.parametrize('R', [81, 9, 3])
+def test_device_gamma_draws_match_the_gamma_law_at_a_million_samples(R):
+    """High-power check of the Gamma sampler itself (Philox words -> Box-Muller -> Marsaglia-Tsang with the 16 + 16 bit accept
+    uniform): the first step of 10^6 raw trajectories with f_1 = 0, f_n = -200, ml_agg = 1.5, up_spik = 15 and a steep time
+    schedule (P = P11 = 0 at t = 1) is  -3 (g - 2)  for g > 2 and  15 / (1 + g)  for g < 2 (simulation_evaluator.py:102-115), so
+    the draw g can be read back from the value.  One-sample KS against Gamma(shape(t=1), scale(t=1)) of :36-42: at n = 10^6 a
+    deviation of 2e-3 in the CDF - e.g. a biased acceptance test - would be rejected."""
+    from scipy import stats
+
+    from autotune.b200.engine import HyperbandSimSpec
+    from autotune.b200.trajectories import simulate_arms
+    from oracle import gamma_process as gp
+    n = 1000000
+    spec = HyperbandSimSpec('branin', [(1.5, 40, 15, False, 0, 0)], R, 3, 0)
+    raw = simulate_arms(spec, np.zeros(n, np.float32), np.full(n, -200.0, np.float32), np.zeros(n, np.int32),
+                        np.arange(n, dtype=np.int64) + 12345, seed=99 + R)
+    v = raw[:, 1].double().cpu().numpy()
+    g = np.where(v < 0, 2.0 - v / 3.0, 15.0 / np.maximum(v, 1e-30) - 1.0)
+    a, s = gp.gamma_shape_scale(1, R)
+    res = stats.kstest(g, stats.gamma(a, scale=s).cdf)
+    print(f'R={R}: shape {a:.4f} scale {s:.4f}: KS D = {res.statistic:.2e} (p = {res.pvalue:.3f}) over {n} device draws')
+    assert res.statistic < 2.0e-3, (R, a, s, res, g.mean(), a * s)
+    assert abs(g.mean() - a * s) < 5 * np.sqrt(a) * s / np.sqrt(n)          # 5 sigma on the mean
+    assert abs((g > 2).mean() - stats.gamma(a, scale=s).sf(2.0)) < 2.5e-3       # share of down steps
