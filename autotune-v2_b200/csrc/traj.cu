@@ -30,10 +30,10 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
         int t = 1;
         uint32_t ctr = 0;
         const uint32_t g_lo = (uint32_t)gid, g_hi = (uint32_t)(gid >> 32);
-        // the word stream of sim_core.cuh: three blocks feed four attempt pairs
-        auto pair = [&](uint32_t wa, uint32_t wb, uint32_t wu) {
+        // the word stream of sim_core.cuh: one block feeds two attempt pairs
+        auto pair = [&](uint32_t wa, uint32_t wb) {
             float xs[2], ku[2];
-            box_muller_pair(wa, wb, wu, xs[0], xs[1], ku[0], ku[1]);
+            box_muller_pair(wa, wb, xs[0], xs[1], ku[0], ku[1]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (t >= R) break;
@@ -49,13 +49,9 @@ __global__ void __launch_bounds__(128) traj_kernel(const float* __restrict__ tab
         };
         while (t < R) {
             const At2U4 A4 = at2_philox10(At2U4{ctr, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
-            const At2U4 B4 = at2_philox10(At2U4{ctr + 1, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
-            const At2U4 C4 = at2_philox10(At2U4{ctr + 2, g_lo, g_hi, AT2_STREAM_TRAJ}, key0, key1);
-            ctr += 3;
-            pair(A4.x, A4.y, A4.z);
-            pair(A4.w, B4.x, B4.y);
-            pair(B4.z, B4.w, C4.x);
-            pair(C4.y, C4.z, C4.w);
+            ++ctr;
+            pair(A4.x, A4.y);
+            pair(A4.z, A4.w);
         }
     }
 }
