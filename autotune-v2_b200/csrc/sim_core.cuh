@@ -167,12 +167,17 @@ __device__ __noinline__ ArmDraw draw_arm(const ArmSpace& sp, unsigned long long 
     d.fam = sp.scheduler == AT2_SCHED_UNIFORM ? (int)__umulhi(r.z, (uint32_t)sp.F) : arm % sp.F;
     const float u1 = fmaf((float)(r.w >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);
     d.z = d.x2 = d.y2 = 0.0f;
-    // the second block feeds the initial noise and the extra coordinates only: nothing reads it on a noise-free 2-D problem
-    if (sp.noise != 0.0f || sp.func == AT2_FUNC_EGG4) {
-        const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
+    if (sp.noise != 0.0f) {
         // Box-Muller with the approximate MUFU forms (relative error ~1e-6, far below the FP32 tolerance tier; the full and
-        // the early-stopping kernels share this function, so they stay bit-identical to each other)
-        d.z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) * fast_cos((float)(r2.x >> 8) * 3.7450703e-7f);   // 2 pi / 2^24
+        // the early-stopping kernels share this function, so they stay bit-identical to each other).  The angle's leading
+        // 24 bits are the low bytes of the x, u1 and y words - bits their own conversions (>> 8) never look at - so a noisy
+        // 2-D problem draws an arm from ONE Philox block.  (The fourth byte repeats x's: 2^-24 of a turn, immaterial.)
+        const uint32_t ang = __byte_perm(__byte_perm(r.x, r.y, 0x0040), r.w, 0x0410);   // bytes (x.0, w.0, y.0, x.0), MSB first
+        d.z = fast_sqrt(-1.3862943611198906f * fast_lg2(u1)) * fast_cos((float)ang * 1.4629180792671596e-9f);   // 2 pi / 2^32
+    }
+    // the second block feeds the extra coordinates of the 4-D extension only
+    if (sp.func == AT2_FUNC_EGG4) {
+        const At2U4 r2 = at2_philox10(At2U4{1u, (uint32_t)gid, (uint32_t)(gid >> 32), AT2_STREAM_ARM}, sp.key0, sp.key1);
         d.x2 = fmaf((float)(r2.y >> 8) * 5.9604644775390625e-8f, sp.x_rng, sp.x_min);
         d.y2 = fmaf((float)(r2.z >> 8) * 5.9604644775390625e-8f, sp.y_rng, sp.y_min);
     }
