@@ -231,3 +231,29 @@ def test_device_gamma_draws_match_the_gamma_law_at_a_million_samples(R):
     assert res.statistic < 2.0e-3, (R, a, s, res, g.mean(), a * s)
     assert abs(g.mean() - a * s) < 5 * np.sqrt(a) * s / np.sqrt(n)          # 5 sigma on the mean
     assert abs((g > 2).mean() - stats.gamma(a, scale=s).sf(2.0)) < 2.5e-3       # share of down steps
+
+
+def test_initial_noise_is_standard_normal_and_independent_of_the_hyperparameters():
+    """An arm's initial noise z (benchmarks/opt_function_problem.py:138: f_1 = f + init_noise * N(0, 1)) is drawn from the same
+    Philox block as its hyperparameters - its Box-Muller angle out of the low bytes the x / y / radius conversions never look
+    at.  Read back from the first checkpoint of raw arms (f_1 - f + start_shift = init_noise * z): ~10^6 values, one-sample KS
+    against N(0, 1), and no correlation with x, y or the radius' own uniform."""
+    from scipy import stats
+
+    from autotune.b200.engine import HyperbandSimSpec, run_optimiser_repetitions, tpe_config
+    from autotune.benchmarks.opt_function_problem import NOISE_FREE_FUNCTIONS
+    noise, s0 = 10.0, 25.0
+    spec = HyperbandSimSpec('branin', [(1.5, 10, 15, False, s0, 200)], 81, 3, noise)
+    out = run_optimiser_repetitions(spec, 9000, tpe_config(False), seed=77, details=True)      # 9000 x 117 arms
+    xy = out['arm_xy'].double().cpu().numpy().reshape(-1, 2)
+    f1 = out['ckpt_loss'][:, :, 0].double().cpu().numpy().reshape(-1)
+    f = np.vectorize(NOISE_FREE_FUNCTIONS['branin'])(xy[:, 0], xy[:, 1])
+    z = (f1 - f + s0) / noise
+    assert z.size >= 1000000
+    # f_1 is a float32 of magnitude up to ~300: z is resolved to ~3e-6
+    res = stats.kstest(z, 'norm')
+    print(f'initial noise: n = {z.size}, mean {z.mean():.2e}, std {z.std():.5f}, KS D = {res.statistic:.2e} (p = {res.pvalue:.3f})')
+    assert res.statistic < 2.0e-3, res
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1.0) < 5e-3
+    for other in (xy[:, 0], xy[:, 1], np.abs(z) * np.sign(xy[:, 0] - 2.5)):
+        assert abs(np.corrcoef(z, other)[0, 1]) < 5e-3
