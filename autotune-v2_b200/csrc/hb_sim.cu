@@ -100,7 +100,7 @@ static std::atomic<unsigned> g_launch_seq{0};   // one sequence for every kernel
 #define AT2_SPLIT_LEAN true
 #endif
 #ifndef AT2_SPLIT_SMOOTH
-#define AT2_SPLIT_SMOOTH false
+#define AT2_SPLIT_SMOOTH true
 #endif
 #ifndef AT2_HB_MAX_WARPS
 #define AT2_HB_MAX_WARPS 24

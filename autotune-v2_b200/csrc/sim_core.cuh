@@ -281,10 +281,9 @@ __device__ __forceinline__ float step_folded(float f, float g, float fn, float u
 // acceptance test - so the attempt is branch-free and needs no bounds check.  Checkpoints are flagged in the records
 // themselves (sign bit of w, set by at2_hb_tables_build for the plan's checkpoint positions): an accepted attempt at a
 // flagged step stores the new loss through the lane's row pointer and moves that pointer one row down - two predicated
-// instructions, no branch.  Every active lane needs at least R - 1 attempts, so the first (R - 1) / 8 superblocks (three
-// Philox blocks, eight attempts each) run with no vote and no divergence - one large basic block in which the integer
-// Philox rounds of the next blocks overlap the MUFU/FP32 chains of the attempts; only the tail, where lanes finish one after
-// the other, tests for completion.
+// instructions, no branch.  Every active lane needs at least R - 1 attempts, so the first (R - 1) / 4 trips (one Philox
+// block, four attempts each) run with no vote and no divergence - the integer Philox rounds of the next block overlap the
+// MUFU/FP32 chains of the attempts; only the tail, where lanes finish one after the other, tests for completion.
 //
 // PARTIAL = true (early-stopping evaluation): every lane has its own stop_t and stops advancing there, and only checkpoint
 // `only_c` is produced, into ck[0] (instantiate with CK = 1: a smoothed arm then accumulates that one Savitzky-Golay
@@ -395,37 +394,41 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
     if (!PARTIAL || unfinished()) {
         // every unfinished lane needs at least this many more attempts
         const unsigned need = __reduce_min_sync(0xffffffffu, active ? (unsigned)(stop_t - 1) : 0xffffffffu);
-        const int n_main = need == 0xffffffffu ? 0 : (int)(need >> 3);
+        // counted trips: eight attempts each in a partial run, four in a full one
+        const int n_main = need == 0xffffffffu ? 0 : (int)(need >> (PARTIAL ? 3 : 2));
         uint32_t ctr = 0;
         At2U4 A = block(0), B;
-        // ONE loop instance serves the counted superblocks and the tail (the completion vote only runs once the counted
-        // part is over): the kernels that carry a lean and a smoothed trajectory loop were instruction-fetch bound with a
-        // separate tail loop each (ncu, six families: no_instruction 1.1 cycles per instruction; merged: 3.13 -> 2.89 ms).
-        // Full runs test for completion every eight attempts (a mid-body test costs more in scheduling freedom than the
-        // ~2 attempts per pass it saves: measured +1.5 %); partial runs - often only a few steps long - every four.
-        // run(cap_tag, n_counted, until): superblocks while fewer than n_counted have run or some lane is below `until`
+        // ONE loop instance serves the counted trips and the tail (the completion vote only runs once the counted part is
+        // over): the kernels that carry a lean and a smoothed trajectory loop were instruction-fetch bound with a separate
+        // tail loop each (ncu, six families: no_instruction 1.1 cycles per instruction; merged: 3.13 -> 2.89 ms).
+        // A full run's trip is ONE Philox block = four attempts, with the next block's integer rounds issued ahead of them
+        // (they overlap the attempts' MUFU chains): half the code of an eight-attempt trip - which is what lets every loop
+        // variant carry its capture-free copy - and a tail that overshoots the slowest lane by two attempts on average
+        // instead of four (measured against the eight-attempt trip: -1.7 % flat, -2 % with smoothed families).
+        // A partial run - often only a few steps long - generates its blocks only once it knows it needs them.
+        // run(cap_tag, n_counted, until): trips while fewer than n_counted have run or some lane is below `until`
         int it = 0;
         auto run = [&](auto cap_tag, int n_counted, uint32_t until) {
 #pragma unroll 1
             for (;; ++it) {
                 if (it >= n_counted && !__any_sync(0xffffffffu, addr < until)) break;
-                At2U4 An;
                 if constexpr (PARTIAL) {
                     pair(A.x, A.y, cap_tag);
                     pair(A.z, A.w, cap_tag);
                     if (it >= n_counted && !__any_sync(0xffffffffu, addr < until)) break;
                     B = block(ctr + 1);
-                    An = block(ctr + 2);
+                    const At2U4 An = block(ctr + 2);
+                    ctr += 2;
+                    pair(B.x, B.y, cap_tag);
+                    pair(B.z, B.w, cap_tag);
+                    A = An;
                 } else {
-                    B = block(ctr + 1);
-                    An = block(ctr + 2);      // the next superblock's first block: its integer rounds overlap this one's MUFU chains
+                    const At2U4 An = block(ctr + 1);
+                    ctr += 1;
                     pair(A.x, A.y, cap_tag);
                     pair(A.z, A.w, cap_tag);
+                    A = An;
                 }
-                ctr += 2;
-                pair(B.x, B.y, cap_tag);
-                pair(B.z, B.w, cap_tag);
-                A = An;
             }
         };
         if constexpr (PARTIAL) {
@@ -433,11 +436,11 @@ __device__ __forceinline__ void philox_trajectory(const SimTables& tb, bool acti
         } else if constexpr (!SPLIT) {
             run(std::true_type{}, n_main, end_addr);
         } else {
-            // capturing superblocks until every lane stands at or beyond step lean_from (inactive lanes sit on the sentinel,
+            // capturing trips until every lane stands at or beyond step lean_from (inactive lanes sit on the sentinel,
             // beyond any step), then the capture-free copy to the end; the end value is the last checkpoint
             const bool split = tb.lean_from < R;
             const uint32_t lean_addr = rec_base + (uint32_t)(split ? tb.lean_from : R) * (AT2_REC * 4u);
-            run(std::true_type{}, split ? ((tb.lean_from - 1) >> 3) : n_main, split ? lean_addr : end_addr);
+            run(std::true_type{}, split ? ((tb.lean_from - 1) >> 2) : n_main, split ? lean_addr : end_addr);
             if (split) {
                 run(std::false_type{}, n_main, end_addr);
                 // to the last row by its own address, not through ckp: on a short plan a lane may already have captured the
