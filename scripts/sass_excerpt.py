@@ -18,21 +18,21 @@ for line in sass.splitlines():
     m = re.match(r'\s+/\*([0-9a-f]{4,5})\*/\s+(.*?);\s*/\*', line)
     if m:
         ins.append((int(m.group(1), 16), m.group(2).strip()))
-# the two innermost big loops: backward branches spanning 300-450 instructions
+# the two innermost trajectory loops: backward branches spanning 120-260 instructions
 loops = []
 for a, t in ins:
     m = re.search(r'\bBRA(?:\.U)?\s+(?:!?U?P\d,\s*)?0x([0-9a-f]+)', t)
-    if m and 300 <= (a - int(m.group(1), 16)) // 16 + 1 <= 450:
+    if m and 120 <= (a - int(m.group(1), 16)) // 16 + 1 <= 260:
         loops.append((int(m.group(1), 16), a))
 out = [f'SASS of the trajectory loops of {sym}',
-       '(cuobjdump -sass of autotune-v2_b200/lib/libat2_b200.so, sm_100a; scripts/sass_excerpt.py).  One iteration = one',
-       'superblock = three Philox4x32-10 blocks -> four Box-Muller pairs -> eight Marsaglia-Tsang attempts + recurrence steps',
-       '(csrc/sim_core.cuh philox_trajectory).  Loop 1 captures checkpoints (predicated STS + row-pointer bump); loop 2 is the',
-       'capture-free copy that runs after the second-to-last checkpoint.', '']
+       '(cuobjdump -sass of autotune-v2_b200/lib/libat2_b200.so, sm_100a; scripts/sass_excerpt.py).  One trip = one',
+       'Philox4x32-10 block (the NEXT trip\'s, issued ahead) + two Box-Muller pairs -> four Marsaglia-Tsang attempts + recurrence',
+       'steps (csrc/sim_core.cuh philox_trajectory).  Loop 1 captures checkpoints (predicated STS + row-pointer bump); loop 2 is',
+       'the capture-free copy that runs after the second-to-last checkpoint.', '']
 for k, (lo, hi) in enumerate(loops[:2]):
     body = [(a, t) for a, t in ins if lo <= a <= hi]
     hist = collections.Counter(re.sub(r'^@!?U?P\d+\s+', '', t).split()[0].split('.')[0] for _, t in body)
-    out.append(f'== loop {k + 1}: 0x{lo:04x}..0x{hi:04x}, {len(body)} instructions per 8 attempts = {len(body) / 8:.1f} per attempt')
+    out.append(f'== loop {k + 1}: 0x{lo:04x}..0x{hi:04x}, {len(body)} instructions per 4 attempts = {len(body) / 4:.1f} per attempt')
     out.append('   ' + ', '.join(f'{op} {n}' for op, n in hist.most_common()))
     pipes = {'fma (FFMA FMUL FADD IMAD)': sum(hist[o] for o in ('FFMA', 'FMUL', 'FADD', 'IMAD')),
              'alu (LOP3 I2FP PRMT FSETP FSEL SEL VIADD ISETP IADD3 SHF)': sum(hist[o] for o in ('LOP3', 'I2FP', 'PRMT', 'FSETP', 'FSEL', 'SEL', 'VIADD', 'ISETP', 'IADD3', 'SHF')),
