@@ -374,6 +374,10 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F /* record blocks *
     const size_t per_warp_budget = 9 * 1024;
     int best_tw = 1, best_g = 1;
     double best_score = -1.0;
+    int km_a = 1, km_b = 1;
+    halving_id_buffer_sizes(plan, &km_a, &km_b);
+    // can one warp hold a whole repetition at all?  (R = 243: 369 arms x 6 checkpoints do not fit the per-warp budget)
+    const bool solo_fits = (size_t)C * ((A + 31) & ~31) * sizeof(T) + sort_per_warp <= per_warp_budget;
     for (int tw = 1; tw <= 8; tw *= 2) {
         for (int g = 1; g <= 64; ++g) {
             const int items = g * A;
@@ -386,7 +390,15 @@ int choose_launch(const at2_plan* plan, int has_smooth, int F /* record blocks *
             if (team_bytes > per_warp_budget * tw && !(tw == 8 && g == 1)) continue;
             // halving wants at least one repetition per warp of the team
             const double sh_balance = (double)g / ((double)((g + tw - 1) / tw) * tw);
-            const double score = packing * (0.9 + 0.1 * sh_balance) - 0.002 * tw;
+            // a team of several warps gives up the dynamic tile schedule, the tile-wide halving and the barrier-free
+            // trajectory phase: where one warp can hold a repetition, a team is worth it only for a clear packing gain
+            // (R = 27: team of 2 x 16 repetitions 0.89 ms, one warp x 7 repetitions 0.75 ms); where it cannot, the team
+            // shapes compete among themselves as before (R = 243: 4 warps x 3 repetitions)
+            double score = packing * (0.9 + 0.1 * sh_balance) - (solo_fits ? 0.03 * (tw - 1) : 0.002 * tw);
+            // warp-private float tiles halve their repetitions together only while the tile's survivor lists fit the sort
+            // scratch (fill_params: tile_halving); one repetition more than that falls back to per-repetition halving,
+            // which costs more than a slightly emptier last warp pass (measured on R = 27: 8 repetitions 0.89 ms, 7: 0.75)
+            if (sizeof(T) == 4 && tw == 1 && (size_t)(((g * (km_a + km_b) + 1) & ~1) * 2 + g * 12) > (size_t)npad * 4) score *= 0.85;
             if (score > best_score + 1e-9) best_score = score, best_tw = tw, best_g = g;
         }
     }
